@@ -1,0 +1,81 @@
+"""ctypes binding of the C ABI in include/unet_b200.h (libunet_b200.so).
+
+The library is the product path: there is no CPU or PyTorch fallback.  Importing this
+module on a box without the built library raises; calling a compute entry point without
+a CUDA device raises RuntimeError (the library returns UB_E_DRIVER / a cudaError_t).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libunet_b200.so")
+
+
+class Tensor4(C.Structure):
+    """ub_tensor4: NHWC bf16 view, strides in elements (include/unet_b200.h)."""
+
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+        ("sn", C.c_longlong), ("sy", C.c_longlong), ("sx", C.c_longlong),
+    ]
+
+
+_P = C.c_void_p
+_T4 = C.POINTER(Tensor4)
+_i, _ll, _f = C.c_int, C.c_longlong, C.c_float
+
+# name -> (restype, argtypes); mirrors include/unet_b200.h one to one
+SIGNATURES = {
+    "ub_version": (_i, []),
+    "ub_error_string": (C.c_char_p, [_i]),
+    "ub_device_error": (_i, [C.POINTER(C.c_uint)]),
+    "ub_set_tuning": (None, [_i, _i, _i, _i]),
+    "ub_pack_weight": (_i, [_P, _P, _i, _i, _i, _P]),
+    "ub_unpack_grad": (_i, [_P, _P, _i, _i, _i, _i, _P]),
+    "ub_conv3x3_fwd": (_i, [_T4, _P, _P, _T4, _i, _P]),
+    "ub_conv3x3_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
+    "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),
+    "ub_upconv2x2_fwd": (_i, [_T4, _P, _P, _T4, _P]),
+    "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
+    "ub_upconv2x2_wgrad": (_i, [_T4, _T4, _P, _P]),
+    "ub_conv1_fwd": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_conv1_wgrad": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_pool2x2_fwd": (_i, [_P, _P, _P, _T4, _i, _i, _i, _i, _i, _P]),
+    "ub_pool2x2_bwd": (_i, [_P, _T4, _i, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "ub_head_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_head_bwd": (_i, [_P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_loss_workspace_bytes": (_ll, []),
+    "ub_loss_fwd_bwd": (_i, [_i, _P, _P, _i, _P, _P, _P, _P, _i, _i, _i, _i, _f, _P]),
+    "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),
+    "ub_sgd_momentum": (_i, [_P, _P, _P, _ll, _f, _f, _i, _P]),
+    "ub_naive_conv3x3": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
+    "ub_probe_run": (_i, [_i, C.POINTER(C.c_float), _i]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libunet_b200.so (once) and attach the prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no fallback path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code, what=""):
+    """Turn a non-zero library return code into RuntimeError (the reference's error convention
+    for this path is Python exceptions, e.g. torch.cat's RuntimeError on odd sizes)."""
+    if code != 0:
+        msg = load().ub_error_string(int(code)).decode()
+        raise RuntimeError(f"unet_b200 {what}: error {code}: {msg}")

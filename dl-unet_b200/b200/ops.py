@@ -1,0 +1,207 @@
+"""Tensor-level wrappers over the C ABI: each function takes torch CUDA tensors, builds the
+ub_tensor4 views and launches on torch's current stream.  Activations are NHWC bf16 tensors of
+shape [N, H, W, C] (possibly strided views with channel stride 1).  No function here computes
+anything in PyTorch -- torch is used for device memory and streams only."""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .lib import Tensor4, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("unet_b200 ops need CUDA tensors: there is no CPU path")
+
+
+def t4(t):
+    """[N,H,W,C] bf16 view -> ub_tensor4."""
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.stride(3) != 1:
+        raise RuntimeError(f"expected an NHWC bf16 view with unit channel stride, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    n, h, w, c = t.shape
+    sn = t.stride(0) if n > 1 else max(t.stride(0), h * t.stride(1))
+    return Tensor4(t.data_ptr(), n, h, w, c, sn, t.stride(1), t.stride(2))
+
+
+def _t4p(t):
+    return C.byref(t4(t)) if t is not None else None
+
+
+def set_tuning(bn=0, bw=0, bh=0, splits=0):
+    _lib.load().ub_set_tuning(bn, bw, bh, splits)
+
+
+def device_error():
+    code = C.c_uint(0)
+    rc = _lib.load().ub_device_error(C.byref(code))
+    return rc, code.value
+
+
+# ---------------------------------------------------------------- weights
+PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_UP_FWD, PACK_UP_DGRAD = 0, 1, 2, 3
+
+
+def pack_weight(w, mode, out=None):
+    """fp32 master in torch layout -> bf16 K-major GEMM operand (see ub_pack_weight)."""
+    _need_cuda(w)
+    w = w.detach()
+    if not w.is_contiguous() or w.dtype != torch.float32:
+        raise RuntimeError("pack_weight expects a contiguous fp32 weight")
+    if mode in (PACK_CONV_FWD, PACK_CONV_DGRAD):
+        cout, cin = w.shape[0], w.shape[1]
+        shape = (cout, 9 * cin) if mode == PACK_CONV_FWD else (cin, 9 * cout)
+    else:
+        cin, cout = w.shape[0], w.shape[1]
+        shape = (4 * cout, cin) if mode == PACK_UP_FWD else (cin, 4 * cout)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().ub_pack_weight(_ptr(w), _ptr(out), mode, cout, cin, _stream()), "pack_weight")
+    return out
+
+
+def unpack_grad(packed, dw, mode, accumulate=False):
+    if mode == PACK_CONV_FWD:
+        cout, cin = dw.shape[0], dw.shape[1]
+    else:
+        cin, cout = dw.shape[0], dw.shape[1]
+    check(_lib.load().ub_unpack_grad(_ptr(packed), _ptr(dw), mode, cout, cin, int(accumulate), _stream()), "unpack_grad")
+    return dw
+
+
+# ---------------------------------------------------------------- tensor-pipe ops
+def conv3x3_fwd(x, w_fwd, bias, y, relu=True):
+    _need_cuda(x, w_fwd, y)
+    check(_lib.load().ub_conv3x3_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), int(relu), _stream()), "conv3x3_fwd")
+    return y
+
+
+def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None):
+    _need_cuda(dy, w_dgrad, dx)
+    check(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
+    return dx
+
+
+def conv3x3_wgrad(x, dy, dw_packed):
+    _need_cuda(x, dy, dw_packed)
+    check(_lib.load().ub_conv3x3_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "conv3x3_wgrad")
+    return dw_packed
+
+
+def upconv2x2_fwd(x, w_fwd, bias, y):
+    _need_cuda(x, w_fwd, y)
+    check(_lib.load().ub_upconv2x2_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _stream()), "upconv2x2_fwd")
+    return y
+
+
+def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None):
+    _need_cuda(dy, w_dgrad, dx)
+    check(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
+    return dx
+
+
+def upconv2x2_wgrad(x, dy, dw_packed):
+    _need_cuda(x, dy, dw_packed)
+    check(_lib.load().ub_upconv2x2_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "upconv2x2_wgrad")
+    return dw_packed
+
+
+# ---------------------------------------------------------------- HBM-bound ops
+def conv1_fwd(image, w, bias, y):
+    """image fp32 [N,1,H,W] -> y bf16 [N,H-2,W-2,64], bias + ReLU fused (network.py:131)."""
+    _need_cuda(image, w, bias, y)
+    n, _, h, wd = image.shape
+    check(_lib.load().ub_conv1_fwd(_ptr(image), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, _stream()), "conv1_fwd")
+    return y
+
+
+def conv1_wgrad(image, dy, dw, db):
+    n, _, h, wd = image.shape
+    check(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
+
+
+def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
+    _need_cuda(x, y, idx)
+    n, h, w, c = x.shape
+    check(_lib.load().ub_pool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), _t4p(cat), int(c_off), n, h, w, c, _stream()), "pool2x2_fwd")
+    return y, idx
+
+
+def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx):
+    n, h, w, c = dx.shape
+    check(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), n, h, w, c,
+                                     _stream()), "pool2x2_bwd")
+    return dx
+
+
+def head_fwd(x, w, bias, logits=None, argmax=None):
+    n, h, wd, _ = x.shape
+    check(_lib.load().ub_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(logits), _ptr(argmax), n, h, wd, _stream()), "head_fwd")
+
+
+def head_bwd(x, w, dlogits, dx, dw, db):
+    n, h, wd, _ = x.shape
+    check(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), n, h, wd, _stream()),
+          "head_bwd")
+
+
+LOSS_BCE, LOSS_SOFTMAX_CE = 0, 1
+
+
+def loss_workspace(device):
+    nbytes = _lib.load().ub_loss_workspace_bytes()
+    return torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+
+
+def loss_fwd_bwd(kind, logits, label, weight, dlogits, loss_out, workspace, grad_scale):
+    """logits fp32 [B,2,Hp,Wp]; label [B,L,L] uint8|int64; weight [B,L,L] fp32 (trainer.py:60-75)."""
+    _need_cuda(logits, label, weight, loss_out, workspace)
+    b, _, hp, wp = logits.shape
+    l = label.shape[-1]
+    lb = {torch.uint8: 1, torch.int64: 8}[label.dtype]
+    check(_lib.load().ub_loss_fwd_bwd(kind, _ptr(logits), _ptr(label), lb, _ptr(weight), _ptr(dlogits), _ptr(loss_out),
+                                      _ptr(workspace), b, hp, wp, l, float(grad_scale), _stream()), "loss_fwd_bwd")
+
+
+def colsum(g, out):
+    """out[c] += sum over pixels of the bf16 NHWC view g (dense in n,y,x up to the pixel stride)."""
+    n, h, w, c = g.shape
+    ld = g.stride(2)
+    if g.stride(1) != w * ld or (n > 1 and g.stride(0) != h * w * ld):
+        raise RuntimeError("colsum needs a view that is dense over pixels")
+    check(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
+
+
+def sgd_momentum(p, g, buf, lr, momentum, first_step):
+    check(_lib.load().ub_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum),
+                                      int(first_step), _stream()), "sgd_momentum")
+
+
+def naive_conv3x3(x, w_fwd, bias, relu):
+    n, h, w, cin = x.shape
+    cout = w_fwd.shape[0]
+    y = torch.empty((n, h - 2, w - 2, cout), dtype=torch.float32, device=x.device)
+    check(_lib.load().ub_naive_conv3x3(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), n, h, w, cin, cout, int(relu),
+                                       _stream()), "naive_conv3x3")
+    return y
+
+
+def probe_run(cap_rows=128):
+    buf = (C.c_float * (cap_rows * 6))(*([-1.0] * (cap_rows * 6)))
+    check(_lib.load().ub_probe_run(0, buf, cap_rows * 6), "probe")
+    rows = []
+    for i in range(cap_rows):
+        r = list(buf[i * 6:(i + 1) * 6])
+        if r[0] < 0:
+            break
+        rows.append(r)
+    return rows

@@ -1,0 +1,620 @@
+// HBM-bound kernels of the U-Net path: first conv (Cin = 1), 2x2 max-pool with
+// argmax codes (+ the skip copy into the decoder's concat buffer), the 64->2 head,
+// the pixel-wise weighted losses, bias-gradient column sums, weight (un)packing and
+// the fused SGD-momentum step.  All use 128-bit accesses on NHWC bf16 tensors:
+// a thread owns 8 consecutive channels (16 B) of one pixel, so a warp touches
+// 512 contiguous bytes.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// conv11c: 1 -> 64 channels, 3x3 valid, fp32 image in, bf16 NHWC out, fused
+// bias + ReLU (network.py:131).  K = 9 cannot feed the tensor pipe; the kernel
+// is bound by its 2 B x 64 x pixels output write.
+// grid.x covers pixels*8 threads; thread = (pixel, channel octet).
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                                                        int n_img, int H, int W) {
+  __shared__ float sw[64 * 9 + 64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sw[576 + i] = b[i];
+  __syncthreads();
+  const int Ho = H - 2, Wo = W - 2;
+  const long long total = (long long)n_img * Ho * Wo * 8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int oct = (int)(gid & 7);
+    long long pix = gid >> 3;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const float* xp = x + ((long long)n * H + oy) * W + ox;
+    float in[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) in[r * 3 + s] = __ldg(xp + r * W + s);
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float* wc = sw + (oct * 8 + c) * 9;
+      float a = sw[576 + oct * 8 + c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(in[t], wc[t], a);
+      o[c] = fmaxf(a, 0.0f);
+    }
+    *reinterpret_cast<uint4*>(y + (gid >> 3) * 64 + oct * 8) = pack8(o);
+  }
+}
+
+// conv11c weight + bias gradient: dW[co, tap] = sum_p dY[p, co] * x[p + tap], db[co] = sum_p dY[p, co].
+// dY is bf16 NHWC (already ReLU-masked).  One thread = (pixel, channel octet); block-level
+// reduction in shared memory, then one atomicAdd per (co, tap) per block.
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x,
+                                                          const __nv_bfloat16* __restrict__ dy,
+                                                          float* __restrict__ dw, float* __restrict__ db, int n_img,
+                                                          int H, int W) {
+  const int Ho = H - 2, Wo = W - 2;
+  const long long total = (long long)n_img * Ho * Wo * 8;
+  float acc[8][10];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[c][t] = 0.0f;
+  const int oct = threadIdx.x & 7;  // blockDim.x multiple of 8 and stride multiple of 8 keeps oct fixed
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    long long pix = gid >> 3;
+    const int ox = (int)(pix % Wo);
+    long long r2 = pix / Wo;
+    const int oy = (int)(r2 % Ho);
+    const int n = (int)(r2 / Ho);
+    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(dy + pix * 64 + oct * 8));
+    float g[8];
+    unpack8(g4, g);
+    const float* xp = x + ((long long)n * H + oy) * W + ox;
+    float in[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) in[r * 3 + s] = __ldg(xp + r * W + s);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+      acc[c][9] += g[c];
+    }
+  }
+  // reduce over the 32 threads of the block that share `oct` within each warp (lanes with equal lane&7)
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+      float v = acc[c][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[c][t] = v;
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // lanes 0..7 hold the warp sums for octets 0..7
+  __shared__ float sred[8][64][10];  // [warp][channel][tap]
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int t = 0; t < 10; ++t) sred[warp][lane * 8 + c][t] = acc[c][t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 10; i += blockDim.x) {
+    const int ch = i / 10, t = i % 10;
+    float v = 0.0f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sred[wv][ch][t];
+    if (t < 9)
+      atomicAdd(dw + ch * 9 + t, v);
+    else
+      atomicAdd(db + ch, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 2x2 stride-2 max pool (network.py:133,139,145,151) on bf16 NHWC.
+// Writes: dense pooled tensor, 1-byte argmax code (dy*2+dx, first maximum in
+// row-major window order, NaN wins -- the ATen rule), and the same value into the
+// decoder's concat buffer at the crop_and_concat offset (network.py:124-127):
+// concat coordinate = pooled coordinate - c, c = int((Hp - Hu) * 0.5).
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+                                                       __nv_bfloat16* __restrict__ cat, int n_img, int H, int W, int C,
+                                                       int cat_H, int cat_W, int cat_C, int c_off) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long long total = (long long)n_img * Ho * Wo * C8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(gid % C8);
+    long long pix = gid / C8;
+    const int ox = (int)(pix % Wo);
+    long long r2 = pix / Wo;
+    const int oy = (int)(r2 % Ho);
+    const int n = (int)(r2 / Ho);
+    const __nv_bfloat16* xp = x + (((long long)n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
+    float v[4][8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xp)), v[0]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xp + C)), v[1]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xp + (long long)W * C)), v[2]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xp + (long long)W * C + C)), v[3]);
+    float m[8];
+    uint32_t code[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      m[c] = v[0][c];
+      code[c] = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const float t = v[k][c];
+        if (t > m[c] || t != t) {
+          m[c] = t;
+          code[c] = k;
+        }
+      }
+    }
+    const uint4 o = pack8(m);
+    *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = o;
+    uint2 cc;
+    cc.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+    cc.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+    *reinterpret_cast<uint2*>(idx + pix * C + c8 * 8) = cc;
+    if (cat != nullptr) {
+      const int cy = oy - c_off, cx = ox - c_off;
+      if (cy >= 0 && cy < cat_H && cx >= 0 && cx < cat_W)
+        *reinterpret_cast<uint4*>(cat + (((long long)n * cat_H + cy) * cat_W + cx) * cat_C + c8 * 8) = o;
+    }
+  }
+}
+
+// Max-pool backward fused with (a) the sum of the two gradient producers of the pooled
+// tensor -- the next encoder conv's dgrad (dense) and the skip half of the concat
+// gradient (window of dcat at the crop_and_concat offset) -- and (b) the ReLU backward of
+// the conv that fed the pool (gradient passes only where the pooled value > 0).
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ dcat,
+                                                       const uint8_t* __restrict__ idx,
+                                                       const __nv_bfloat16* __restrict__ pooled,
+                                                       __nv_bfloat16* __restrict__ dx, int n_img, int H, int W, int C,
+                                                       int cat_H, int cat_W, int cat_C, int c_off) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long long total = (long long)n_img * Ho * Wo * C8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(gid % C8);
+    long long pix = gid / C8;
+    const int ox = (int)(pix % Wo);
+    long long r2 = pix / Wo;
+    const int oy = (int)(r2 % Ho);
+    const int n = (int)(r2 / Ho);
+    float g[8], pv[8];
+    if (dy != nullptr) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + pix * C + c8 * 8)), g);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] = 0.0f;
+    }
+    if (dcat != nullptr) {
+      const int cy = oy - c_off, cx = ox - c_off;
+      if (cy >= 0 && cy < cat_H && cx >= 0 && cx < cat_W) {
+        float g2[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dcat + (((long long)n * cat_H + cy) * cat_W + cx) * cat_C + c8 * 8)),
+                g2);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) g[c] += g2[c];
+      }
+    }
+    unpack8(__ldg(reinterpret_cast<const uint4*>(pooled + pix * C + c8 * 8)), pv);
+    const uint2 cc = __ldg(reinterpret_cast<const uint2*>(idx + pix * C + c8 * 8));
+    float o[4][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t code = ((c < 4 ? cc.x : cc.y) >> ((c & 3) * 8)) & 0xff;
+      const float gv = pv[c] > 0.0f ? g[c] : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][c] = (code == (uint32_t)k) ? gv : 0.0f;
+    }
+    __nv_bfloat16* xp = dx + (((long long)n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(xp) = pack8(o[0]);
+    *reinterpret_cast<uint4*>(xp + C) = pack8(o[1]);
+    *reinterpret_cast<uint4*>(xp + (long long)W * C) = pack8(o[2]);
+    *reinterpret_cast<uint4*>(xp + (long long)W * C + C) = pack8(o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// finalconv: 1x1, 64 -> 2 (network.py:190).  bf16 NHWC in, fp32 NCHW logits out,
+// optional fused 2-class argmax (tester.py:30, trainer.py:82: ties -> class 0).
+// 8 threads per pixel, each 8 channels, shuffle-reduced.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ logits, uint8_t* __restrict__ amax,
+                                                       long long n_pix_per_img, int n_img) {
+  const int oct = threadIdx.x & 7;
+  float w0[8], w1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    w0[c] = __ldg(w + oct * 8 + c);
+    w1[c] = __ldg(w + 64 + oct * 8 + c);
+  }
+  const float b0 = __ldg(b), b1 = __ldg(b + 1);
+  const long long total = n_pix_per_img * n_img * 8;
+  const long long total_r = (total + 31) & ~31ll;  // keep whole warps in the loop for the shuffles
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total_r;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gid >> 3;
+    float s0 = 0.0f, s1 = 0.0f;
+    if (gid < total) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * 64 + oct * 8)), v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        s0 = fmaf(v[c], w0[c], s0);
+        s1 = fmaf(v[c], w1[c], s1);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (gid < total && oct == 0) {
+      s0 += b0;
+      s1 += b1;
+      const long long n = pix / n_pix_per_img, r = pix - n * n_pix_per_img;
+      if (logits != nullptr) {
+        logits[(n * 2) * n_pix_per_img + r] = s0;
+        logits[(n * 2 + 1) * n_pix_per_img + r] = s1;
+      }
+      if (amax != nullptr) amax[pix] = (s1 > s0) ? 1 : 0;
+    }
+  }
+}
+
+// Head backward: dX[p, c] = (dl0[p] W0[c] + dl1[p] W1[c]) * (X[p, c] > 0)  (ReLU of conv12e),
+// dW[k, c] = sum_p dl_k[p] X[p, c], db[k] = sum_p dl_k[p].
+__global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const float* __restrict__ w,
+                                                       const float* __restrict__ dlogits,
+                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+                                                       float* __restrict__ db, long long n_pix_per_img, int n_img) {
+  const int oct = threadIdx.x & 7;
+  float w0[8], w1[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    w0[c] = __ldg(w + oct * 8 + c);
+    w1[c] = __ldg(w + 64 + oct * 8 + c);
+  }
+  float a0[8], a1[8], sb0 = 0.0f, sb1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a0[c] = a1[c] = 0.0f;
+  const long long total = n_pix_per_img * n_img * 8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gid >> 3;
+    const long long n = pix / n_pix_per_img, r = pix - n * n_pix_per_img;
+    const float d0 = __ldg(dlogits + (n * 2) * n_pix_per_img + r);
+    const float d1 = __ldg(dlogits + (n * 2 + 1) * n_pix_per_img + r);
+    float v[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * 64 + oct * 8)), v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      o[c] = v[c] > 0.0f ? fmaf(d0, w0[c], d1 * w1[c]) : 0.0f;
+      a0[c] = fmaf(d0, v[c], a0[c]);
+      a1[c] = fmaf(d1, v[c], a1[c]);
+    }
+    if (oct == 0) {
+      sb0 += d0;
+      sb1 += d1;
+    }
+    *reinterpret_cast<uint4*>(dx + pix * 64 + oct * 8) = pack8(o);
+  }
+  // reduce lanes with equal oct (xor 8, 16), then across warps through smem
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    a0[c] += __shfl_xor_sync(0xffffffffu, a0[c], 8);
+    a0[c] += __shfl_xor_sync(0xffffffffu, a0[c], 16);
+    a1[c] += __shfl_xor_sync(0xffffffffu, a1[c], 8);
+    a1[c] += __shfl_xor_sync(0xffffffffu, a1[c], 16);
+  }
+  sb0 = warp_sum(sb0);
+  sb1 = warp_sum(sb1);
+  __shared__ float sred[8][130];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sred[warp][lane * 8 + c] = a0[c];
+      sred[warp][64 + lane * 8 + c] = a1[c];
+    }
+  }
+  if (lane == 0) {
+    sred[warp][128] = sb0;
+    sred[warp][129] = sb1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) {
+    float v = 0.0f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sred[wv][i];
+    if (i < 128)
+      atomicAdd(dw + i, v);
+    else
+      atomicAdd(db + (i - 128), v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Pixel-wise weighted losses on 2-channel fp32 logits [B,2,Hp,Wp] (centre-cropped
+// to the label size: trainer.py:60-61), label [B,L,L] (uint8 or int64), weight
+// [B,L,L] fp32.  kind 0: BCE-with-logits on the one-hot target, mean over B*2*L*L
+// (trainer.py:63-75, nn.BCEWithLogitsLoss(weight)); kind 1: weighted softmax
+// cross-entropy, mean over B*L*L (BASELINE config 5).  Fused forward + dlogits.
+// Deterministic reduction: per-block partials, last block sums them in order.
+template <typename LabelT>
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ logits, const LabelT* __restrict__ label,
+                                                   const float* __restrict__ weight, float* __restrict__ dlogits,
+                                                   float* __restrict__ loss_out, float* __restrict__ partials,
+                                                   unsigned int* __restrict__ counter, int B, int Hp, int Wp, int L,
+                                                   int pad, int kind, float grad_scale) {
+  const long long total = (long long)B * L * L;
+  const long long plane = (long long)Hp * Wp;
+  float acc = 0.0f;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(gid % L);
+    long long r = gid / L;
+    const int yy = (int)(r % L);
+    const int n = (int)(r / L);
+    const long long off = (long long)(yy + pad) * Wp + (xx + pad);
+    const float z0 = __ldg(logits + (n * 2ll) * plane + off);
+    const float z1 = __ldg(logits + (n * 2ll + 1) * plane + off);
+    const float wv = __ldg(weight + gid);
+    const int lab = (int)label[gid];
+    float g0, g1;
+    if (kind == 0) {
+      // softplus(z) - y z, stable: max(z,0) - y z + log1p(exp(-|z|))
+      const float y0 = lab ? 0.0f : 1.0f, y1 = lab ? 1.0f : 0.0f;
+      const float l0 = fmaxf(z0, 0.0f) - y0 * z0 + log1pf(expf(-fabsf(z0)));
+      const float l1 = fmaxf(z1, 0.0f) - y1 * z1 + log1pf(expf(-fabsf(z1)));
+      acc += wv * (l0 + l1);
+      const float s0 = 1.0f / (1.0f + expf(-z0)), s1 = 1.0f / (1.0f + expf(-z1));
+      g0 = wv * (s0 - y0);
+      g1 = wv * (s1 - y1);
+    } else {
+      const float m = fmaxf(z0, z1);
+      const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+      const float s = e0 + e1;
+      const float lse = m + logf(s);
+      acc += wv * (lse - (lab ? z1 : z0));
+      const float p0 = e0 / s, p1 = e1 / s;
+      g0 = wv * (p0 - (lab ? 0.0f : 1.0f));
+      g1 = wv * (p1 - (lab ? 1.0f : 0.0f));
+    }
+    if (dlogits != nullptr) {
+      // dlogits has the logits' own (uncropped) shape; the cropped-away border stays zero
+      dlogits[(n * 2ll) * plane + off] = g0 * grad_scale;
+      dlogits[(n * 2ll + 1) * plane + off] = g1 * grad_scale;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sw[8];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sw[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += sw[i];
+    partials[blockIdx.x] = v;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-order tree over the partials: deterministic for a given grid size
+    float v = 0.0f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += partials[i];
+    v = warp_sum(v);
+    if (lane == 0) sw[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sw[i];
+      const float denom = (kind == 0) ? 2.0f * (float)total : (float)total;
+      *loss_out = t / denom;
+      *counter = 0;  // re-arm for the next launch (graph replays included)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Column sums of a bf16 [pixels, C] view (pixel stride `ld` elements): bias gradients.
+// blockDim = 256 = 32 pixel lanes x 8 ... generalised: thread = (pixel slot, channel octet).
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out,
+                                                     long long n_pix, int C, long long ld) {
+  const int C8 = C >> 3;
+  // threads are laid out [pixel_slot][c8] with c8 fastest; requires 256 % C8 == 0 or C8 % 256 == 0
+  const int tpb = blockDim.x;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+  if (C8 <= tpb) {
+    const int slots = tpb / C8;
+    const int c8 = threadIdx.x % C8, slot = threadIdx.x / C8;
+    for (long long pix = (long long)blockIdx.x * slots + slot; pix < n_pix; pix += (long long)gridDim.x * slots) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(g + pix * ld + c8 * 8)), v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += v[c];
+    }
+    __shared__ float sred[256][9];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sred[threadIdx.x][c] = acc[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += tpb) {
+      const int cc8 = i >> 3, c = i & 7;
+      float v = 0.0f;
+      for (int s = 0; s < slots; ++s) v += sred[s * C8 + cc8][c];
+      atomicAdd(out + i, v);
+    }
+  } else {
+    // C8 > 256 never happens for this network (C <= 1024 -> C8 <= 128)
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Weight packing: fp32 masters in torch layout -> bf16 K-major GEMM operands.
+//  mode 0 conv fwd   : dst[co][(r,s)][ci]            = W[co][ci][r][s]
+//  mode 1 conv dgrad : dst[ci][(r',s')][co]          = W[co][ci][2-r'][2-s']
+//  mode 2 upconv fwd : dst[(a,b,co)][ci]             = W[ci][co][a][b]
+//  mode 3 upconv dgrad: dst[ci][(a,b,co)]            = W[ci][co][a][b]
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                                                          int mode, int Cout, int Cin) {
+  const int T = (mode < 2) ? 9 : 4;
+  const long long total = (long long)Cout * Cin * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long src;
+    if (mode == 0) {
+      const int ci = (int)(i % Cin);
+      long long r = i / Cin;
+      const int t = (int)(r % 9);
+      const int co = (int)(r / 9);
+      src = ((long long)co * Cin + ci) * 9 + t;
+    } else if (mode == 1) {
+      const int co = (int)(i % Cout);
+      long long r = i / Cout;
+      const int t = (int)(r % 9);
+      const int ci = (int)(r / 9);
+      src = ((long long)co * Cin + ci) * 9 + (8 - t);
+    } else if (mode == 2) {
+      const int ci = (int)(i % Cin);
+      long long r = i / Cin;
+      const int co = (int)(r % Cout);
+      const int ab = (int)(r / Cout);
+      src = ((long long)ci * Cout + co) * 4 + ab;
+    } else {
+      const int co = (int)(i % Cout);
+      long long r = i / Cout;
+      const int ab = (int)(r % 4);
+      const int ci = (int)(r / 4);
+      src = ((long long)ci * Cout + co) * 4 + ab;
+    }
+    dst[i] = __float2bfloat16_rn(__ldg(w + src));
+  }
+}
+
+// Packed fp32 weight gradient (wgrad kernel layout) -> torch layout, scaled.
+//  mode 0 conv   : src[co][(r,s)][ci] -> dW[co][ci][r][s]
+//  mode 2 upconv : src[(a,b,co)][ci]  -> dW[ci][co][a][b]
+__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ src, float* __restrict__ dw,
+                                                          int mode, int Cout, int Cin, int accumulate) {
+  const int T = (mode == 0) ? 9 : 4;
+  const long long total = (long long)Cout * Cin * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long s;
+    if (mode == 0) {
+      const int t = (int)(i % 9);
+      long long r = i / 9;
+      const int ci = (int)(r % Cin);
+      const int co = (int)(r / Cin);
+      s = ((long long)co * 9 + t) * Cin + ci;
+    } else {
+      const int ab = (int)(i % 4);
+      long long r = i / 4;
+      const int co = (int)(r % Cout);
+      const int ci = (int)(r / Cout);
+      s = ((long long)ab * Cout + co) * Cin + ci;
+    }
+    const float v = __ldg(src + s);
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SGD with momentum over a flat fp32 arena (optim.SGD(lr, momentum), trainer.py:30,78):
+//   buf = g (first step) | momentum*buf + g ;  p -= lr*buf.  No dampening/nesterov/weight decay.
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ buf, long long n, float lr, float momentum,
+                                                  int first_step) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 bv;
+    if (first_step) {
+      bv = gv;
+    } else {
+      bv = reinterpret_cast<float4*>(buf)[i];
+      bv.x = fmaf(momentum, bv.x, gv.x); bv.y = fmaf(momentum, bv.y, gv.y);
+      bv.z = fmaf(momentum, bv.z, gv.z); bv.w = fmaf(momentum, bv.w, gv.w);
+    }
+    pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+    reinterpret_cast<float4*>(buf)[i] = bv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  // tail
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gv = g[i];
+    const float bv = first_step ? gv : fmaf(momentum, buf[i], gv);
+    buf[i] = bv;
+    p[i] -= lr * bv;
+  }
+}
+
+// Naive direct 3x3 valid conv on NHWC bf16 (fp32 accumulate): test-only comparator that
+// shares nothing with the tcgen05 path.  One thread per output element.
+__global__ void naive_conv3x3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wpk,
+                                     const float* __restrict__ bias, float* __restrict__ y, int n_img, int H, int W,
+                                     int Cin, int Cout, int relu) {
+  const int Ho = H - 2, Wo = W - 2;
+  const long long total = (long long)n_img * Ho * Wo * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long pix = i / Cout;
+    const int ox = (int)(pix % Wo);
+    long long r2 = pix / Wo;
+    const int oy = (int)(r2 % Ho);
+    const int n = (int)(r2 / Ho);
+    float a = bias ? bias[co] : 0.0f;
+    for (int t = 0; t < 9; ++t) {
+      const __nv_bfloat16* xp = x + (((long long)n * H + oy + t / 3) * W + ox + t % 3) * Cin;
+      const __nv_bfloat16* wp = wpk + ((long long)co * 9 + t) * Cin;
+      for (int c = 0; c < Cin; ++c) a = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), a);
+    }
+    y[i] = relu ? fmaxf(a, 0.0f) : a;
+  }
+}
+
+}  // namespace ub

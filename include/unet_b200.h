@@ -1,0 +1,126 @@
+/*
+ * unet_b200.h -- C ABI of the B200-native U-Net hot path.
+ *
+ * The reference (nsirons/DL-unet) has no FFI of its own: its operator layer is
+ * whatever ATen kernel `torch.nn` dispatches to.  Each entry point below replaces
+ * one of those dispatches; the reference call site it stands in for is cited per
+ * function (paths relative to the reference repo).  INTEGRATION.md shows the
+ * ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer unless stated otherwise; nothing is
+ *     allocated or freed by the library; `stream` is a cudaStream_t cast to void*.
+ *   - activations are NHWC bf16, described by ub_tensor4 (channel stride is 1;
+ *     n/y/x strides are in ELEMENTS, so channel-slices of a wider buffer and
+ *     windows of a larger image are expressible -- this is how the skip
+ *     connection is written in place).
+ *   - return value: 0 = ok, negative = UB_E_* (bad shape / alignment / no
+ *     driver), positive = cudaError_t of the failed launch.  No entry point
+ *     synchronises the device, exits the process or falls back to the CPU.
+ *   - all entry points are re-entrant and capturable into a CUDA graph.
+ */
+#ifndef UNET_B200_H_
+#define UNET_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_E_SHAPE (-1)     /* dimension not supported (e.g. channels not a multiple of 64) */
+#define UB_E_ALIGN (-2)     /* pointer / stride not 16-byte aligned */
+#define UB_E_DRIVER (-3)    /* cuTensorMapEncodeTiled unavailable (no CUDA driver) */
+#define UB_E_TENSORMAP (-4) /* the driver rejected a tensor map */
+#define UB_E_ARG (-5)       /* null pointer / bad enum */
+
+typedef struct ub_tensor4 {
+  void* ptr;             /* first element of the view */
+  int n, h, w, c;        /* extents of the view */
+  long long sn, sy, sx;  /* element strides of n, y (row), x (pixel); channel stride is 1 */
+} ub_tensor4;
+
+int ub_version(void);
+const char* ub_error_string(int code);
+/* Non-zero after a kernel aborted on a pipeline dead-lock guard; host memory out-param. Synchronises. */
+int ub_device_error(unsigned int* out_code);
+/* Tuning overrides for experiments: <=0 restores the heuristic. */
+void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
+
+/* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------
+ * mode 0: Conv2d [Cout,Cin,3,3]           -> forward operand  [Cout][9][Cin]   bf16
+ * mode 1: Conv2d [Cout,Cin,3,3]           -> dgrad operand    [Cin][9][Cout]   bf16 (taps rotated 180 deg)
+ * mode 2: ConvTranspose2d [Cin,Cout,2,2]  -> forward operand  [4*Cout][Cin]    bf16 (rows ordered a,b,co)
+ * mode 3: ConvTranspose2d [Cin,Cout,2,2]  -> dgrad operand    [Cin][4*Cout]    bf16                      */
+int ub_pack_weight(const float* w, void* dst_bf16, int mode, int cout, int cin, void* stream);
+/* inverse of modes 0 / 2 for the fp32 packed gradient the wgrad kernels produce */
+int ub_unpack_grad(const float* packed, float* dw, int mode, int cout, int cin, int accumulate, void* stream);
+
+/* ---- 3x3 valid convolution (nn.Conv2d(k=3) + F.relu; network.py:131-188) -------------
+ * y[n,oy,ox,co] = act(bias[co] + sum_{r,s,ci} x[n,oy+r,ox+s,ci] * W[co,ci,r,s]);  y is (h-2)x(w-2). */
+int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, int relu,
+                   void* stream);
+/* dx = full correlation of dy with the rotated weights; if relu_src != NULL the ReLU backward of the
+ * layer that produced x is fused: dx *= (relu_src > 0).  (autograd of network.py:131-188) */
+int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                     void* stream);
+/* dw_packed[co][tap][ci] += sum_pixels dy * x   (fp32, caller zeroes it; split-K atomics) */
+int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream);
+
+/* ---- 2x2 stride-2 up-convolution (nn.ConvTranspose2d(k=2,s=2); network.py:159,167,175,183) ----
+ * y[n,2i+a,2j+b,co] = bias[co] + sum_ci x[n,i,j,ci] * W[ci,co,a,b]; y is normally the upper channel
+ * half of the decoder's concat buffer (network.py:127), expressed through y->ptr / strides.          */
+int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, void* stream);
+int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                       void* stream);
+int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream);
+
+/* ---- first convolution, Cin = 1 (network.py:131), fp32 NCHW image in, bf16 NHWC out, bias+ReLU fused ---- */
+int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y_bf16, int n, int h, int w_,
+                 void* stream);
+/* dw[64*9] += , db[64] += (fp32, caller zeroes) */
+int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* dw, float* db, int n, int h, int w_, void* stream);
+
+/* ---- 2x2 max pool (F.max_pool2d(t,2,2); network.py:133,139,145,151) + skip write (network.py:108-127) ----
+ * x: dense [n,h,w,c] bf16.  y: dense [n,h/2,w/2,c].  idx: 1 byte per output element, code = dy*2+dx of the
+ * first maximum in row-major window order (ATen's tie rule; NaN wins).  If cat != NULL the pooled value
+ * is also written to cat[n, oy - c_off, ox - c_off, 0:c] where in range: c_off = int((Hpool - Hup)*0.5)
+ * is crop_and_concat's offset (negative = zero padding, the border is never written).                */
+int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4* cat, int c_off, int n, int h, int w,
+                   int c, void* stream);
+/* dx[n,h,w,c] = scatter((dy + window(dcat)) * (pooled > 0)) by idx; dy / dcat may be NULL */
+int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsigned char* idx, const void* pooled,
+                   void* dx, int n, int h, int w, int c, void* stream);
+
+/* ---- 1x1 head, 64 -> 2 (network.py:190) and argmax (tester.py:30; trainer.py:82) ---- */
+int ub_head_fwd(const void* x_bf16, const float* w, const float* bias, float* logits_nchw, unsigned char* argmax,
+                int n, int h, int w_, void* stream);
+int ub_head_bwd(const void* x_bf16, const float* w, const float* dlogits_nchw, void* dx_bf16, float* dw, float* db,
+                int n, int h, int w_, void* stream);
+
+/* ---- pixel-wise weighted loss, forward + dlogits fused (trainer.py:60-75) ----
+ * kind 0: BCE-with-logits vs the one-hot target, mean over B*2*L*L (nn.BCEWithLogitsLoss(weight));
+ * kind 1: weighted softmax cross-entropy, mean over B*L*L.
+ * logits [B,2,hp,wp] fp32, centre-cropped by pad = (hp-L)/2; label [B,L,L] (label_bytes 1 or 8);
+ * weight [B,L,L] fp32; dlogits [B,2,hp,wp] (may be NULL) receives grad_scale * dloss_sum/dz;
+ * workspace: ub_loss_workspace_bytes() bytes, zero-initialised once by the caller.                  */
+long long ub_loss_workspace_bytes(void);
+int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_bytes, const float* weight,
+                    float* dlogits, float* loss_out, void* workspace, int b, int hp, int wp, int l, float grad_scale,
+                    void* stream);
+
+/* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients); out += */
+int ub_colsum(const void* g_bf16, float* out, long long n_pix, int c, long long ld, void* stream);
+
+/* ---- optim.SGD(lr, momentum=0.99).step() over a flat arena (trainer.py:30,78) ---- */
+int ub_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,
+                    void* stream);
+
+/* ---- test-only comparators / probes (never on the product path) ---- */
+int ub_naive_conv3x3(const void* x_bf16, const void* w_fwd, const float* bias, float* y_f32, int n, int h, int w_,
+                     int cin, int cout, int relu, void* stream);
+/* Runs the descriptor-semantics probes; writes up to `cap` floats of results to host `out`. */
+int ub_probe_run(int which, float* out_host, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H_ */
