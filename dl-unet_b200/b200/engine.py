@@ -1,0 +1,364 @@
+"""Execution engine of the B200 U-Net path: owns the flat parameter / gradient arenas, the
+packed bf16 weight caches and the per-shape activation workspaces, and issues the explicit
+forward and backward kernel schedules (the replacement for the ATen dispatch + autograd tape
+of network.py:129-192 / trainer.py:77).
+
+Data layout in HBM
+  * activations: NHWC bf16, one buffer per layer output; the decoder's concat buffers
+    [B, Hu, Hu, 2*C] are written in place by the pool kernel (skip half, at the
+    crop_and_concat offset; border pre-zeroed once) and the up-convolution epilogue (upper half),
+    so network.py:126-127's pad + cat are never materialised.
+  * parameters: one flat fp32 arena in state_dict order (the nn.Parameters are views of it),
+    one flat fp32 gradient arena in BACKWARD-COMPLETION order (finalconv first) so gradient
+    buckets become ready front to back, one flat momentum arena.
+  * derived caches: bf16 K-major packed weights (forward and dgrad operand per layer),
+    refreshed when the masters change.
+"""
+import torch
+
+from . import ops
+from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
+
+PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
+# order in which backward finishes each layer's gradients
+BACKWARD_LAYER_ORDER = [n for (n, _, _, _) in reversed(LAYERS)]
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class ParamStore:
+    """Flat fp32 arenas for the 46 parameters, their gradients and momentum buffers."""
+
+    def __init__(self, module):
+        self.module = module
+        self.device = None
+        self.p_arena = self.g_arena = self.m_arena = None
+        # one layout for parameters, gradients and momentum: BACKWARD-completion order (finalconv
+        # first), each tensor padded to 64 elements, so (a) gradient buckets fill front to back and
+        # (b) the optimizer is a single elementwise kernel over [0, total)
+        self.numel, self.g_off = {}, {}
+        for name in PARAM_NAMES:
+            lname, pname = name.split(".")
+            shape = weight_shape(lname) if pname == "weight" else (LAYER_BY_NAME[lname][2],)
+            n = 1
+            for d in shape:
+                n *= d
+            self.numel[name] = n
+        goff = 0
+        for lname in BACKWARD_LAYER_ORDER:
+            for pname in ("weight", "bias"):
+                name = f"{lname}.{pname}"
+                self.g_off[name] = goff
+                goff += _align(self.numel[name])
+        self.p_off = self.g_off
+        self.total = goff
+        self.packs = {}
+        self.pack_versions = None
+        self.dirty = True
+        self.first_step = True
+
+    def params(self):
+        return {name: self.module.get_parameter(name) for name in PARAM_NAMES}
+
+    def adopt(self, device):
+        """Make every nn.Parameter a view of the flat arena on `device` (idempotent).  Called at
+        the top of each forward: `.to(device)` and `load_state_dict` may have re-pointed them."""
+        ps = self.params()
+        ok = self.p_arena is not None and self.p_arena.device == device
+        if ok:
+            base = self.p_arena.data_ptr()
+            for name, p in ps.items():
+                if p.data_ptr() != base + 4 * self.p_off[name] or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if ok:
+            return
+        for name, p in ps.items():
+            if p.device != device:
+                raise RuntimeError(f"parameter {name} is on {p.device}, input on {device}: call unet.to(device) first")
+        arena = torch.zeros(self.total, dtype=torch.float32, device=device)
+        for name, p in ps.items():
+            view = arena[self.p_off[name]:self.p_off[name] + self.numel[name]].view(p.shape)
+            view.copy_(p.detach().to(torch.float32))
+            p.data = view
+        self.p_arena = arena
+        self.g_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.m_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.dwp_arena = None
+        self.device = device
+        self.dirty = True
+        self.first_step = True
+
+    def p(self, name):
+        return self.p_arena[self.p_off[name]:self.p_off[name] + self.numel[name]]
+
+    def g(self, name):
+        return self.g_arena[self.g_off[name]:self.g_off[name] + self.numel[name]]
+
+    def grad_view(self, name):
+        lname, pname = name.split(".")
+        shape = weight_shape(lname) if pname == "weight" else (LAYER_BY_NAME[lname][2],)
+        return self.g(name).view(shape)
+
+    def versions(self):
+        return tuple(p._version for p in self.params().values())
+
+    def refresh_packs(self):
+        """Re-derive the bf16 GEMM operands when the fp32 masters changed."""
+        v = self.versions()
+        if not self.dirty and v == self.pack_versions:
+            return
+        for (lname, kind, cin, cout) in LAYERS:
+            w = self.p(lname + ".weight").view(weight_shape(lname))
+            if kind == "conv":
+                old = self.packs.get(lname, (None, None))
+                self.packs[lname] = (ops.pack_weight(w, ops.PACK_CONV_FWD, old[0]),
+                                     ops.pack_weight(w, ops.PACK_CONV_DGRAD, old[1]))
+            elif kind == "up":
+                old = self.packs.get(lname, (None, None))
+                self.packs[lname] = (ops.pack_weight(w, ops.PACK_UP_FWD, old[0]),
+                                     ops.pack_weight(w, ops.PACK_UP_DGRAD, old[1]))
+        self.pack_versions = v
+        self.dirty = False
+
+    def packed_grad_arena(self):
+        """fp32 scratch the wgrad kernels accumulate into (packed layout), zeroed per backward."""
+        if self.dwp_arena is None:
+            n = sum(_align(self.numel[l + ".weight"]) for (l, k, _, _) in LAYERS if k in ("conv", "up"))
+            self.dwp_arena = torch.empty(n, dtype=torch.float32, device=self.device)
+            self.dwp_off = {}
+            off = 0
+            for (l, k, _, _) in LAYERS:
+                if k in ("conv", "up"):
+                    self.dwp_off[l] = off
+                    off += _align(self.numel[l + ".weight"])
+        return self.dwp_arena
+
+    def dwp(self, lname):
+        self.packed_grad_arena()
+        return self.dwp_arena[self.dwp_off[lname]:self.dwp_off[lname] + self.numel[lname + ".weight"]]
+
+
+class Workspace:
+    """Activation (and, for training, gradient) buffers for one (batch, size) shape."""
+
+    def __init__(self, batch, size, device, train):
+        g = Geometry(size)
+        self.geom, self.B, self.S, self.train = g, batch, size, train
+        self.busy = False
+        bf = dict(dtype=torch.bfloat16, device=device)
+        B = batch
+        a = {}
+        for l in (1, 2, 3, 4):
+            C = LEVEL_C[l]
+            a[f"e{l}1"] = torch.empty(B, g.enc1[l], g.enc1[l], C, **bf)
+            a[f"e{l}2"] = torch.empty(B, g.enc2[l], g.enc2[l], C, **bf)
+            a[f"p{l}"] = torch.empty(B, g.pool[l], g.pool[l], C, **bf)
+            a[f"i{l}"] = torch.empty(B, g.pool[l], g.pool[l], C, dtype=torch.uint8, device=device)
+            # zero once: the padded border of the skip half is never written afterwards
+            a[f"cat{l}"] = torch.zeros(B, g.up[l], g.up[l], 2 * C, **bf)
+            a[f"d{l}1"] = torch.empty(B, g.dec1[l], g.dec1[l], C, **bf)
+            a[f"d{l}2"] = torch.empty(B, g.dec2[l], g.dec2[l], C, **bf)
+        a["e51"] = torch.empty(B, g.enc1[5], g.enc1[5], 1024, **bf)
+        a["e52"] = torch.empty(B, g.enc2[5], g.enc2[5], 1024, **bf)
+        self.act = a
+        self.grad = {}
+        if train:
+            for k, t in a.items():
+                if k[0] != "i":
+                    self.grad[k] = torch.empty_like(t)
+        self.image = None
+
+
+class Engine:
+    def __init__(self, module):
+        self.store = ParamStore(module)
+        self.workspaces = {}
+        self.grad_ready_hook = None  # callable(start, end): gradient arena slice [start, end) is final
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, batch, size, device, train):
+        key = (batch, size, str(device), train)
+        pool = self.workspaces.setdefault(key, [])
+        for ws in pool:
+            if not ws.busy:
+                return ws
+        ws = Workspace(batch, size, device, train)
+        pool.append(ws)
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image, train, argmax_out=None, want_logits=True):
+        """image: fp32 [B,1,S,S] CUDA.  Returns (logits fp32 [B,2,So,So] or None, workspace)."""
+        if image.dim() != 4 or image.shape[1] != 1 or image.shape[2] != image.shape[3]:
+            raise RuntimeError(f"expected a [B,1,S,S] image batch, got {tuple(image.shape)}")
+        if not image.is_cuda:
+            raise RuntimeError("the B200 U-Net path has no CPU implementation: move the module and the input to a CUDA device")
+        st = self.store
+        st.adopt(image.device)
+        st.refresh_packs()
+        image = image.contiguous().float()
+        B, _, S, _ = image.shape
+        ws = self.workspace(B, S, image.device, train)
+        g, a = ws.geom, ws.act
+        ws.image = image
+        P, pk = st.p, st.packs
+
+        ops.conv1_fwd(image, P("conv11c.weight"), P("conv11c.bias"), a["e11"])
+        ops.conv3x3_fwd(a["e11"], pk["conv12c"][0], P("conv12c.bias"), a["e12"])
+        x = a["e12"]
+        for l in (1, 2, 3, 4):
+            C = LEVEL_C[l]
+            if l > 1:
+                ops.conv3x3_fwd(x, pk[f"conv{l}1c"][0], P(f"conv{l}1c.bias"), a[f"e{l}1"])
+                ops.conv3x3_fwd(a[f"e{l}1"], pk[f"conv{l}2c"][0], P(f"conv{l}2c.bias"), a[f"e{l}2"])
+            ops.pool2x2_fwd(a[f"e{l}2"], a[f"p{l}"], a[f"i{l}"], a[f"cat{l}"][..., :C], g.coff[l])
+            x = a[f"p{l}"]
+        ops.conv3x3_fwd(x, pk["conv51c"][0], P("conv51c.bias"), a["e51"])
+        ops.conv3x3_fwd(a["e51"], pk["conv52c"][0], P("conv52c.bias"), a["e52"])
+        x = a["e52"]
+        for l in (4, 3, 2, 1):
+            C = LEVEL_C[l]
+            ops.upconv2x2_fwd(x, pk[f"upconv{l}"][0], P(f"upconv{l}.bias"), a[f"cat{l}"][..., C:])
+            ops.conv3x3_fwd(a[f"cat{l}"], pk[f"conv{l}1e"][0], P(f"conv{l}1e.bias"), a[f"d{l}1"])
+            ops.conv3x3_fwd(a[f"d{l}1"], pk[f"conv{l}2e"][0], P(f"conv{l}2e.bias"), a[f"d{l}2"])
+            x = a[f"d{l}2"]
+        logits = None
+        if want_logits:
+            logits = torch.empty(B, 2, g.out, g.out, dtype=torch.float32, device=image.device)
+        ops.head_fwd(x, P("finalconv.weight"), P("finalconv.bias"), logits, argmax_out)
+        return logits, ws
+
+    # ------------------------------------------------------------------ backward
+    def _ready(self, lname):
+        if self.grad_ready_hook is not None:
+            st = self.store
+            s = st.g_off[lname + ".weight"]
+            e = st.g_off[lname + ".bias"] + _align(st.numel[lname + ".bias"])
+            self.grad_ready_hook(s, e)
+
+    def _conv_bwd(self, lname, x, dy, dx, relu_src):
+        """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer."""
+        st = self.store
+        dwp = st.dwp(lname)
+        ops.conv3x3_wgrad(x, dy, dwp)
+        ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
+        ops.colsum(dy, st.g(lname + ".bias"))
+        self._ready(lname)
+        if dx is not None:
+            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src)
+
+    def backward(self, ws, dlogits):
+        """dlogits: fp32 [B,2,So,So] (d loss / d logits).  Fills the gradient arena; if every
+        param.grad still is its arena view (no zero_grad since the last backward) the new
+        gradients are accumulated on top, as autograd would."""
+        st = self.store
+        a, gr, g = ws.act, ws.grad, ws.geom
+        self._accumulate = all(
+            p.grad is not None and p.grad.data_ptr() == st.grad_view(n).data_ptr() for n, p in st.params().items())
+        if not self._accumulate:
+            st.g_arena.zero_()
+        st.packed_grad_arena().zero_()
+        P, pk = st.p, st.packs
+        dlogits = dlogits.contiguous().float()
+
+        ops.head_bwd(a["d12"], P("finalconv.weight"), dlogits, gr["d12"], st.g("finalconv.weight"),
+                     st.g("finalconv.bias"))
+        self._ready("finalconv")
+        dy = gr["d12"]
+        for l in (1, 2, 3, 4):
+            C = LEVEL_C[l]
+            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"])
+            self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None)
+            # up-convolution: its output is the upper channel half of the concat buffer
+            up_name = f"upconv{l}"
+            src = a[f"d{l + 1}2"] if l < 4 else a["e52"]
+            dsrc = gr[f"d{l + 1}2"] if l < 4 else gr["e52"]
+            dyu = gr[f"cat{l}"][..., C:]
+            dwp = st.dwp(up_name)
+            ops.upconv2x2_wgrad(src, dyu, dwp)
+            ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
+            ops.colsum(dyu, st.g(up_name + ".bias"))
+            self._ready(up_name)
+            ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
+            dy = dsrc
+        # bottleneck
+        self._conv_bwd("conv52c", a["e51"], gr["e52"], gr["e51"], a["e51"])
+        self._conv_bwd("conv51c", a["p4"], gr["e51"], gr["p4"], None)
+        for l in (4, 3, 2, 1):
+            C = LEVEL_C[l]
+            H = g.enc2[l]
+            if H & 1:
+                gr[f"e{l}2"].zero_()  # floor-mode pool: the last row / column gets no gradient
+            ops.pool2x2_bwd(gr[f"p{l}"], gr[f"cat{l}"][..., :C], g.coff[l], a[f"i{l}"], a[f"p{l}"], gr[f"e{l}2"])
+            self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"])
+            if l > 1:
+                self._conv_bwd(f"conv{l}1c", a[f"p{l - 1}"], gr[f"e{l}1"], gr[f"p{l - 1}"], None)
+            else:
+                ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
+                self._ready("conv11c")
+
+    def assign_grads(self, accumulate_existing=True):
+        """Expose the gradient arena through param.grad (views; no copies)."""
+        st = self.store
+        for name, p in st.params().items():
+            v = st.grad_view(name)
+            if p.grad is None or not accumulate_existing:
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                p.grad.add_(v)
+            # else: p.grad already is this view and was overwritten -> caller zero_grad()s per step
+
+
+class _Lease:
+    """Marks a workspace busy for as long as an autograd graph may still need its activations."""
+
+    def __init__(self, ws):
+        self.ws = ws
+        ws.busy = True
+
+    def release(self):
+        if self.ws is not None:
+            self.ws.busy = False
+            self.ws = None
+
+    def __del__(self):
+        self.release()
+
+
+class _UnetFn(torch.autograd.Function):
+    """Whole-network autograd node: forward = Engine.forward, backward = Engine.backward.  The 46
+    parameter gradients are delivered through param.grad views of the flat arena (so a fused
+    optimizer and bucketed all-reduce can work on contiguous memory) and not through autograd's
+    return values."""
+
+    @staticmethod
+    def forward(ctx, engine, image, anchor):
+        logits, ws = engine.forward(image, train=True)
+        ctx.engine, ctx.ws = engine, ws
+        ctx.lease = _Lease(ws)  # the workspace is released when backward ran or the graph died
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        engine, ws = ctx.engine, ctx.ws
+        try:
+            engine.backward(ws, dlogits)
+            engine.assign_grads()
+        finally:
+            ctx.lease.release()
+        return None, None, None
+
+
+def unet_forward(engine, image):
+    """Autograd-aware forward used by network.Unet.forward."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in engine.store.module.parameters()):
+        if image.requires_grad:
+            raise RuntimeError("gradients w.r.t. the input image are not part of the reference path (network.py:131)")
+        # `anchor` makes the output require grad so that autograd calls our backward
+        anchor = next(p for p in engine.store.module.parameters() if p.requires_grad)
+        return _UnetFn.apply(engine, image, anchor)
+    logits, _ = engine.forward(image, train=False)
+    return logits

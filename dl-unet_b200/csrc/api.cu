@@ -496,7 +496,7 @@ int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int
 int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4* cat, int c_off, int n, int h, int w,
                    int c, void* stream) {
   if (!x || !y || !idx) return UB_E_ARG;
-  if ((h & 1) || (w & 1) || (c % 8) || n <= 0 || h <= 0 || w <= 0) return UB_E_SHAPE;
+  if ((c % 8) || n <= 0 || h < 2 || w < 2) return UB_E_SHAPE; // odd h/w: floor mode, last row/col ignored
   if (!aligned16(x) || !aligned16(y) || (reinterpret_cast<uintptr_t>(idx) & 7)) return UB_E_ALIGN;
   __nv_bfloat16* catp = nullptr;
   int ch = 0, cw = 0, cc = 0;
@@ -518,7 +518,7 @@ int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4*
 int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsigned char* idx, const void* pooled,
                    void* dx, int n, int h, int w, int c, void* stream) {
   if (!idx || !pooled || !dx) return UB_E_ARG;
-  if ((h & 1) || (w & 1) || (c % 8) || n <= 0) return UB_E_SHAPE;
+  if ((c % 8) || n <= 0 || h < 2 || w < 2) return UB_E_SHAPE;
   if (!aligned16(dx) || !aligned16(pooled) || (dy && !aligned16(dy))) return UB_E_ALIGN;
   const __nv_bfloat16* catp = nullptr;
   int ch = 0, cw = 0, cc = 0;

@@ -1,0 +1,164 @@
+"""Pin the oracle against the reference itself and (re)generate tests/golden/*.npz.
+
+Runs ONLY in the build container, where /root/reference exists (it cannot travel to the GPU box):
+
+    python oracle/validate_against_reference.py            # check + write golden fixtures
+
+What is checked, on the CPU in fp32, bit-exactly (torch.equal):
+  * init_state_dict(seed) == torch.manual_seed(seed); network.Unet().state_dict()
+  * forward() == network.Unet.forward on S = 188 (crop branch of crop_and_concat), 220 and 252
+  * crop_and_concat pad / crop / odd-size RuntimeError behaviour (network.py:108-127)
+  * one trainer.py:54-78 step (BCEWithLogitsLoss(weight) at B = 1, loss.backward(), optim.SGD
+    lr=1e-4 momentum=0.99) repeated twice: loss, 46 grads, updated weights
+  * tester.py:29-30 mask
+The golden files hold only seeds, logits, losses and per-parameter gradient digests (the 31 M
+weights are regenerated from the seed by init_state_dict, which this script proves equal).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, HERE)
+import unet_oracle as O  # noqa: E402
+
+
+def import_reference():
+    """Import the reference modules unmodified; `batchgenerators` (only used for maybe_mkdir_p,
+    trainer.py:4) is not installed, so a 1-function stub stands in for it."""
+    bg = types.ModuleType("batchgenerators")
+    bgu = types.ModuleType("batchgenerators.utilities")
+    bgf = types.ModuleType("batchgenerators.utilities.file_and_folder_operations")
+    bgf.maybe_mkdir_p = lambda d: os.makedirs(d, exist_ok=True)
+    sys.modules.setdefault("batchgenerators", bg)
+    sys.modules.setdefault("batchgenerators.utilities", bgu)
+    sys.modules.setdefault("batchgenerators.utilities.file_and_folder_operations", bgf)
+    sys.path.insert(0, REF)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import network as ref_network
+        import functions as ref_functions
+    sys.path.remove(REF)
+    return ref_network, ref_functions
+
+
+def grad_digest(g):
+    g = g.detach().double().flatten()
+    head = (g[:5].tolist() + [0.0] * 5)[:5]
+    return np.array([g.norm().item(), g.sum().item(), g.abs().max().item()] + head, dtype=np.float64)
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref_network, ref_functions = import_reference()
+    ok = True
+
+    def check(name, cond):
+        nonlocal ok
+        print(("PASS " if cond else "FAIL ") + name, flush=True)
+        ok = ok and bool(cond)
+
+    # ---- init
+    for seed in (0, 7):
+        torch.manual_seed(seed)
+        ref = ref_network.Unet()
+        sd = O.init_state_dict(seed)
+        rsd = ref.state_dict()
+        check(f"state_dict keys/order seed={seed}", list(rsd.keys()) == O.PARAM_NAMES == list(sd.keys()))
+        check(f"state_dict values bit-equal seed={seed}", all(torch.equal(rsd[k], sd[k]) for k in rsd))
+
+    # ---- crop_and_concat
+    ref = ref_network.Unet()
+    a, b = torch.randn(1, 2, 8, 8), torch.randn(1, 3, 4, 4)
+    check("crop_and_concat crop 8->4", torch.equal(ref.crop_and_concat(a, b), O.crop_and_concat(a, b)))
+    a, b = torch.randn(1, 2, 32, 32), torch.randn(1, 3, 56, 56)
+    check("crop_and_concat pad 32->56", torch.equal(ref.crop_and_concat(a, b), O.crop_and_concat(a, b)))
+    raised = [False, False]
+    for i, fn in enumerate((ref.crop_and_concat, O.crop_and_concat)):
+        try:
+            fn(torch.randn(1, 1, 5, 5), torch.randn(1, 1, 8, 8))
+        except RuntimeError:
+            raised[i] = True
+    check("crop_and_concat odd difference raises RuntimeError in both", raised == [True, True])
+    check("output_size: 188->4, 220->36, 572->388, 204->None",
+          (O.output_size(188), O.output_size(220), O.output_size(572), O.output_size(204)) == (4, 36, 388, None))
+
+    # ---- forward / train step / mask, and golden fixtures
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for (S, B, seed) in ((188, 1, 0), (220, 1, 1), (252, 2, 2)):
+        torch.manual_seed(seed)
+        ref = ref_network.Unet()
+        sd = O.init_state_dict(seed)
+        images, labels, weight = O.synthetic_batch(B, S, seed=100 + seed)
+        L = labels.shape[-1]
+        with torch.no_grad():
+            rl = ref(images)
+        ol = O.forward(sd, images)
+        check(f"forward bit-equal S={S} B={B}", torch.equal(rl, ol))
+        check(f"mask equal S={S}", torch.equal(
+            rl[:, :, :L, :L].argmax(dim=1), O.predict_mask(sd, images, L)))
+
+        gold = {"S": S, "B": B, "seed": seed, "data_seed": 100 + seed, "logits0": ol.numpy().copy()}
+        if B == 1:
+            # the reference's own loss object is exact only at B = 1
+            opt = torch.optim.SGD(ref.parameters(), lr=0.0001, momentum=0.99)      # trainer.py:30
+            mom = {}
+            for step in range(2):
+                opt.zero_grad()                                                        # trainer.py:54
+                preds = ref(images)                                                    # trainer.py:58
+                pad = int((preds.shape[-1] - labels.shape[-1]) / 2)                    # trainer.py:60
+                preds = preds[:, :, pad:labels.shape[-1] + pad, pad:labels.shape[-1] + pad]
+                ll = torch.empty_like(preds)                                           # trainer.py:63-66
+                ll[:, 0, :, :] = 1 - labels[:, 0, :, :]
+                ll[:, 1, :, :] = labels[:, 0, :, :]
+                criterion = torch.nn.BCEWithLogitsLoss(weight=weight)                  # trainer.py:73
+                loss = criterion(preds, ll)
+                loss.backward()                                                        # trainer.py:77
+                rgrads = {k: p.grad.clone() for k, p in ref.named_parameters()}
+                opt.step()                                                             # trainer.py:78
+                oloss, _, ograds = O.train_step(sd, mom, images, labels, weight)
+                check(f"train step {step} loss bit-equal S={S}", torch.equal(loss.detach(), oloss))
+                check(f"train step {step} 46 grads bit-equal S={S}",
+                      all(torch.equal(rgrads[k], ograds[k]) for k in rgrads))
+                check(f"train step {step} updated weights bit-equal S={S}",
+                      all(torch.equal(p.detach(), sd[k]) for k, p in ref.named_parameters()))
+                gold[f"loss{step}"] = np.float64(oloss.item())
+                gold[f"grad_digest{step}"] = np.stack([grad_digest(ograds[k]) for k in O.PARAM_NAMES])
+            gold["logits_after2"] = O.forward(sd, images).detach().numpy().copy()
+        else:
+            # B > 1: the intended per-pixel broadcast (weight.unsqueeze(1)); oracle only
+            mom = {}
+            oloss, _, ograds = O.train_step(sd, mom, images, labels, weight)
+            gold["loss0"] = np.float64(oloss.item())
+            gold["grad_digest0"] = np.stack([grad_digest(ograds[k]) for k in O.PARAM_NAMES])
+        # softmax-CE variant (oracle = torch)
+        sd2 = O.init_state_dict(seed)
+        closs, _, cgrads = O.train_step(sd2, {}, images, labels, weight, kind="ce")
+        gold["ce_loss0"] = np.float64(closs.item())
+        gold["ce_grad_digest0"] = np.stack([grad_digest(cgrads[k]) for k in O.PARAM_NAMES])
+        path = os.path.join(ROOT, "tests", "golden", f"unet_S{S}_B{B}_seed{seed}.npz")
+        np.savez_compressed(path, **gold)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+    # ---- pool indices / tie rule
+    x = torch.relu(torch.randn(2, 3, 8, 8)).round()  # many ties and all-zero windows
+    v, i = O.pool_with_indices(x)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pool_ties.npz"), x=x.numpy(), v=v.numpy(), i=i.numpy())
+
+    # ---- reference weight-map helpers, for the f1 row (kept for later rounds)
+    lab = (torch.rand(1, 36, 36) > 0.5).long()
+    cb = ref_functions.class_balance(lab)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "class_balance.npz"), lab=lab.numpy(), w=cb.numpy())
+
+    print("ALL PASS" if ok else "SOME CHECKS FAILED")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

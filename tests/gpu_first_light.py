@@ -147,7 +147,7 @@ def sec_upconv():
         # dgrad
         dcat = torch.randn(n, 2 * h, 2 * w, 2 * cout, device=DEV).to(torch.bfloat16)
         dyv = dcat[..., cout:]
-        refd = F.conv2d(nchw(dyv), bf(wt).float().permute(1, 0, 2, 3), stride=2)  # [n, cin, h, w]
+        refd = F.conv2d(nchw(dyv), bf(wt).float(), stride=2)  # weight [cin, cout, 2, 2] acts as [out, in, 2, 2]
         xsrc = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
         dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
         ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt.contiguous(), ops.PACK_UP_DGRAD), dx, None)

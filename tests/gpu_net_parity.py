@@ -1,0 +1,122 @@
+"""Whole-network parity + first timings on a B200 (diagnostic script; the asserting versions live
+in tests/test_gpu_*.py):  python tests/gpu_net_parity.py [sizes...]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+
+import unet_oracle as O  # noqa: E402
+from network import Unet  # noqa: E402
+from b200 import train as T  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    d = (a - b)
+    return dict(rel_l2=(d.norm() / (b.norm() + 1e-300)).item(), max_rel=(d.abs().max() / (b.abs().max() + 1e-300)).item())
+
+
+def bf16_round_sd(sd):
+    return {k: (v.to(torch.bfloat16).float() if k.endswith("weight") and "conv11c" not in k and "finalconv" not in k else v)
+            for k, v in sd.items()}
+
+
+def parity(S, B, seed, round_weights):
+    torch.manual_seed(seed)
+    net = Unet()
+    sd = O.init_state_dict(seed)
+    same = all(torch.equal(sd[k], v) for k, v in net.state_dict().items())
+    if round_weights:
+        sd = bf16_round_sd(sd)
+        net.load_state_dict(sd)
+    images, labels, weight = O.synthetic_batch(B, S, seed=100 + seed)
+    if round_weights:
+        images = images.to(torch.bfloat16).float()
+    net.to(DEV)
+    # oracle (CPU fp32)
+    t0 = time.time()
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    oloss, ologits, ograds = O.train_step(sd_o, {}, images, labels, weight)
+    t_cpu = time.time() - t0
+    # ours
+    opt = T.FusedSGD(net, lr=1e-4, momentum=0.99)
+    opt.zero_grad()
+    logits = net(images.to(DEV))
+    loss = T.weighted_bce_with_logits(logits, labels.to(DEV), weight.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    L = labels.shape[-1]
+    agree = (logits.argmax(1).cpu() == ologits.argmax(1)).float().mean().item()
+    r = rel(logits, ologits)
+    print(f"S={S} B={B} seed={seed} round_w={round_weights} init_same={same} cpu_step={t_cpu:.1f}s")
+    print(f"  logits rel_l2={r['rel_l2']:.3e} max_rel={r['max_rel']:.3e} argmax_agree={agree:.5f} "
+          f"loss ours={loss.item():.6f} oracle={oloss.item():.6f} rel={abs(loss.item() - oloss.item()) / abs(oloss.item()):.2e}")
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        rr = rel(p.grad, ograds[k])
+        if rr["rel_l2"] > worst[1]:
+            worst = (k, rr["rel_l2"])
+        print(f"    grad {k:18s} rel_l2={rr['rel_l2']:.3e} max_rel={rr['max_rel']:.3e}")
+    print(f"  worst grad rel_l2: {worst}")
+    opt.step()
+    torch.cuda.synchronize()
+    w = max(rel(p.detach(), sd_o[k])["max_rel"] for k, p in net.named_parameters())
+    print(f"  after SGD step: max over params of max_rel(weight) = {w:.3e}")
+    # masks
+    m = net.predict(images.to(DEV), L)
+    mo = O.predict_mask(sd_o, images, L)
+    print(f"  predict() mask agreement after step: {(m.cpu() == mo).float().mean().item():.5f}")
+
+
+def timing(S, B, steps=5):
+    torch.manual_seed(0)
+    net = Unet().to(DEV)
+    opt = T.FusedSGD(net)
+    images, labels, weight = O.synthetic_batch(B, S, seed=1)
+    images, labels, weight = images.to(DEV), labels.to(DEV).to(torch.uint8), weight.to(DEV)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for i in range(steps + 2):
+        if i == 2:
+            torch.cuda.synchronize()
+            t0 = time.time()
+            tf = tb = 0.0
+        opt.zero_grad()
+        ev[0].record()
+        logits = net(images)
+        loss = T.weighted_bce_with_logits(logits, labels, weight)
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        if i >= 2:
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1])
+            tb += ev[1].elapsed_time(ev[2])
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / steps
+    print(f"timing S={S} B={B}: {dt * 1e3:.2f} ms/step wall -> {B / dt:.1f} tiles/s; fwd+loss {tf / steps:.2f} ms, "
+          f"bwd {tb / steps:.2f} ms; loss={loss.item():.4f}; "
+          f"fwd TFLOP/s={300.86e9 * B * (S == 572) / (tf / steps * 1e-3) / 1e12:.1f} "
+          f"bwd TFLOP/s={601.3e9 * B * (S == 572) / (tb / steps * 1e-3) / 1e12:.1f}", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "small"):
+        parity(188, 1, 0, False)
+        parity(220, 1, 1, True)
+        parity(252, 2, 2, True)
+    if which in ("all", "full"):
+        parity(572, 1, 0, True)
+    if which in ("all", "time"):
+        timing(572, 1)
+        timing(572, 4)
+        timing(572, 16)
