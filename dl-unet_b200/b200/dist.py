@@ -1,0 +1,79 @@
+"""Data-parallel training across the GPUs of one box: one process per GPU (torchrun), tiles
+partitioned by rank, ONE exchange step -- a sum all-reduce of the flat gradient arena over
+NCCL / NVLink, issued bucket by bucket on a side stream while backward is still producing the
+later buckets (the arena is laid out in backward-completion order, so buckets fill front to back).
+
+The reference has no multi-device code (main_main.py:157-167); this is SURVEY.md section 8 row (e).
+The loss must be normalised by the GLOBAL batch (b200.train.*(global_batch=...)) so that the summed
+gradients equal the single-GPU gradients of the concatenated batch.
+"""
+import torch
+import torch.distributed as dist
+
+
+def partition(n_items, rank, world):
+    """Contiguous, balanced split of n_items independent units (tiles) over ranks."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def bucket_bounds(total, ready_ends, bucket_elems):
+    """Pure helper (unit-tested on CPU): given the arena offsets at which successive layers complete,
+    return the [start, end) slices to all-reduce, each at least bucket_elems long except the last."""
+    out, start = [], 0
+    for e in ready_ends:
+        if e - start >= bucket_elems or e == total:
+            if e > start:
+                out.append((start, e))
+            start = e
+    if start < total:
+        out.append((start, total))
+    return out
+
+
+class GradAllReducer:
+    def __init__(self, unet, bucket_mb=32.0, group=None):
+        self.engine = unet.engine if hasattr(unet, "engine") else unet
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.comm_stream = None
+        self.start = 0
+        self.works = []
+        self.engine.grad_ready_hook = self._on_ready
+        self.engine.grad_done_hook = self._on_done
+
+    def broadcast_parameters(self, src=0):
+        st = self.engine.store
+        dist.broadcast(st.p_arena, src, group=self.group)
+        dist.broadcast(st.m_arena, src, group=self.group)  # momentum must agree too
+        st.dirty = True
+
+    def _flush(self, end):
+        st = self.engine.store
+        if end <= self.start:
+            return
+        if not st.g_arena.is_cuda:  # host-side logic tests (gloo): same bucketing, no streams
+            self.works.append(dist.all_reduce(st.g_arena[self.start:end], group=self.group, async_op=True))
+            self.start = end
+            return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=st.g_arena.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.works.append(dist.all_reduce(st.g_arena[self.start:end], group=self.group, async_op=True))
+        self.start = end
+
+    def _on_ready(self, s, e):
+        if e - self.start >= self.bucket_elems:
+            self._flush(e)
+
+    def _on_done(self):
+        self._flush(self.engine.store.total)
+        for w in self.works:
+            w.wait()  # the compute stream waits for the reduced buckets
+        self.works = []
+        self.start = 0

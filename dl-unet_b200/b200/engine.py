@@ -177,6 +177,7 @@ class Engine:
         self.store = ParamStore(module)
         self.workspaces = {}
         self.grad_ready_hook = None  # callable(start, end): gradient arena slice [start, end) is final
+        self.grad_done_hook = None   # callable(): every gradient has been produced
 
     # ------------------------------------------------------------------ workspaces
     def workspace(self, batch, size, device, train):
@@ -299,6 +300,8 @@ class Engine:
             else:
                 ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
                 self._ready("conv11c")
+        if self.grad_done_hook is not None:
+            self.grad_done_hook()
 
     def assign_grads(self, accumulate_existing=True):
         """Expose the gradient arena through param.grad (views; no copies)."""

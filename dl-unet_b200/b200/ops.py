@@ -14,6 +14,57 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Stats:
+    """Launch accounting for bench.py: `launches` counts every kernel this library launched;
+    with `timing` on, each tensor-pipe launch is bracketed by CUDA events on the launching stream
+    and recorded as (family, algorithmic FLOPs, start, end)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.records = []
+
+    def reset(self):
+        self.launches = 0
+        self.records = []
+
+    def summarize(self):
+        """-> {family: (total_flops_or_bytes, total_ms, n_launches)}; call after a synchronize."""
+        out = {}
+        for fam, work, e0, e1 in self.records:
+            t = e0.elapsed_time(e1)
+            w, ms, n = out.get(fam, (0.0, 0.0, 0))
+            out[fam] = (w + work, ms + t, n + 1)
+        return out
+
+
+STATS = _Stats()
+
+
+class _timed:
+    def __init__(self, family, work):
+        self.family, self.work = family, work
+
+    def __enter__(self):
+        if STATS.timing:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STATS.timing:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            STATS.records.append((self.family, self.work, self.e0, e1))
+        return False
+
+
+def _chk(code, what=""):
+    """check() + launch accounting (every successful call below is exactly one kernel launch)."""
+    check(code, what)
+    STATS.launches += 1
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -65,7 +116,7 @@ def pack_weight(w, mode, out=None):
         shape = (4 * cout, cin) if mode == PACK_UP_FWD else (cin, 4 * cout)
     if out is None:
         out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-    check(_lib.load().ub_pack_weight(_ptr(w), _ptr(out), mode, cout, cin, _stream()), "pack_weight")
+    _chk(_lib.load().ub_pack_weight(_ptr(w), _ptr(out), mode, cout, cin, _stream()), "pack_weight")
     return out
 
 
@@ -74,44 +125,56 @@ def unpack_grad(packed, dw, mode, accumulate=False):
         cout, cin = dw.shape[0], dw.shape[1]
     else:
         cin, cout = dw.shape[0], dw.shape[1]
-    check(_lib.load().ub_unpack_grad(_ptr(packed), _ptr(dw), mode, cout, cin, int(accumulate), _stream()), "unpack_grad")
+    _chk(_lib.load().ub_unpack_grad(_ptr(packed), _ptr(dw), mode, cout, cin, int(accumulate), _stream()), "unpack_grad")
     return dw
 
 
 # ---------------------------------------------------------------- tensor-pipe ops
 def conv3x3_fwd(x, w_fwd, bias, y, relu=True):
     _need_cuda(x, w_fwd, y)
-    check(_lib.load().ub_conv3x3_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), int(relu), _stream()), "conv3x3_fwd")
+    n, h, w, co = y.shape
+    with _timed("igemm", 2.0 * n * h * w * co * 9 * x.shape[3]):
+        _chk(_lib.load().ub_conv3x3_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), int(relu), _stream()), "conv3x3_fwd")
     return y
 
 
 def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None):
     _need_cuda(dy, w_dgrad, dx)
-    check(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
+    n, h, w, co = dy.shape
+    with _timed("igemm", 2.0 * n * h * w * co * 9 * dx.shape[3]):
+        _chk(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
     return dx
 
 
 def conv3x3_wgrad(x, dy, dw_packed):
     _need_cuda(x, dy, dw_packed)
-    check(_lib.load().ub_conv3x3_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "conv3x3_wgrad")
+    n, h, w, co = dy.shape
+    with _timed("wgrad", 2.0 * n * h * w * co * 9 * x.shape[3]):
+        _chk(_lib.load().ub_conv3x3_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "conv3x3_wgrad")
     return dw_packed
 
 
 def upconv2x2_fwd(x, w_fwd, bias, y):
     _need_cuda(x, w_fwd, y)
-    check(_lib.load().ub_upconv2x2_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _stream()), "upconv2x2_fwd")
+    n, h, w, ci = x.shape
+    with _timed("igemm", 2.0 * n * h * w * ci * 4 * y.shape[3]):
+        _chk(_lib.load().ub_upconv2x2_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _stream()), "upconv2x2_fwd")
     return y
 
 
 def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None):
     _need_cuda(dy, w_dgrad, dx)
-    check(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
+    n, h, w, ci = dx.shape
+    with _timed("igemm", 2.0 * n * h * w * ci * 4 * dy.shape[3]):
+        _chk(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
     return dx
 
 
 def upconv2x2_wgrad(x, dy, dw_packed):
     _need_cuda(x, dy, dw_packed)
-    check(_lib.load().ub_upconv2x2_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "upconv2x2_wgrad")
+    n, h, w, ci = x.shape
+    with _timed("wgrad", 2.0 * n * h * w * ci * 4 * dy.shape[3]):
+        _chk(_lib.load().ub_upconv2x2_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "upconv2x2_wgrad")
     return dw_packed
 
 
@@ -120,37 +183,37 @@ def conv1_fwd(image, w, bias, y):
     """image fp32 [N,1,H,W] -> y bf16 [N,H-2,W-2,64], bias + ReLU fused (network.py:131)."""
     _need_cuda(image, w, bias, y)
     n, _, h, wd = image.shape
-    check(_lib.load().ub_conv1_fwd(_ptr(image), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, _stream()), "conv1_fwd")
+    _chk(_lib.load().ub_conv1_fwd(_ptr(image), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, _stream()), "conv1_fwd")
     return y
 
 
 def conv1_wgrad(image, dy, dw, db):
     n, _, h, wd = image.shape
-    check(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
+    _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
 
 
 def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
     _need_cuda(x, y, idx)
     n, h, w, c = x.shape
-    check(_lib.load().ub_pool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), _t4p(cat), int(c_off), n, h, w, c, _stream()), "pool2x2_fwd")
+    _chk(_lib.load().ub_pool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), _t4p(cat), int(c_off), n, h, w, c, _stream()), "pool2x2_fwd")
     return y, idx
 
 
 def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx):
     n, h, w, c = dx.shape
-    check(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), n, h, w, c,
+    _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), n, h, w, c,
                                      _stream()), "pool2x2_bwd")
     return dx
 
 
 def head_fwd(x, w, bias, logits=None, argmax=None):
     n, h, wd, _ = x.shape
-    check(_lib.load().ub_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(logits), _ptr(argmax), n, h, wd, _stream()), "head_fwd")
+    _chk(_lib.load().ub_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(logits), _ptr(argmax), n, h, wd, _stream()), "head_fwd")
 
 
 def head_bwd(x, w, dlogits, dx, dw, db):
     n, h, wd, _ = x.shape
-    check(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), n, h, wd, _stream()),
+    _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), n, h, wd, _stream()),
           "head_bwd")
 
 
@@ -168,7 +231,7 @@ def loss_fwd_bwd(kind, logits, label, weight, dlogits, loss_out, workspace, grad
     b, _, hp, wp = logits.shape
     l = label.shape[-1]
     lb = {torch.uint8: 1, torch.int64: 8}[label.dtype]
-    check(_lib.load().ub_loss_fwd_bwd(kind, _ptr(logits), _ptr(label), lb, _ptr(weight), _ptr(dlogits), _ptr(loss_out),
+    _chk(_lib.load().ub_loss_fwd_bwd(kind, _ptr(logits), _ptr(label), lb, _ptr(weight), _ptr(dlogits), _ptr(loss_out),
                                       _ptr(workspace), b, hp, wp, l, float(grad_scale), _stream()), "loss_fwd_bwd")
 
 
@@ -178,11 +241,11 @@ def colsum(g, out):
     ld = g.stride(2)
     if g.stride(1) != w * ld or (n > 1 and g.stride(0) != h * w * ld):
         raise RuntimeError("colsum needs a view that is dense over pixels")
-    check(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
+    _chk(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
 
 
 def sgd_momentum(p, g, buf, lr, momentum, first_step):
-    check(_lib.load().ub_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum),
+    _chk(_lib.load().ub_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum),
                                       int(first_step), _stream()), "sgd_momentum")
 
 
@@ -190,14 +253,14 @@ def naive_conv3x3(x, w_fwd, bias, relu):
     n, h, w, cin = x.shape
     cout = w_fwd.shape[0]
     y = torch.empty((n, h - 2, w - 2, cout), dtype=torch.float32, device=x.device)
-    check(_lib.load().ub_naive_conv3x3(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), n, h, w, cin, cout, int(relu),
+    _chk(_lib.load().ub_naive_conv3x3(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), n, h, w, cin, cout, int(relu),
                                        _stream()), "naive_conv3x3")
     return y
 
 
 def probe_run(cap_rows=128):
     buf = (C.c_float * (cap_rows * 6))(*([-1.0] * (cap_rows * 6)))
-    check(_lib.load().ub_probe_run(0, buf, cap_rows * 6), "probe")
+    _chk(_lib.load().ub_probe_run(0, buf, cap_rows * 6), "probe")
     rows = []
     for i in range(cap_rows):
         r = list(buf[i * 6:(i + 1) * 6])

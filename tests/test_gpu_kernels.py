@@ -1,0 +1,259 @@
+"""GPU parity tests, per kernel, through the C ABI (b200.ops -> libunet_b200.so), against the matching
+torch.nn.functional op on IDENTICAL (bf16-rounded) inputs.  Integer / index / copy results are
+bit-exact; floating point within the tolerance written at each assert: a bf16-output kernel is
+allowed the bf16 rounding of its own output (2^-9 relative per element, ~1.7e-3 rel-L2) on top of
+fp32 accumulation-order noise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_OUT_TOL = 3e-3   # rel-L2 of a bf16-rounded output vs the fp32 reference
+FP32_TOL = 2e-5       # rel-L2 of an fp32 output (accumulation order only)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from b200 import ops as o
+    return o
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def nhwc(t):
+    return bf(t.permute(0, 2, 3, 1)).contiguous()
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+DEV = "cuda:0"
+CONV_SHAPES = [(1, 20, 20, 64, 64), (2, 30, 30, 128, 128), (1, 18, 34, 64, 256), (1, 12, 12, 256, 512),
+               (3, 10, 10, 128, 64), (1, 9, 9, 1024, 1024), (2, 70, 70, 64, 64), (1, 5, 3, 64, 64)]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3x3_fwd_dgrad_wgrad(ops, shape):
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device=DEV)
+    xq = bf(x).float().requires_grad_(True)
+    wq = bf(wt).float().requires_grad_(True)
+    ref = F.relu(F.conv2d(xq, wq, b))
+    y = torch.full((n, h - 2, w - 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_fwd(nhwc(x), ops.pack_weight(wt, ops.PACK_CONV_FWD), b, y, relu=True)
+    assert rel_l2(nchw(y), ref) < BF16_OUT_TOL
+    # backward of the un-activated conv with a given upstream gradient
+    dy = torch.randn(n, cout, h - 2, w - 2, device=DEV)
+    dyq = bf(dy).float()
+    gx, gw = torch.autograd.grad(F.conv2d(xq, wq), (xq, wq), dyq)
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, None)
+    assert rel_l2(nchw(dx), gx) < BF16_OUT_TOL
+    ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))   # fused ReLU backward
+    assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+    dwp = torch.zeros(cout, 9 * cin, device=DEV)
+    ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp)
+    dw = torch.empty_like(wt)
+    ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
+    assert rel_l2(dw, gw) < FP32_TOL
+
+
+def test_conv3x3_strided_views_write_in_place(ops):
+    n, h, w, cin, cout = 2, 22, 22, 64, 128
+    torch.manual_seed(1)
+    big = bf(torch.randn(n, h + 6, w + 6, 192, device=DEV))
+    xv = big[:, 3:3 + h, 3:3 + w, 64:128]
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / 24
+    b = torch.randn(cout, device=DEV)
+    ref = F.relu(F.conv2d(nchw(xv), bf(wt).float(), b))
+    out = torch.zeros(n, h - 2, w - 2, 384, dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_fwd(xv, ops.pack_weight(wt, ops.PACK_CONV_FWD), b, out[..., 128:256], relu=True)
+    assert rel_l2(nchw(out[..., 128:256]), ref) < BF16_OUT_TOL
+    assert bool((out[..., :128] == 0).all()) and bool((out[..., 256:] == 0).all())   # neighbours untouched
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256)])
+def test_upconv2x2(ops, shape):
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(cin, cout, 2, 2, device=DEV) / cin ** 0.5
+    b = torch.randn(cout, device=DEV)
+    xq = bf(x).float().requires_grad_(True)
+    wq = bf(wt).float().requires_grad_(True)
+    ref = F.conv_transpose2d(xq, wq, b, stride=2)
+    cat = torch.zeros(n, 2 * h, 2 * w, 2 * cout, dtype=torch.bfloat16, device=DEV)
+    ops.upconv2x2_fwd(nhwc(x), ops.pack_weight(wt, ops.PACK_UP_FWD), b, cat[..., cout:])
+    assert rel_l2(nchw(cat[..., cout:]), ref) < BF16_OUT_TOL
+    assert bool((cat[..., :cout] == 0).all())                       # the skip half of the concat buffer is untouched
+    dcat = bf(torch.randn(n, 2 * h, 2 * w, 2 * cout, device=DEV))
+    dyv = dcat[..., cout:]
+    gx, gw = torch.autograd.grad(ref, (xq, wq), nchw(dyv))
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt, ops.PACK_UP_DGRAD), dx, nhwc(x))
+    assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+    dwp = torch.zeros(4 * cout, cin, device=DEV)
+    ops.upconv2x2_wgrad(nhwc(x), dyv, dwp)
+    dw = torch.empty_like(wt)
+    ops.unpack_grad(dwp, dw, ops.PACK_UP_FWD)
+    assert rel_l2(dw, gw) < FP32_TOL
+
+
+def test_pack_modes_exact(ops):
+    wt = torch.randn(128, 64, 3, 3, device=DEV)
+    assert torch.equal(ops.pack_weight(wt, 0), bf(wt.permute(0, 2, 3, 1).reshape(128, 576)))
+    assert torch.equal(ops.pack_weight(wt, 1), bf(torch.flip(wt, (2, 3)).permute(1, 2, 3, 0).reshape(64, 9 * 128)))
+    wu = torch.randn(128, 64, 2, 2, device=DEV)
+    assert torch.equal(ops.pack_weight(wu, 2), bf(wu.permute(2, 3, 1, 0).reshape(256, 128)))
+    assert torch.equal(ops.pack_weight(wu, 3), bf(wu.permute(0, 2, 3, 1).reshape(128, 256)))
+
+
+def test_conv1(ops):
+    torch.manual_seed(4)
+    n, h, w = 2, 40, 44
+    img = torch.rand(n, 1, h, w, device=DEV)
+    w1 = torch.randn(64, 1, 3, 3, device=DEV).requires_grad_(True)
+    b1 = torch.randn(64, device=DEV).requires_grad_(True)
+    y = torch.empty(n, h - 2, w - 2, 64, dtype=torch.bfloat16, device=DEV)
+    ops.conv1_fwd(img, w1.detach(), b1.detach(), y)
+    pre = F.conv2d(img, w1, b1)
+    assert rel_l2(nchw(y), F.relu(pre)) < BF16_OUT_TOL
+    dy = bf(torch.randn(n, h - 2, w - 2, 64, device=DEV))
+    gw, gb = torch.autograd.grad(pre, (w1, b1), nchw(dy))
+    dw, db = torch.zeros(64, 9, device=DEV), torch.zeros(64, device=DEV)
+    ops.conv1_wgrad(img, dy, dw, db)
+    assert rel_l2(dw.view(64, 1, 3, 3), gw) < FP32_TOL and rel_l2(db, gb) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 12), (1, 8, 8, 128, 8), (2, 20, 20, 64, 8), (1, 24, 24, 256, 20), (1, 11, 11, 64, 6)])
+def test_pool_indices_and_skip_write_bit_exact(ops, case):
+    n, h, w, c, hu = case
+    torch.manual_seed(sum(case))
+    x = bf(torch.randn(n, h, w, c, device=DEV).clamp_min(0))        # post-ReLU: all-zero windows and ties abound
+    hp = h // 2
+    coff = int((hp - hu) * 0.5)
+    y = torch.empty(n, hp, hp, c, dtype=torch.bfloat16, device=DEV)
+    idx = torch.empty(n, hp, hp, c, dtype=torch.uint8, device=DEV)
+    cat = torch.zeros(n, hu, hu, 2 * c, dtype=torch.bfloat16, device=DEV)
+    ops.pool2x2_fwd(x, y, idx, cat[..., :c], coff)
+    rv, ri = F.max_pool2d(nchw(x), 2, 2, return_indices=True)
+    assert torch.equal(nchw(y), rv)                                  # values bit-exact
+    oy = torch.arange(hp, device=DEV).view(1, 1, hp, 1)
+    ox = torch.arange(hp, device=DEV).view(1, 1, 1, hp)
+    code = idx.permute(0, 3, 1, 2).long()
+    assert torch.equal((2 * oy + code // 2) * w + (2 * ox + code % 2), ri)   # ATen flat indices bit-exact
+    assert torch.equal(nchw(cat[..., :c]), F.pad(rv, (-coff,) * 4))          # crop_and_concat placement bit-exact
+    assert bool((cat[..., c:] == 0).all())
+    # backward: sum of the two producers, ReLU mask, scatter
+    dyp = bf(torch.randn(n, hp, hp, c, device=DEV))
+    dcat = bf(torch.randn(n, hu, hu, 2 * c, device=DEV))
+    dx = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=DEV)
+    ops.pool2x2_bwd(dyp, dcat[..., :c], coff, idx, y, dx)
+    xr = nchw(x).requires_grad_(True)
+    g = bf(nchw(dyp) + F.pad(nchw(dcat[..., :c]), (coff,) * 4)).float()
+    F.max_pool2d(F.relu(xr), 2, 2).backward(g)
+    assert torch.equal(nchw(dx), xr.grad)
+
+
+def test_pool_nan_propagates(ops):
+    x = torch.zeros(1, 2, 2, 64, dtype=torch.bfloat16, device=DEV)
+    x[0, 1, 0, 3] = float("nan")
+    x[0, 0, 1, 3] = 5.0
+    y = torch.empty(1, 1, 1, 64, dtype=torch.bfloat16, device=DEV)
+    idx = torch.empty(1, 1, 1, 64, dtype=torch.uint8, device=DEV)
+    ops.pool2x2_fwd(x, y, idx, None, 0)
+    rv, ri = F.max_pool2d(nchw(x), 2, 2, return_indices=True)
+    assert torch.isnan(y[0, 0, 0, 3]) and torch.isnan(rv[0, 3, 0, 0])
+    assert int(idx[0, 0, 0, 3]) == 2 and int(ri[0, 3, 0, 0]) == 2
+
+
+def test_head_fwd_bwd(ops):
+    torch.manual_seed(5)
+    n, h, w = 2, 36, 36
+    x = bf(torch.randn(n, h, w, 64, device=DEV).clamp_min(0))
+    wf = (torch.randn(2, 64, 1, 1, device=DEV) / 8).requires_grad_(True)
+    bfin = torch.randn(2, device=DEV).requires_grad_(True)
+    logits = torch.empty(n, 2, h, w, device=DEV)
+    am = torch.empty(n, h, w, dtype=torch.uint8, device=DEV)
+    ops.head_fwd(x, wf.detach(), bfin.detach(), logits, am)
+    xr = nchw(x).requires_grad_(True)
+    ref = F.conv2d(F.relu(xr), wf, bfin)
+    assert rel_l2(logits, ref) < 1e-4                                 # fp32 output
+    assert torch.equal(am.long(), (logits[:, 1] > logits[:, 0]).long())   # argmax rule: ties -> class 0
+    dl = torch.randn(n, 2, h, w, device=DEV)
+    gx, gw, gb = torch.autograd.grad(ref, (xr, wf, bfin), dl)
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros(2, 64, device=DEV), torch.zeros(2, device=DEV)
+    ops.head_bwd(x, wf.detach(), dl, dx, dw, db)
+    assert rel_l2(nchw(dx), gx) < BF16_OUT_TOL
+    assert rel_l2(dw.view(2, 64, 1, 1), gw) < 1e-3 and rel_l2(db, gb) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", [(1, 36, 36), (3, 40, 36), (2, 388, 388)])
+def test_losses_fwd_bwd(ops, case):
+    b, hp, l = case
+    torch.manual_seed(6)
+    for scale in (10.0, 150.0):                                      # N(0,10^2) and the net's real logit scale
+        z = (torch.randn(b, 2, hp, hp, device=DEV) * scale).requires_grad_(True)
+        lab = (torch.rand(b, l, l, device=DEV) > 0.6).long()
+        wm = 1 + 10 * torch.rand(b, l, l, device=DEV)
+        pad = (hp - l) // 2
+        zc = z[:, :, pad:pad + l, pad:pad + l]
+        ws = ops.loss_workspace(DEV)
+        for kind in (ops.LOSS_BCE, ops.LOSS_SOFTMAX_CE):
+            if kind == ops.LOSS_BCE:       # trainer.py:63-75 with the per-pixel weight
+                ref = F.binary_cross_entropy_with_logits(zc, torch.stack([1 - lab, lab], 1).float(), weight=wm.unsqueeze(1))
+                gs = 1.0 / (2 * b * l * l)
+            else:
+                ref = (F.cross_entropy(zc, lab, reduction="none") * wm).mean()
+                gs = 1.0 / (b * l * l)
+            (gz,) = torch.autograd.grad(ref, z)
+            for lt in (lab, lab.to(torch.uint8)):
+                out = torch.zeros(1, device=DEV)
+                dz = torch.zeros_like(z)
+                ops.loss_fwd_bwd(kind, z.detach(), lt, wm, dz, out, ws, gs)
+                assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())      # tolerance: fp32 sum order
+                assert rel_l2(dz, gz) < 1e-6
+
+
+def test_colsum_sgd(ops):
+    torch.manual_seed(7)
+    g = bf(torch.randn(3, 10, 12, 256, device=DEV))
+    out = torch.zeros(128, device=DEV)
+    ops.colsum(g[..., 128:], out)
+    assert rel_l2(out, g[..., 128:].float().sum((0, 1, 2))) < 1e-6
+    nel = 1000003
+    p = torch.randn(nel, device=DEV)
+    pr = torch.nn.Parameter(p.clone())
+    opt = torch.optim.SGD([pr], lr=1e-4, momentum=0.99)
+    buf = torch.zeros(nel, device=DEV)
+    gr = torch.randn(nel, device=DEV)
+    for step in range(3):
+        pr.grad = gr * (step + 1)
+        opt.step()
+        ops.sgd_momentum(p, gr * (step + 1), buf, 1e-4, 0.99, step == 0)
+    assert rel_l2(p, pr.detach()) < 1e-7
+    assert rel_l2(buf, opt.state[pr]["momentum_buffer"]) < 1e-7
+
+
+def test_bad_arguments_raise(ops):
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device=DEV)    # channels not a multiple of 64
+    y = torch.zeros(1, 6, 6, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        ops.conv3x3_fwd(x, torch.zeros(64, 9 * 48, dtype=torch.bfloat16, device=DEV), None, y)
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        ops.conv3x3_fwd(x, torch.zeros(64, 576, dtype=torch.bfloat16, device=DEV), None,
+                        torch.zeros(1, 5, 6, 64, dtype=torch.bfloat16, device=DEV))

@@ -1,0 +1,149 @@
+"""CPU: host-side logic of the drop-in (geometry, module surface, error behaviour, C ABI exports)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import unet_oracle as O
+from b200 import lib
+from b200.dist import bucket_bounds, partition
+from b200.geometry import Geometry, conv_flops_per_tile, crop_offset, input_size_compute
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_geometry_572():
+    g = Geometry(572)
+    assert g.out == 388
+    assert g.pool == {1: 284, 2: 140, 3: 68, 4: 32}
+    assert g.up == {4: 56, 3: 104, 2: 200, 1: 392}
+    assert g.coff == {4: -12, 3: -18, 2: -30, 1: -54}        # zero padding of the pooled skip (quirk 1)
+
+
+def test_geometry_crop_branch_and_errors():
+    g = Geometry(188)
+    assert g.out == 4 and g.coff == {4: 0, 3: 6, 2: 18, 1: 42}  # positive = centre crop
+    with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
+        Geometry(204)
+    with pytest.raises(RuntimeError):
+        Geometry(100)
+    for s in range(188, 700, 2):
+        ours = None
+        try:
+            ours = Geometry(s).out
+        except RuntimeError:
+            pass
+        assert ours == O.output_size(s), s
+
+
+def test_crop_offset_matches_reference_rule():
+    for ha in range(1, 40):
+        for hb in range(1, 40):
+            assert crop_offset(ha, hb) == int((ha - hb) * 0.5)
+
+
+def test_input_size_compute():
+    assert input_size_compute(388) == (388, 572, 388)
+    assert input_size_compute(512)[1:] == (700, 516)
+    assert input_size_compute(196)[1:] == (380, 196)
+    assert input_size_compute(4096)[1] == 4284
+
+
+def test_flop_table():
+    f = conv_flops_per_tile(572)
+    assert abs(sum(f.values()) / 1e9 - 300.86) < 0.05
+    assert abs(f["conv41e"] / 1e9 - 27.519) < 0.01
+
+
+def test_unet_module_surface():
+    from network import Unet
+    torch.manual_seed(0)
+    net = Unet()
+    sd = O.init_state_dict(0)
+    assert list(net.state_dict().keys()) == O.PARAM_NAMES
+    assert all(torch.equal(sd[k], v) for k, v in net.state_dict().items())   # same init as the reference
+    assert sum(p.numel() for p in net.parameters()) == 31030658
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        net(torch.zeros(1, 1, 188, 188))
+    a, b = torch.randn(1, 2, 8, 8), torch.randn(1, 3, 4, 4)
+    assert torch.equal(net.crop_and_concat(a, b), O.crop_and_concat(a, b))
+    a, b = torch.randn(1, 2, 32, 32), torch.randn(1, 3, 56, 56)
+    assert torch.equal(net.crop_and_concat(a, b), O.crop_and_concat(a, b))
+    with pytest.raises(RuntimeError):
+        net.crop_and_concat(torch.zeros(1, 1, 5, 5), torch.zeros(1, 1, 8, 8))
+    # state_dict round trip in the reference's .pth format
+    net2 = Unet()
+    net2.load_state_dict(net.state_dict())
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+
+
+def test_arena_layout_is_backward_ordered():
+    from network import Unet
+    st = Unet().engine.store
+    order = sorted(st.g_off, key=st.g_off.get)
+    assert order[0] == "finalconv.weight" and order[-1] == "conv11c.bias"
+    assert all(v % 64 == 0 for v in st.g_off.values())
+    assert st.total >= 31030658
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "unet_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|void|long long|const char\*)\s+(ub_[a-z0-9_]+)\s*\(", header, re.M))
+    handle = lib.load()
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/unet_b200.h but not exported"
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    assert handle.ub_version() == 1
+    assert b"no CUDA driver" in handle.ub_error_string(-3)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.conv1_fwd(torch.zeros(1, 1, 8, 8), torch.zeros(64, 1, 3, 3), torch.zeros(64), torch.zeros(1, 6, 6, 64))
+
+
+def test_partition_and_buckets():
+    for n in (121, 128, 7):
+        for w in (1, 2, 4, 8):
+            parts = [partition(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(e - s for s, e in parts) - min(e - s for s, e in parts) <= 1
+    ends = [100, 300, 1000, 1100, 5000]
+    b = bucket_bounds(5000, ends, 800)
+    assert b == [(0, 1000), (1000, 5000)]
+    assert bucket_bounds(5000, ends, 10 ** 9) == [(0, 5000)]
+
+
+def test_drop_in_functions_match_golden(golden_dir):
+    import functions
+    g = np.load(os.path.join(golden_dir, "class_balance.npz"))
+    assert np.array_equal(functions.class_balance(torch.from_numpy(g["lab"])).numpy(), g["w"])
+    m = functions.evaluation_metrics(torch.tensor([[1, 0], [1, 1]]), torch.tensor([[1, 1], [0, 1]]))
+    assert m.shape == (2, 1) and abs(m[0, 0] - 0.5) < 1e-12 and abs(m[1, 0] - 0.5) < 1e-12
+    assert functions.input_size_compute(torch.zeros(1, 1, 388, 388)) == (388, 572, 388)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_weighted_map_matches_reference():
+    import importlib.util
+    import functions
+    spec = importlib.util.spec_from_file_location("ref_functions", "/root/reference/functions.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(3)
+    lab = torch.zeros(2, 48, 48, dtype=torch.int64)
+    lab[0, 5:15, 5:20] = 1
+    lab[0, 22:40, 10:18] = 1
+    lab[0, 30:44, 30:45] = 1
+    lab[1, 8:40, 8:24] = 1
+    lab[1, 10:30, 30:44] = 1
+    assert torch.equal(functions.weighted_map(lab), ref.weighted_map(lab))
+    assert torch.equal(functions.class_balance(lab), ref.class_balance(lab))

@@ -1,0 +1,68 @@
+"""CPU: the oracle against the golden vectors produced from the reference itself
+(oracle/validate_against_reference.py), and -- when /root/reference is mounted -- against the
+reference directly."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import unet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def digest(g):
+    g = g.detach().double().flatten()
+    head = (g[:5].tolist() + [0.0] * 5)[:5]
+    return np.array([g.norm().item(), g.sum().item(), g.abs().max().item()] + head)
+
+
+@pytest.mark.parametrize("name", ["unet_S188_B1_seed0", "unet_S220_B1_seed1"])
+def test_oracle_reproduces_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    S, B, seed = int(g["S"]), int(g["B"]), int(g["seed"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state_dict(seed)
+    images, labels, weight = O.synthetic_batch(B, S, seed=int(g["data_seed"]))
+    logits = O.forward(sd, images)
+    np.testing.assert_allclose(logits.numpy(), g["logits0"], rtol=1e-5, atol=1e-4)
+    mom = {}
+    for step in range(2):
+        loss, _, grads = O.train_step(sd, mom, images, labels, weight)
+        assert abs(loss.item() - float(g[f"loss{step}"])) <= 1e-5 * abs(float(g[f"loss{step}"]))
+        d = np.stack([digest(grads[k]) for k in O.PARAM_NAMES])
+        ref = g[f"grad_digest{step}"]
+        np.testing.assert_allclose(d[:, 0], ref[:, 0], rtol=1e-4)           # per-parameter gradient norms
+        np.testing.assert_allclose(d[:, 2], ref[:, 2], rtol=1e-4)           # per-parameter max |g|
+    after = O.forward(sd, images)
+    np.testing.assert_allclose(after.detach().numpy(), g["logits_after2"], rtol=1e-4, atol=1e-3)
+
+
+def test_pool_tie_rule_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pool_ties.npz"))
+    v, i = O.pool_with_indices(torch.from_numpy(g["x"]))
+    assert np.array_equal(v.numpy(), g["v"]) and np.array_equal(i.numpy(), g["i"])
+
+
+def test_output_sizes_and_crop_rule():
+    assert [O.output_size(s) for s in (188, 220, 252, 572, 204)] == [4, 36, 68, 388, None]
+    assert O.crop_offset(32, 56) == -12 and O.crop_offset(284, 392) == -54 and O.crop_offset(20, 8) == 6
+    assert O.crop_offset(5, 8) == -1  # truncation toward zero -> torch.cat then raises
+    with pytest.raises(RuntimeError):
+        O.crop_and_concat(torch.zeros(1, 1, 5, 5), torch.zeros(1, 1, 8, 8))
+
+
+def test_init_std_quirk():
+    sd = O.init_state_dict(0)
+    assert abs(sd["conv12c.weight"].std().item() - 2 / (576 ** 0.5)) < 2e-3   # 2/sqrt(N), not sqrt(2/N)
+    assert abs(sd["conv11c.weight"].std().item() - 2 ** 0.5) < 0.15
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted (GPU box)")
+def test_oracle_bit_equal_to_reference():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "validate_against_reference.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
