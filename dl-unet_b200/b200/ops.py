@@ -92,6 +92,10 @@ def set_tuning(bn=0, bw=0, bh=0, splits=0):
     _lib.load().ub_set_tuning(bn, bw, bh, splits)
 
 
+def set_option(key, value):
+    _lib.load().ub_set_option(int(key), int(value))
+
+
 def device_error():
     code = C.c_uint(0)
     rc = _lib.load().ub_device_error(C.byref(code))
@@ -258,9 +262,9 @@ def naive_conv3x3(x, w_fwd, bias, relu):
     return y
 
 
-def probe_run(cap_rows=128):
+def probe_run(cap_rows=128, which=0):
     buf = (C.c_float * (cap_rows * 6))(*([-1.0] * (cap_rows * 6)))
-    _chk(_lib.load().ub_probe_run(0, buf, cap_rows * 6), "probe")
+    _chk(_lib.load().ub_probe_run(which, buf, cap_rows * 6), "probe")
     rows = []
     for i in range(cap_rows):
         r = list(buf[i * 6:(i + 1) * 6])

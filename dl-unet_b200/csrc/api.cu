@@ -16,12 +16,14 @@
 #include "igemm.cuh"
 #include "probe.cuh"
 #include "wgrad.cuh"
+#include "wgrad3.cuh"
 
 using namespace ub;
 
 namespace {
 
 int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
+int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -65,19 +67,21 @@ int check_view(const ub_tensor4* t) {
 
 // 4-D NHWC bf16 map over a (possibly strided) view: dims {c, w, h, n}, box {64, bw, bh, 1}, SWIZZLE_128B.
 int make_map4(CUtensorMap* m, void* ptr, int c, int w, int h, int n, long long sx, long long sy, long long sn,
-              int bw, int bh) {
+              int bw, int bh, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return UB_E_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
+  // the swizzle span equals the box row: 64 channels = 128 B, 32 channels = 64 B
+  const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
 }
-int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh) {
-  return make_map4(m, t->ptr, t->c, t->w, t->h, t->n, t->sx, t->sy, t->sn, bw, bh);
+int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh, int box_c = 64) {
+  return make_map4(m, t->ptr, t->c, t->w, t->h, t->n, t->sx, t->sy, t->sn, bw, bh, box_c);
 }
 // 2-D K-major weight matrix [rows][k] bf16, box {64, box_rows}
 int make_map2(CUtensorMap* m, const void* ptr, long long k, long long rows, int box_rows) {
@@ -210,6 +214,54 @@ void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) 
   P.out_H = H;
 }
 
+int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+  Wgrad3Params P;
+  memset(&P, 0, sizeof(P));
+  // chunk = 16 x KH output pixels; pick the KH that pads the image least (ties: larger chunk)
+  long long best = -1;
+  for (int kh = 8; kh >= 2; kh >>= 1) {
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (best < 0 || padded < best) best = padded;
+  }
+  for (int kh = 8; kh >= 2; kh >>= 1) {  // largest chunk within 6 % of the least padding
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (padded * 100 <= best * 106) {
+      P.KH = kh;
+      break;
+    }
+  }
+  P.chunks_x = (dy->w + 15) / 16;
+  P.chunks_y = (dy->h + P.KH - 1) / P.KH;
+  P.n_img = dy->n;
+  P.Cout = dy->c;
+  P.Cin = x->c;
+  P.m_tiles = (dy->c + 127) / 128;
+  P.ci_tiles = x->c / 32;
+  P.fuse_s = g_wgrad_mode != 1;
+  P.dw = dw;
+  const long long items = (long long)P.m_tiles * P.ci_tiles;
+  const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
+  long long splits = (3ll * num_sms() + items - 1) / items;
+  if (splits > chunks / 4) splits = chunks / 4;
+  if (splits < 1) splits = 1;
+  if (g_force_splits > 0) splits = g_force_splits;
+  P.splits = (int)splits;
+  int e;
+  if ((e = make_map4(&P.g_map, dy, 16, P.KH, 64))) return e;
+  if ((e = make_map4(&P.x_map, x, 18, P.KH + 2, 32))) return e;
+  P.nstage = Wgrad3Cfg::nstage(P.KH);
+  P.stage_bytes = Wgrad3Cfg::stage_bytes(P.KH);
+  P.g_bytes = Wgrad3Cfg::g_bytes(P.KH);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  wgrad3_kernel<<<(int)(items * splits), 256, Wgrad3Cfg::smem_bytes(P.KH), st>>>(P);
+  return (int)cudaGetLastError();
+}
+
 int set_mask(IgemmParams& P, const ub_tensor4* relu_src, const ub_tensor4* dx) {
   P.mask = nullptr;
   if (relu_src == nullptr) return 0;
@@ -250,6 +302,10 @@ int ub_device_error(unsigned int* out_code) {
   *out_code = v;
   if (e != cudaSuccess) return (int)e;
   return (int)e2;
+}
+
+void ub_set_option(int key, int value) {
+  if (key == 1) g_wgrad_mode = value;
 }
 
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits) {
@@ -337,6 +393,10 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
   if ((e = check_view(x)) || (e = check_view(dy))) return e;
   if (!dw_packed || !aligned16(dw_packed)) return dw_packed ? UB_E_ALIGN : UB_E_ARG;
   if (dy->n != x->n || dy->h != x->h - 2 || dy->w != x->w - 2) return UB_E_SHAPE;
+  // measured on B200 (profiles/r1_layer_table.log): the haloed-patch kernel wins while the input has few
+  // channels (dY is re-read Cin/32 times), the tap-per-CTA kernel wins for the deep, spatially small layers
+  const bool use3 = g_wgrad_mode == 3 ? (x->c <= 128 || (x->c <= 256 && dy->w >= 160)) : (g_wgrad_mode != 0);
+  if (use3) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
   WgradParams P;
   memset(&P, 0, sizeof(P));
   pick_kpatch(dy->w, dy->h, P.KW, P.KH);
@@ -486,8 +546,8 @@ int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
   const long long total = (long long)n * (h - 2) * (w_ - 2) * 8;
-  long long blocks = (total + 256ll * 32 - 1) / (256ll * 32);
-  if (blocks > 2ll * num_sms()) blocks = 2ll * num_sms();
+  long long blocks = (total + 256ll * 16 - 1) / (256ll * 16);
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
   if (blocks < 1) blocks = 1;
   conv1_wgrad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, dw, db, n, h, w_);
   return (int)cudaGetLastError();
@@ -618,9 +678,46 @@ int ub_naive_conv3x3(const void* x, const void* w_fwd, const float* bias, float*
 // Probe driver: generates integer-valued operands, runs probe_kernel over a list of
 // (mode, shift, pitch, base_offset) variants, checks D against the "absolute-address
 // swizzle" hypothesis on the host.  out rows: {mode, shift, pitch, use_bo, max_abs_err, n_bad}.
+static int probe_mma_rate(float* out_host, int cap) {
+  struct V { int n, a_mn, b_mn, b_layout, b_lbo, b_sbo, m; };
+  const V vars[] = {
+      {256, 0, 0, 2, 16, 1024, 64}, {128, 0, 0, 2, 16, 1024, 64}, {64, 0, 0, 2, 16, 1024, 64}, {32, 0, 0, 2, 16, 1024, 64},
+      {16, 0, 0, 2, 16, 1024, 128}, {112, 0, 0, 2, 16, 1024, 128}, {160, 0, 0, 2, 16, 1024, 128},
+      {256, 0, 0, 2, 16, 1024}, {128, 0, 0, 2, 16, 1024}, {64, 0, 0, 2, 16, 1024}, {96, 0, 0, 2, 16, 1024},
+      {256, 1, 1, 2, 8192, 1024}, {128, 1, 1, 2, 8192, 1024}, {64, 1, 1, 2, 8192, 1024},
+      {256, 1, 0, 2, 16, 1024}, {256, 0, 1, 2, 8192, 1024}, {64, 1, 0, 2, 16, 1024}, {64, 0, 1, 2, 8192, 1024},
+      {96, 1, 1, 4, 64, 512}, {96, 1, 1, 4, 4096, 512}, {32, 1, 1, 4, 64, 512}, {96, 1, 1, 2, 128, 1024},
+      {192, 1, 1, 2, 128, 1024}, {96, 0, 1, 4, 64, 512},
+  };
+  const int nv = (int)(sizeof(vars) / sizeof(vars[0]));
+  long long* dout = nullptr;
+  cudaError_t ce;
+  if ((ce = cudaMalloc(&dout, 16)) != cudaSuccess) return (int)ce;
+  const int smem = 131072 + 256 + 1024;
+  cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int nout = 0;
+  for (int i = 0; i < nv && (nout + 1) * 6 <= cap; ++i) {
+    MmaRateParams P;
+    P.n = vars[i].n; P.a_mn = vars[i].a_mn; P.b_mn = vars[i].b_mn; P.b_layout = vars[i].b_layout;
+    P.b_lbo = vars[i].b_lbo; P.b_sbo = vars[i].b_sbo; P.iters = 2000; P.out = dout; P.m = vars[i].m ? vars[i].m : 128;
+    probe_mma_rate_kernel<<<1, 128, smem>>>(P);
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return (int)ce;
+    long long h[2];
+    cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
+    float* o = out_host + nout * 6;
+    o[0] = (float)vars[i].n; o[1] = (float)vars[i].a_mn; o[2] = (float)vars[i].b_mn; o[3] = (float)vars[i].b_layout;
+    o[4] = (float)((double)h[0] / (double)h[1]);  // cycles per MMA
+    o[5] = (float)(vars[i].m ? vars[i].m : 128);
+    ++nout;
+  }
+  cudaFree(dout);
+  return 0;
+}
+
 int ub_probe_run(int which, float* out_host, int cap) {
-  (void)which;
   if (!out_host || cap < 6) return UB_E_ARG;
+  if (which == 1) return probe_mma_rate(out_host, cap);
   const int RA = 320;
   std::vector<__nv_bfloat16> ha(RA * 64), hb(64 * 64);
   std::vector<float> fa(RA * 64), fb(64 * 64);

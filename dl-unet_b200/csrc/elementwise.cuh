@@ -35,15 +35,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                         int n_img, int H, int W) {
-  __shared__ float sw[64 * 9 + 64];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) sw[576 + i] = b[i];
-  __syncthreads();
+  // blockDim and the grid stride are multiples of 8, so a thread keeps its channel octet for the whole
+  // loop: its 8 x 9 weights and 8 biases live in registers (no shared-memory traffic in the loop)
+  const int oct = threadIdx.x & 7;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = __ldg(b + oct * 8 + c);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (oct * 8 + c) * 9 + t);
+  }
   const int Ho = H - 2, Wo = W - 2;
   const long long total = (long long)n_img * Ho * Wo * 8;
   for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
        gid += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(gid & 7);
     long long pix = gid >> 3;
     const int ox = (int)(pix % Wo);
     pix /= Wo;
@@ -58,10 +63,9 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float* wc = sw + (oct * 8 + c) * 9;
-      float a = sw[576 + oct * 8 + c];
+      float a = br[c];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(in[t], wc[t], a);
+      for (int t = 0; t < 9; ++t) a = fmaf(in[t], wr[c][t], a);
       o[c] = fmaxf(a, 0.0f);
     }
     *reinterpret_cast<uint4*>(y + (gid >> 3) * 64 + oct * 8) = pack8(o);

@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop (all values stay warp-uniform, so ptxas keeps descriptors and
+    // coordinates in uniform registers); one elected lane issues the copies.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -125,11 +127,14 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
           const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1, 1);
-            uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            uint8_t* sb = sa + C::A_BYTES;
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)p.a_bytes + (uint32_t)C::B_BYTES);
-            tma_load_4d(sa, am, &full[stage], kc * 64, ax, ay, img);
-            tma_load_2d(sb, &p.b_map, &full[stage], (tap * p.kchunks + kc) * 64, n0);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * C::STAGE_BYTES;
+              uint8_t* sb = sa + C::A_BYTES;
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)p.a_bytes + (uint32_t)C::B_BYTES);
+              tma_load_4d(sa, am, &full[stage], kc * 64, ax, ay, img);
+              tma_load_2d(sb, &p.b_map, &full[stage], (tap * p.kchunks + kc) * 64, n0);
+            }
+            __syncwarp();
             if (++stage == C::NSTAGE) {
               stage = 0;
               phase ^= 1;
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -158,18 +163,21 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = umma_smem_desc(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4 -> +2)
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4 -> +2)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (ki == k_iters - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == C::NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
       }
     }
   } else if (warp >= 4) {

@@ -89,4 +89,66 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
   }
 }
 
+// MMA issue-rate probe: `iters` x 4 back-to-back tcgen05.mma on operands that already sit in shared
+// memory (contents irrelevant), one commit at the end; reports SM cycles.  Separates the tensor
+// pipe + smem operand fetch rate from everything TMA / L2 related.
+struct MmaRateParams {
+  int m;            // UMMA M (64 or 128)
+  int n;            // UMMA N
+  int a_mn, b_mn;   // 0 = K-major, 1 = MN-major
+  int b_layout;     // 2 = SW128, 4 = SW64
+  int b_lbo, b_sbo; // bytes
+  int iters;
+  long long* out;   // [2]: cycles, n_mma
+};
+
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(const MmaRateParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;            // 64 KB
+  uint8_t* sb = smem + 65536;    // 64 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 131072);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 131072 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(p.m, p.n, p.a_mn, p.b_mn);
+    const long long t0 = clock64();
+    for (int it = 0; it < p.iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = p.a_mn ? umma_smem_desc(smem_u32(sa) + k * 2048, 8192, 1024, 0, 2)
+                                   : umma_smem_desc(smem_u32(sa) + k * 32, 16, 1024, 0, 2);
+        const uint64_t bd = p.b_mn ? umma_smem_desc(smem_u32(sb) + k * (p.b_layout == 2 ? 2048 : 1024), p.b_lbo, p.b_sbo, 0, p.b_layout)
+                                   : umma_smem_desc(smem_u32(sb) + k * 32, 16, 1024, 0, 2);
+        umma_bf16(tmem + (k & 1) * 256, ad, bd, idesc, 1);
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0, 13);
+    const long long t1 = clock64();
+    p.out[0] = t1 - t0;
+    p.out[1] = (long long)p.iters * 4;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace ub

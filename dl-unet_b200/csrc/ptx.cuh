@@ -165,14 +165,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 //   MN-major (rows = K index, 128 B = 64 M/N elems):  SBO = bytes between 8-row K groups,
 //                                                     LBO = bytes between 64-element M/N blocks
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t base_offset = 0) {
+                                                   uint32_t base_offset = 0, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;                           // descriptor version (Blackwell)
   d |= (uint64_t)(base_offset & 7) << 49;
-  d |= 2ull << 61;                           // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;               // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate.

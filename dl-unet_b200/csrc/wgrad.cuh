@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
 
   if (n_iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      {
         const CUtensorMap* am = &p.a_map[p.tap_amap[tap]];
         const int dx = p.tap_dx[tap], dy = p.tap_dy[tap];
         const uint32_t tx_bytes = (uint32_t)(m_valid_blocks + BN / 64) * 8192u;
@@ -107,14 +107,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           const int img = r / p.chunks_y;
           const int x0 = cx * p.KW, y0 = cy * p.KH;
           mbar_wait(&empty[stage], phase ^ 1, 5);
-          uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          for (int b = 0; b < m_valid_blocks; ++b)
-            tma_load_4d(sa + b * 8192, am, &full[stage], mt * 128 + b * 64, x0, y0, img);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            for (int b = 0; b < m_valid_blocks; ++b)
+              tma_load_4d(sa + b * 8192, am, &full[stage], mt * 128 + b * 64, x0, y0, img);
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b)
-            tma_load_4d(sb + b * 8192, &p.b_map, &full[stage], nt * BN + b * 64, x0 + dx, y0 + dy, img);
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_4d(sb + b * 8192, &p.b_map, &full[stage], nt * BN + b * 64, x0 + dx, y0 + dy, img);
+          }
+          __syncwarp();
           if (++stage == C::NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -131,20 +134,23 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixels (K) per MMA = two 8-row groups = 2048 B
-            const uint64_t adesc = umma_smem_desc(sa + k * 2048, 8192, 1024);
-            const uint64_t bdesc = umma_smem_desc(sb + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // 16 pixels (K) per MMA = two 8-row groups = 2048 B
+              const uint64_t adesc = umma_smem_desc(sa + k * 2048, 8192, 1024);
+              const uint64_t bdesc = umma_smem_desc(sb + k * 2048, 8192, 1024);
+              umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (i == n_iters - 1) umma_commit(tfull);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == C::NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tfull);
       }
     } else if (warp >= 4) {
       const int q = warp - 4;

@@ -11,6 +11,10 @@ for p in (os.path.join(ROOT, "dl-unet_b200"), os.path.join(ROOT, "oracle"), ROOT
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # the torch references in the GPU tests must be true fp32 (cuDNN / cuBLAS default to TF32 for convs)
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):

@@ -52,6 +52,12 @@ def sec_probe():
         print(f"  {int(r[0])}    {int(r[1]):2d}    {int(r[2]):2d}     {int(r[3])}      {r[4]:.3e}  {int(r[5])}")
 
 
+def sec_mma_rate():
+    print("   N a_mn b_mn b_layout   M    cycles/MMA   (nominal = N/2 for M=128)")
+    for r in ops.probe_run(64, which=1):
+        print(f" {int(r[0]):4d}   {int(r[1])}    {int(r[2])}      {int(r[3])}    {int(r[5]):5d}   {r[4]:8.1f}")
+
+
 CONV_SHAPES = [
     (1, 20, 20, 64, 64), (2, 30, 30, 128, 128), (1, 18, 34, 64, 256), (1, 12, 12, 256, 512),
     (3, 10, 10, 128, 64), (1, 66, 66, 64, 128), (1, 9, 9, 1024, 1024), (2, 140, 140, 64, 64),
@@ -126,6 +132,37 @@ def sec_conv_wgrad():
         ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
         torch.cuda.synchronize()
         report(f"conv_wgrad {n, h, w, cin, cout}", dw, ref)
+
+
+def sec_wgrad_modes():
+    """3x3 wgrad: tap-per-CTA kernel (mode 0) vs haloed-patch kernel without (1) / with (2) fused s taps."""
+    torch.manual_seed(2)
+    shapes = CONV_SHAPES + [(16, 72, 72, 64, 64), (16, 72, 72, 128, 128), (4, 200, 200, 256, 128), (16, 30, 30, 1024, 1024)]
+    for (n, h, w, cin, cout) in shapes:
+        ho, wo = h - 2, w - 2
+        x = torch.randn(n, cin, h, w, device=DEV)
+        dy = torch.randn(n, cout, ho, wo, device=DEV)
+        wt = torch.zeros(cout, cin, 3, 3, device=DEV, requires_grad=True)
+        F.conv2d(bf(x).float(), wt).backward(bf(dy).float())
+        ref = wt.grad
+        xh, dyh = nhwc(x), nhwc(dy)
+        for mode in (0, 1, 2):
+            ops.set_option(1, mode)
+            dwp = torch.zeros(cout, 9 * cin, dtype=torch.float32, device=DEV)
+            ops.conv3x3_wgrad(xh, dyh, dwp)
+            dw = torch.empty_like(ref)
+            ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.conv3x3_wgrad(xh, dyh, dwp)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 5 * 1e3
+            fl = 2.0 * n * ho * wo * cout * cin * 9
+            report(f"wgrad mode {mode} {n, h, w, cin, cout} {us:8.1f} us {fl / us / 1e6:7.1f} TF/s", dw, ref)
+    ops.set_option(1, 2)
 
 
 UP_SHAPES = [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256)]
@@ -301,7 +338,7 @@ def sec_elementwise():
 
 SECTIONS = {
     "probe": sec_probe, "conv_fwd": sec_conv_fwd, "conv_dgrad": sec_conv_dgrad, "conv_wgrad": sec_conv_wgrad,
-    "upconv": sec_upconv, "elementwise": sec_elementwise,
+    "upconv": sec_upconv, "elementwise": sec_elementwise, "wgrad_modes": sec_wgrad_modes, "mma_rate": sec_mma_rate,
 }
 
 if __name__ == "__main__":

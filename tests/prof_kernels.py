@@ -1,0 +1,44 @@
+"""Kernel micro-benchmarks for ncu: python tests/prof_kernels.py <case> ; cases: wg52 (conv52c wgrad),
+wg12 (conv12c wgrad), fw12 (conv12c fwd), fw42 (conv42c fwd), wg22 (conv22c wgrad)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
+import torch  # noqa: E402
+from b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+CASES = {"wg52": (16, 30, 1024, 1024), "wg12": (16, 570, 64, 64), "wg22": (16, 282, 128, 128),
+         "fw12": (16, 570, 64, 64), "fw42": (16, 66, 512, 512), "fw22": (16, 282, 128, 128)}
+case = sys.argv[1]
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+n, h, cin, cout = CASES[case]
+torch.manual_seed(0)
+x = torch.randn(n, h, h, cin, device=DEV).to(torch.bfloat16)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if case.startswith("wg"):
+    dy = torch.randn(n, h - 2, h - 2, cout, device=DEV).to(torch.bfloat16)
+    dwp = torch.zeros(cout, 9 * cin, device=DEV)
+    ops.set_option(1, mode)
+    ops.conv3x3_wgrad(x, dy, dwp)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.conv3x3_wgrad(x, dy, dwp)
+    e1.record()
+else:
+    w = torch.randn(cout, 9 * cin, device=DEV).to(torch.bfloat16) / 30
+    b = torch.zeros(cout, device=DEV)
+    y = torch.empty(n, h - 2, h - 2, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_fwd(x, w, b, y)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.conv3x3_fwd(x, w, b, y)
+    e1.record()
+torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / reps * 1e3
+fl = 2.0 * n * (h - 2) ** 2 * cin * cout * 9
+print(f"{case} mode={mode}: {us:.1f} us  {fl / us / 1e6:.1f} TF/s")

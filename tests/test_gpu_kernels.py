@@ -137,7 +137,7 @@ def test_conv1(ops):
     assert rel_l2(dw.view(64, 1, 3, 3), gw) < FP32_TOL and rel_l2(db, gb) < FP32_TOL
 
 
-@pytest.mark.parametrize("case", [(2, 16, 16, 64, 12), (1, 8, 8, 128, 8), (2, 20, 20, 64, 8), (1, 24, 24, 256, 20), (1, 11, 11, 64, 6)])
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 12), (1, 8, 8, 128, 8), (2, 20, 20, 64, 8), (1, 24, 24, 256, 20), (1, 11, 11, 64, 7)])
 def test_pool_indices_and_skip_write_bit_exact(ops, case):
     n, h, w, c, hu = case
     torch.manual_seed(sum(case))
