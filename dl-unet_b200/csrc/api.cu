@@ -14,6 +14,7 @@
 
 #include "elementwise.cuh"
 #include "igemm.cuh"
+#include "igemm2.cuh"
 #include "probe.cuh"
 #include "wgrad.cuh"
 #include "wgrad3.cuh"
@@ -23,6 +24,7 @@ using namespace ub;
 namespace {
 
 int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
+int g_igemm2_mode = 1;  // 0: never use the haloed-patch conv kernel, 1: auto (wide shallow layers), 2: whenever legal
 int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -214,6 +216,83 @@ void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) 
   P.out_H = H;
 }
 
+template <int BN, int MT>
+int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  igemm2_kernel<BN, MT><<<grid, 384, smem_bytes, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+// Haloed-patch 3x3 conv (fwd: base_off 0, dgrad: base_off -2).  Returns 1 if the shape is not eligible.
+bool igemm2_eligible(const ub_tensor4* in, const ub_tensor4* out) {
+  if (g_igemm2_mode == 0) return false;
+  if (in->c > 256 || out->c > 256) return false;
+  if (g_igemm2_mode == 1 && out->w < 96) return false;
+  return true;
+}
+
+int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const ub_tensor4* out, int relu,
+                  const ub_tensor4* relu_src, int base_off, cudaStream_t st) {
+  Igemm2Params P;
+  memset(&P, 0, sizeof(P));
+  const int K = in->c, N = out->c;
+  const int BN = (N % 128 == 0) ? 128 : 64;
+  P.kchunks = K / 64;
+  P.n_tiles_n = N / BN;
+  const int b_slot = BN * 128;
+  const int limit = 232448 - 1024 /*align*/ - 1024 /*barriers*/ - 2 * 16384 /*epilogue staging*/;
+  const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
+  const int nb_stat = 9 * P.kchunks;
+  P.stationary = (P.n_tiles_n == 1 && nb_stat <= IG2_MAX_B && nb_stat * b_slot + 2 * a_slot1 <= limit) ? 1 : 0;
+  int MT;
+  if (P.stationary) {
+    MT = 1;
+    P.a_slot_bytes = a_slot1;
+    P.n_b = nb_stat;
+    P.n_a = (limit - P.n_b * b_slot) / a_slot1;
+    if (P.n_a > IG2_MAX_A) P.n_a = IG2_MAX_A;
+  } else {
+    MT = (BN == 128) ? 2 : 1;   // <64,2> is never needed by this network
+    P.a_slot_bytes = MT == 2 ? a_slot2 : a_slot1;
+    P.n_a = 2;
+    P.n_b = (limit - P.n_a * P.a_slot_bytes) / b_slot;
+    if (P.n_b > 24) P.n_b = 24;
+  }
+  P.tiles_x = (out->w + 8 * MT - 1) / (8 * MT);
+  P.tiles_y = (out->h + 15) / 16;
+  P.n_img = out->n;
+  P.base_off = base_off;
+  P.bias = bias;
+  P.relu = relu;
+  P.out_W = out->w;
+  P.out_H = out->h;
+  P.mask = nullptr;
+  int e;
+  if (relu_src) {
+    if ((e = check_view(relu_src))) return e;
+    if (relu_src->n != out->n || relu_src->h != out->h || relu_src->w != out->w || relu_src->c != out->c) return UB_E_SHAPE;
+    P.mask = reinterpret_cast<const __nv_bfloat16*>(relu_src->ptr);
+    P.mask_sn = relu_src->sn;
+    P.mask_sy = relu_src->sy;
+    P.mask_sx = relu_src->sx;
+  }
+  if ((e = make_map4(&P.a_map, in, 8 * MT + 2, 18))) return e;
+  if ((e = make_map2(&P.b_map, w, 9ll * K, N, BN))) return e;
+  if ((e = make_map4(&P.o_map, out, 8, 16))) return e;
+  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 1024 + 1024;
+  if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
+  if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
+  if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
+  return UB_E_SHAPE;
+}
+
 int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
   Wgrad3Params P;
   memset(&P, 0, sizeof(P));
@@ -306,6 +385,7 @@ int ub_device_error(unsigned int* out_code) {
 
 void ub_set_option(int key, int value) {
   if (key == 1) g_wgrad_mode = value;
+  if (key == 2) g_igemm2_mode = value;
 }
 
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits) {
@@ -335,6 +415,7 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
   if ((e = check_view(x)) || (e = check_view(y))) return e;
   if (!w_fwd || !aligned16(w_fwd) || (bias && !aligned16(bias))) return w_fwd ? UB_E_ALIGN : UB_E_ARG;
   if (y->n != x->n || y->h != x->h - 2 || y->w != x->w - 2 || y->h <= 0 || y->w <= 0) return UB_E_SHAPE;
+  if (igemm2_eligible(x, y)) return launch_igemm2(x, w_fwd, bias, y, relu, nullptr, 0, (cudaStream_t)stream);
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
@@ -364,6 +445,7 @@ int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4
   if ((e = check_view(dy)) || (e = check_view(dx))) return e;
   if (!w_dgrad || !aligned16(w_dgrad)) return w_dgrad ? UB_E_ALIGN : UB_E_ARG;
   if (dx->n != dy->n || dx->h != dy->h + 2 || dx->w != dy->w + 2) return UB_E_SHAPE;
+  if (igemm2_eligible(dy, dx)) return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream);
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;

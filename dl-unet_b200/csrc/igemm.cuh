@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     // --------------------------------------------------------- MMA issuer
     {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t hiD = umma_desc_hi(1024);
+      const uint32_t loA0 = umma_desc_lo(smem_u32(smem), 16), loB0 = umma_desc_lo(smem_u32(smem) + C::A_BYTES, 16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -159,15 +161,13 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(sb, 16, 1024);
           if (elect_one()) {
+            const uint32_t so = stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4 -> +2)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 2 * k), umma_desc(hiD, loB0 + so + 2 * k), idesc,
+                        (ki > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty[stage]);
             if (ki == k_iters - 1) umma_commit(&tfull[acc]);

@@ -1,0 +1,341 @@
+// 3x3 convolution forward / data-gradient kernel for the wide, shallow layers (levels 1-2 of the
+// U-Net): "haloed patch + shifted windows", optionally weight-stationary.
+//
+// igemm_kernel re-loads the 128-pixel activation tile once per tap (9 x 16 KB per 64 input channels)
+// and the weight tile once per pixel tile; for N <= 128 output channels that is 110-190 B/clk/SM of
+// L2->SM traffic against ~50 the chip sustains, so those layers run at 20-40 % of the tensor peak.
+// Here one TMA box brings the (8*MT+2) x 18 pixel patch (output tile 8*MT x 16 plus the 1-pixel halo on
+// each side, 64 channels, SWIZZLE_128B) and ALL NINE taps read it: tap (r, s) is a row offset
+// (r*P + s)*128 B of the K-major A descriptor, the 8-row groups of the M = 128 tile are the 16 patch
+// rows (SBO = P*128 B).  UMMA swizzles on absolute smem address bits (ub_probe_run), so this is legal.
+// Weights: if all 9*K/64 weight slabs of the layer fit in shared memory next to two patches they are
+// loaded ONCE per CTA (weight-stationary, persistent over tiles); otherwise they stream through a ring
+// and each slab is used for MT = 2 adjacent pixel sub-tiles.
+//   fwd  : taps read x[y0 + r, x0 + s]           (base offset 0)
+//   dgrad: taps read dy[y0 + r - 2, x0 + s - 2]  (base offset -2, TMA zero fill = the padding), weights
+//          pre-rotated by ub_pack_weight mode 1; optional fused ReLU-backward mask in the epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+struct alignas(64) Igemm2Params {
+  CUtensorMap a_map;  // input view, box {64, 8*MT+2, 18, 1}
+  CUtensorMap b_map;  // packed weights [N][9*K], box {64, BN}
+  CUtensorMap o_map;  // output view, box {64, 8, 16, 1}
+  int kchunks;
+  int tiles_x, tiles_y, n_img, n_tiles_n;
+  int base_off;  // 0 or -2
+  int n_a, n_b, a_slot_bytes, stationary;
+  const float* bias;
+  int relu;
+  const __nv_bfloat16* mask;
+  long long mask_sn, mask_sy, mask_sx;
+  int out_W, out_H;
+};
+
+constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
+  constexpr int P = 8 * MT + 2;          // patch width in pixels
+  constexpr int B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = 2 * MT * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "tmem");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.n_a * p.a_slot_bytes;
+  uint8_t* epi = sB + p.n_b * B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(epi + 2 * 16384);
+  uint64_t* a_empty = a_full + IG2_MAX_A;
+  uint64_t* b_full = a_empty + IG2_MAX_A;
+  uint64_t* b_empty = b_full + IG2_MAX_B;
+  uint64_t* tfull = b_empty + IG2_MAX_B;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.o_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.n_a; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.n_b; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  const int kchunks = p.kchunks;
+  const uint32_t a_bytes = (uint32_t)P * 18u * 128u;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (warp-uniform loop)
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    bool first = true;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles_n;
+      int mt = t / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int x0 = tx * 8 * MT + p.base_off, y0 = ty * 16 + p.base_off, n0 = nt * BN;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&a_empty[as], aph ^ 1, 20);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[as], a_bytes);
+          tma_load_4d(sA + as * p.a_slot_bytes, &p.a_map, &a_full[as], kc * 64, x0, y0, img);
+        }
+        __syncwarp();
+        if (++as == p.n_a) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (p.stationary) {
+          if (first) {
+            if (elect_one()) {
+              for (int tap = 0; tap < 9; ++tap) {
+                const int slot = kc * 9 + tap;
+                mbar_arrive_expect_tx(&b_full[slot], (uint32_t)B_BYTES);
+                tma_load_2d(sB + slot * B_BYTES, &p.b_map, &b_full[slot], (tap * kchunks + kc) * 64, n0);
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1, 21);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_BYTES);
+              tma_load_2d(sB + bs * B_BYTES, &p.b_map, &b_full[bs], (tap * kchunks + kc) * 64, n0);
+            }
+            __syncwarp();
+            if (++bs == p.n_b) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer (warp-uniform loop)
+    // Issue-side cost per MMA group must stay well below the tensor time of the group (4 x 54.5 clk for
+    // N = 64): descriptors are (constant high word, low word = base + immediate), the tap loop is fully
+    // unrolled, and a resident (stationary) weight slab is never waited on again.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    const uint32_t hiA = umma_desc_hi(P * 128), hiB = umma_desc_hi(1024);
+    const uint32_t loA0 = umma_desc_lo(smem_u32(sA), 16), loB0 = umma_desc_lo(smem_u32(sB), 16);
+    const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int it = 0;
+    bool resident = false;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1, 22);
+      const uint32_t d0 = tmem_base + acc * MT * BN;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&a_full[as], aph, 23);
+        const uint32_t loA = loA0 + as * a_slot16;
+        if (p.stationary) {
+          if (!resident)
+            for (int tap = 0; tap < 9; ++tap) mbar_wait(&b_full[kc * 9 + tap], 0, 24);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t loB = loB0 + kc * 9 * (B_BYTES >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t aoff = (((tap / 3) * P + (tap % 3) + 8 * sub) * 128 + k * 32) >> 4;
+                  const uint32_t boff = (tap * B_BYTES + k * 32) >> 4;
+                  umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + boff), idesc,
+                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(&a_empty[as]);
+            if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph, 24);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t loB = loB0 + bs * (B_BYTES >> 4);
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t aoff = (((tap / 3) * P + (tap % 3) + 8 * sub) * 128 + k * 32) >> 4;
+                  umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + 2 * k), idesc,
+                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit(&b_empty[bs]);
+              if (tap == 8) {
+                umma_commit(&a_empty[as]);
+                if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+              }
+            }
+            __syncwarp();
+            if (++bs == p.n_b) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+        if (++as == p.n_a) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      resident = true;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------------------------ epilogue
+    // 8 warps: warp w reads TMEM lanes 32*(w%4).. and owns the 32-column half h = (w-4)/4 of every chunk
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const int by = row >> 3, bx = row & 7;
+    int it = 0;
+    uint32_t chunk_ctr = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles_n;
+      int mt = t / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int y0 = ty * 16, n0 = nt * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase, 25);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const int x0 = (tx * MT + sub) * 8;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + sub) * BN;
+        const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
+        const __nv_bfloat16* mrow = nullptr;
+        if (p.mask != nullptr && px_valid)
+          mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx;
+#pragma unroll 1
+        for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
+          uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+          const int col0 = n0 + j * 64;
+          // ReLU-backward mask: issue this thread's 64 B of the mask row now, consume after the TMEM load
+          uint4 m4[4];
+          if (mrow != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(mrow + col0 + h * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
+          }
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 256);
+          {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_addr + j * 64 + h * 32, v);
+            tmem_ld_wait();
+            const int cbase = col0 + h * 32;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + i));
+                f[i] += b4.x;
+                f[i + 1] += b4.y;
+                f[i + 2] += b4.z;
+                f[i + 3] += b4.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            }
+            if (p.mask != nullptr) {
+              if (mrow != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint32_t mw[4] = {m4[i].x, m4[i].y, m4[i].z, m4[i].w};
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    const uint32_t lo = mw[w] & 0xffffu, hi = mw[w] >> 16;
+                    if (!(lo != 0 && lo < 0x8000u)) f[i * 8 + w * 2] = 0.0f;
+                    if (!(hi != 0 && hi < 0x8000u)) f[i * 8 + w * 2 + 1] = 0.0f;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = 0.0f;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
+              o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+              o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
+              o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+              const int chunk = (h * 4 + c) ^ (row & 7);
+              *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (et == 0) {
+            tma_store_4d(&p.o_map, ebuf, col0, x0, y0, img);
+            tma_store_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace ub

@@ -175,6 +175,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)layout << 61;               // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
   return d;
 }
+// The same descriptor split into its two 32-bit words, so an issue loop can keep the (constant) high
+// word and advance only the start-address field of the low word with one integer add.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout = 2) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
 // Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                  // D format  = F32

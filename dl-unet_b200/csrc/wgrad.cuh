@@ -127,20 +127,20 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     } else if (warp == 1) {
       {
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+        const uint32_t hiD = umma_desc_hi(1024);
+        const uint32_t loA0 = umma_desc_lo(smem_u32(smem), 8192), loB0 = umma_desc_lo(smem_u32(smem) + C::A_BYTES, 8192);
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < n_iters; ++i) {
           mbar_wait(&full[stage], phase, 6);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
           if (elect_one()) {
+            const uint32_t so = stage * (C::STAGE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              // 16 pixels (K) per MMA = two 8-row groups = 2048 B
-              const uint64_t adesc = umma_smem_desc(sa + k * 2048, 8192, 1024);
-              const uint64_t bdesc = umma_smem_desc(sb + k * 2048, 8192, 1024);
-              umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              // 16 pixels (K) per MMA = two 8-row groups = 2048 B (>>4 = 128)
+              umma_bf16(tmem_base, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + 128 * k), idesc,
+                        (i > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty[stage]);
             if (i == n_iters - 1) umma_commit(tfull);

@@ -165,6 +165,55 @@ def sec_wgrad_modes():
     ops.set_option(1, 2)
 
 
+def sec_igemm2():
+    """haloed-patch conv kernel (option 2 = 2: wherever legal) vs the tap-per-load kernel (0): parity + time."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(5)
+    shapes = [(1, 20, 20, 64, 64), (2, 30, 30, 128, 128), (1, 18, 34, 64, 256), (3, 10, 10, 128, 64), (1, 66, 66, 64, 128),
+              (2, 37, 53, 128, 128), (1, 21, 19, 256, 128), (1, 40, 40, 128, 256), (1, 5, 3, 64, 64),
+              (16, 200, 200, 64, 64), (16, 200, 200, 128, 64), (16, 200, 200, 64, 128), (16, 150, 150, 128, 128),
+              (8, 200, 200, 256, 128), (8, 200, 200, 128, 256)]
+    for (n, h, w, cin, cout) in shapes:
+        x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+        wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+        b = torch.randn(cout, device=DEV)
+        dy = torch.randn(n, cout, h - 2, w - 2, device=DEV)
+        big = n * h * w * cin > 4e7
+        if not big:
+            ref = F.relu(F.conv2d(bf(x).float(), bf(wt).float(), b))
+            refd = F.conv_transpose2d(bf(dy).float(), bf(wt).float()) * (bf(x).float() > 0)
+        xh, dyh = nhwc(x), nhwc(dy)
+        wf, wd = ops.pack_weight(wt, ops.PACK_CONV_FWD), ops.pack_weight(wt, ops.PACK_CONV_DGRAD)
+        outs = {}
+        for mode in (0, 2):
+            ops.set_option(2, mode)
+            y = torch.full((n, h - 2, w - 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+            ops.conv3x3_fwd(xh, wf, b, y, relu=True)
+            ops.conv3x3_dgrad(dyh, wd, dx, xh)
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            for _ in range(3):
+                ops.conv3x3_fwd(xh, wf, b, y, relu=True)
+            e[1].record()
+            for _ in range(3):
+                ops.conv3x3_dgrad(dyh, wd, dx, xh)
+            e[2].record()
+            torch.cuda.synchronize()
+            fl = 2.0 * n * (h - 2) * (w - 2) * cin * cout * 9
+            tf, td = e[0].elapsed_time(e[1]) / 3 * 1e3, e[1].elapsed_time(e[2]) / 3 * 1e3
+            tag = f"mode {mode} {n, h, w, cin, cout} fwd {tf:7.1f}us {fl / tf / 1e6:6.0f}TF/s dgrad {td:7.1f}us {fl / td / 1e6:6.0f}TF/s"
+            outs[mode] = (y, dx)
+            if not big:
+                report(tag + " fwd", nchw(y), ref)
+                report("    dgrad+mask", nchw(dx), refd)
+            else:
+                print("  " + tag, flush=True)
+        print("    bit-identical between kernels: fwd", bool(torch.equal(outs[0][0], outs[2][0])), "dgrad", bool(torch.equal(outs[0][1], outs[2][1])))
+    ops.set_option(2, 1)
+
+
 UP_SHAPES = [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256)]
 
 
@@ -338,7 +387,7 @@ def sec_elementwise():
 
 SECTIONS = {
     "probe": sec_probe, "conv_fwd": sec_conv_fwd, "conv_dgrad": sec_conv_dgrad, "conv_wgrad": sec_conv_wgrad,
-    "upconv": sec_upconv, "elementwise": sec_elementwise, "wgrad_modes": sec_wgrad_modes, "mma_rate": sec_mma_rate,
+    "upconv": sec_upconv, "elementwise": sec_elementwise, "wgrad_modes": sec_wgrad_modes, "mma_rate": sec_mma_rate, "igemm2": sec_igemm2,
 }
 
 if __name__ == "__main__":

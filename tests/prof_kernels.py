@@ -10,7 +10,8 @@ from b200 import ops  # noqa: E402
 
 DEV = "cuda:0"
 CASES = {"wg52": (16, 30, 1024, 1024), "wg12": (16, 570, 64, 64), "wg22": (16, 282, 128, 128),
-         "fw12": (16, 570, 64, 64), "fw42": (16, 66, 512, 512), "fw22": (16, 282, 128, 128)}
+         "fw12": (16, 570, 64, 64), "fw42": (16, 66, 512, 512), "fw22": (16, 282, 128, 128),
+         "fwA": (16, 200, 64, 64), "fwB": (16, 200, 128, 128)}
 case = sys.argv[1]
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
@@ -29,6 +30,7 @@ if case.startswith("wg"):
         ops.conv3x3_wgrad(x, dy, dwp)
     e1.record()
 else:
+    ops.set_option(2, mode)   # for forward cases "mode" selects the conv kernel (0 = igemm, 2 = igemm2)
     w = torch.randn(cout, 9 * cin, device=DEV).to(torch.bfloat16) / 30
     b = torch.zeros(cout, device=DEV)
     y = torch.empty(n, h - 2, h - 2, cout, dtype=torch.bfloat16, device=DEV)
