@@ -18,6 +18,7 @@
 #include "probe.cuh"
 #include "wgrad.cuh"
 #include "wgrad3.cuh"
+#include "wgrad5.cuh"
 
 using namespace ub;
 
@@ -293,6 +294,31 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   return UB_E_SHAPE;
 }
 
+// Split-K factor: fill an integer number of waves (1 CTA per SM) as completely as possible while every
+// split keeps at least `min_chunks` pipeline iterations.
+int pick_splits(long long items, long long chunks, int min_chunks) {
+  if (g_force_splits > 0) return g_force_splits;
+  const int sms = num_sms();
+  long long max_splits = chunks / min_chunks;
+  if (max_splits < 1) max_splits = 1;
+  long long best_s = 1;
+  double best_eff = -1.0;
+  for (int waves = 1; waves <= 6; ++waves) {
+    long long s = (long long)waves * sms / items;
+    if (s < 1) s = 1;
+    if (s > max_splits) s = max_splits;
+    const long long ctas = items * s;
+    const long long w = (ctas + sms - 1) / sms;
+    // efficiency of the last wave x a mild preference for more (shorter) waves up to ~3
+    const double eff = (double)ctas / (double)(w * sms) - 0.03 * (w > 3 ? w - 3 : 0) - (w < 2 ? 0.05 : 0.0);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_s = s;
+    }
+  }
+  return (int)best_s;
+}
+
 int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
   Wgrad3Params P;
   memset(&P, 0, sizeof(P));
@@ -320,11 +346,7 @@ int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   P.dw = dw;
   const long long items = (long long)P.m_tiles * P.ci_tiles;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  long long splits = (3ll * num_sms() + items - 1) / items;
-  if (splits > chunks / 4) splits = chunks / 4;
-  if (splits < 1) splits = 1;
-  if (g_force_splits > 0) splits = g_force_splits;
-  P.splits = (int)splits;
+  P.splits = pick_splits(items, chunks, 6);
   int e;
   if ((e = make_map4(&P.g_map, dy, 16, P.KH, 64))) return e;
   if ((e = make_map4(&P.x_map, x, 18, P.KH + 2, 32))) return e;
@@ -337,7 +359,50 @@ int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
-  wgrad3_kernel<<<(int)(items * splits), 256, Wgrad3Cfg::smem_bytes(P.KH), st>>>(P);
+  wgrad3_kernel<<<(int)(items * P.splits), 256, Wgrad3Cfg::smem_bytes(P.KH), st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+int launch_wgrad5(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+  Wgrad5Params P;
+  memset(&P, 0, sizeof(P));
+  long long best = -1;
+  for (int kh = 8; kh >= 2; kh >>= 1) {
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (best < 0 || padded < best) best = padded;
+  }
+  for (int kh = 8; kh >= 2; kh >>= 1) {
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (padded * 100 <= best * 106) {
+      P.KH = kh;
+      break;
+    }
+  }
+  P.chunks_x = (dy->w + 15) / 16;
+  P.chunks_y = (dy->h + P.KH - 1) / P.KH;
+  P.n_img = dy->n;
+  P.Cout = dy->c;
+  P.Cin = x->c;
+  P.m_tiles = (dy->c + 127) / 128;
+  P.ci_groups = (x->c + 127) / 128;
+  P.dw = dw;
+  const long long items = 3ll * P.m_tiles * P.ci_groups;
+  const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
+  P.splits = pick_splits(items, chunks, 6);
+  P.nstage = Wgrad5Cfg::nstage(P.KH);
+  P.stage_bytes = Wgrad5Cfg::stage_bytes(P.KH);
+  P.g_bytes = Wgrad5Cfg::g_bytes(P.KH);
+  P.x_block_bytes = Wgrad5Cfg::x_block_bytes(P.KH);
+  int e;
+  if ((e = make_map4(&P.g_map, dy, 16, P.KH, 64))) return e;
+  if ((e = make_map4(&P.x_map, x, 18, P.KH, 64))) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  wgrad5_kernel<<<(int)(items * P.splits), 256, Wgrad5Cfg::smem_bytes(P.KH), st>>>(P);
   return (int)cudaGetLastError();
 }
 
@@ -477,8 +542,14 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
   if (dy->n != x->n || dy->h != x->h - 2 || dy->w != x->w - 2) return UB_E_SHAPE;
   // measured on B200 (profiles/r1_layer_table.log): the haloed-patch kernel wins while the input has few
   // channels (dY is re-read Cin/32 times), the tap-per-CTA kernel wins for the deep, spatially small layers
-  const bool use3 = g_wgrad_mode == 3 ? (x->c <= 128 || (x->c <= 256 && dy->w >= 160)) : (g_wgrad_mode != 0);
-  if (use3) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
+  // kernel choice measured per layer on B200 (profiles/r1_layer_table_*.log):
+  //   64 -> 64 channels            : haloed patch, all nine taps, 32-channel tile (wgrad3)
+  //   Cin <= 256 on maps >= 100 px : one tap row per CTA, N = 192 (wgrad5)
+  //   deep, spatially small layers : one tap per CTA, N = 256 (wgrad_kernel)
+  int mode = g_wgrad_mode;
+  if (mode == 3) mode = (x->c == 64 && dy->c == 64) ? 2 : (x->c <= 256 && dy->w >= 100) ? 4 : 0;
+  if (mode == 4) return launch_wgrad5(x, dy, dw_packed, (cudaStream_t)stream);
+  if (mode == 1 || mode == 2) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
   WgradParams P;
   memset(&P, 0, sizeof(P));
   pick_kpatch(dy->w, dy->h, P.KW, P.KH);
@@ -503,11 +574,7 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
   P.n_tiles = x->c / BN;
   const long long items = (long long)P.n_taps * P.m_tiles * P.n_tiles;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  long long splits = (4ll * num_sms() + items - 1) / items;
-  if (splits > chunks / 4) splits = chunks / 4;
-  if (splits < 1) splits = 1;
-  if (g_force_splits > 0) splits = g_force_splits;
-  P.splits = (int)splits;
+  P.splits = pick_splits(items, chunks, 8);
   if ((e = make_map4(&P.a_map[0], dy, P.KW, P.KH))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
   if ((e = make_map4(&P.b_map, x, P.KW, P.KH))) return e;
@@ -605,11 +672,7 @@ int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_pack
   P.n_tiles = x->c / BN;
   const long long items = (long long)P.n_taps * P.m_tiles * P.n_tiles;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  long long splits = (4ll * num_sms() + items - 1) / items;
-  if (splits > chunks / 4) splits = chunks / 4;
-  if (splits < 1) splits = 1;
-  if (g_force_splits > 0) splits = g_force_splits;
-  P.splits = (int)splits;
+  P.splits = pick_splits(items, chunks, 8);
   if ((e = make_map4(&P.b_map, x, P.KW, P.KH))) return e;
   return launch_wgrad(P, BN, (cudaStream_t)stream);
 }
@@ -618,8 +681,10 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   if (!image || !w || !bias || !y) return UB_E_ARG;
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(y)) return UB_E_ALIGN;
-  const long long total = (long long)n * (h - 2) * (w_ - 2) * 8;
-  conv1_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_);
+  if (n > 65535 || h - 2 > 65535) return UB_E_SHAPE;
+  const int rpb = 24;
+  const dim3 grid(((w_ - 2) * 8 + 255) / 256, (h - 2 + rpb - 1) / rpb, n);
+  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_, rpb);
   return (int)cudaGetLastError();
 }
 
@@ -627,11 +692,12 @@ int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int
   if (!image || !dy || !dw || !db) return UB_E_ARG;
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
-  const long long total = (long long)n * (h - 2) * (w_ - 2) * 8;
-  long long blocks = (total + 256ll * 16 - 1) / (256ll * 16);
-  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
-  if (blocks < 1) blocks = 1;
-  conv1_wgrad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, dw, db, n, h, w_);
+  if (n > 65535) return UB_E_SHAPE;
+  // aim for ~8 blocks per SM: rows_per_block = ceil(Ho * n / (8 * SMs))
+  int rpb = (int)(((long long)(h - 2) * n + 8ll * num_sms() - 1) / (8ll * num_sms()));
+  if (rpb < 1) rpb = 1;
+  const dim3 grid((h - 2 + rpb - 1) / rpb, n);
+  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, dw, db, n, h, w_, rpb);
   return (int)cudaGetLastError();
 }
 
@@ -685,6 +751,7 @@ int ub_head_fwd(const void* x, const float* w, const float* bias, float* logits,
   if (!x || !w || !bias || (!logits && !argmax)) return UB_E_ARG;
   if (!aligned16(x)) return UB_E_ALIGN;
   const long long npix = (long long)h * w_;
+  if (npix * n * 8 >= (1ll << 31)) return UB_E_SHAPE;
   head_fwd_kernel<<<ew_grid(npix * n * 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, bias, logits,
                                                                           argmax, npix, n);
   return (int)cudaGetLastError();
@@ -695,15 +762,16 @@ int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, f
   if (!x || !w || !dlogits || !dx || !dw || !db) return UB_E_ARG;
   if (!aligned16(x) || !aligned16(dx)) return UB_E_ALIGN;
   const long long npix = (long long)h * w_;
-  long long blocks = (npix * n * 8 + 256ll * 16 - 1) / (256ll * 16);
-  if (blocks > 4ll * num_sms()) blocks = 4ll * num_sms();
+  if (npix * n * 8 >= (1ll << 31)) return UB_E_SHAPE;
+  long long blocks = (npix * n * 8 + 256ll * 8 - 1) / (256ll * 8);
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
   if (blocks < 1) blocks = 1;
   head_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, dlogits,
                                                                 (__nv_bfloat16*)dx, dw, db, npix, n);
   return (int)cudaGetLastError();
 }
 
-static const int kLossMaxBlocks = 1184;  // 8 x 148
+static const int kLossMaxBlocks = 4736;  // 32 x 148
 long long ub_loss_workspace_bytes(void) { return (long long)(kLossMaxBlocks + 4) * sizeof(float); }
 
 int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_bytes, const float* weight,
@@ -714,17 +782,24 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
   if (hp != wp || l > hp || ((hp - l) & 1) || b <= 0 || l <= 0) return UB_E_SHAPE;
   const int pad = (hp - l) / 2;
   const long long total = (long long)b * l * l;
-  long long blocks = (total + 255) / 256;
+  if (total >= (1ll << 31)) return UB_E_SHAPE;
+  long long blocks = (total / 4 + 255) / 256;
   if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  // 128-bit path: every row start (logits, weight, dlogits) must be 16-byte aligned
+  const int vec4 = (l % 4 == 0 && wp % 4 == 0 && pad % 4 == 0 && aligned16(logits) && aligned16(weight) &&
+                    (!dlogits || aligned16(dlogits)) && ((long long)hp * wp) % 4 == 0)
+                       ? 1
+                       : 0;
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
   float* partials = reinterpret_cast<float*>(workspace) + 4;
   if (label_bytes == 1)
     loss_kernel<uint8_t><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-        logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, hp, wp, l, pad, kind, grad_scale);
+        logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, hp, wp, l, pad, kind, grad_scale, vec4);
   else
     loss_kernel<long long><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         logits, (const long long*)label, weight, dlogits, loss_out, partials, counter, b, hp, wp, l, pad, kind,
-        grad_scale);
+        grad_scale, vec4);
   return (int)cudaGetLastError();
 }
 

@@ -34,10 +34,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // grid.x covers pixels*8 threads; thread = (pixel, channel octet).
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
-                                                        int n_img, int H, int W) {
-  // blockDim and the grid stride are multiples of 8, so a thread keeps its channel octet for the whole
-  // loop: its 8 x 9 weights and 8 biases live in registers (no shared-memory traffic in the loop)
-  const int oct = threadIdx.x & 7;
+                                                        int n_img, int H, int W, int rows_per_block) {
+  // grid = (ceil(Wo*8/256), ceil(Ho/rows_per_block), n): no index divisions; a thread keeps its channel
+  // octet and its x position and walks down rows_per_block rows, so its 8 x 9 weights and 8 biases are
+  // loaded once into registers and the three input rows slide (6 of 9 taps are reused per step).
+  const int Ho = H - 2, Wo = W - 2;
+  const int gx = blockIdx.x * 256 + threadIdx.x;
+  const int ox = gx >> 3, oct = gx & 7;
+  const int n = blockIdx.z;
+  if (ox >= Wo) return;
   float wr[8][9], br[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -45,21 +50,23 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (oct * 8 + c) * 9 + t);
   }
-  const int Ho = H - 2, Wo = W - 2;
-  const long long total = (long long)n_img * Ho * Wo * 8;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (long long)gridDim.x * blockDim.x) {
-    long long pix = gid >> 3;
-    const int ox = (int)(pix % Wo);
-    pix /= Wo;
-    const int oy = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
-    const float* xp = x + ((long long)n * H + oy) * W + ox;
-    float in[9];
+  const int y_begin = blockIdx.y * rows_per_block;
+  const int y_end = min(Ho, y_begin + rows_per_block);
+  const float* xp = x + ((long long)n * H + y_begin) * W + ox;
+  float in[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+  for (int s = 0; s < 3; ++s) {
+    in[3 + s] = __ldg(xp + s);
+    in[6 + s] = __ldg(xp + W + s);
+  }
+  for (int oy = y_begin; oy < y_end; ++oy) {
 #pragma unroll
-      for (int s = 0; s < 3; ++s) in[r * 3 + s] = __ldg(xp + r * W + s);
+    for (int s = 0; s < 3; ++s) {
+      in[s] = in[3 + s];
+      in[3 + s] = in[6 + s];
+      in[6 + s] = __ldg(xp + 2 * W + s);
+    }
+    xp += W;
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       for (int t = 0; t < 9; ++t) a = fmaf(in[t], wr[c][t], a);
       o[c] = fmaxf(a, 0.0f);
     }
-    *reinterpret_cast<uint4*>(y + (gid >> 3) * 64 + oct * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(y + (((long long)n * Ho + oy) * Wo + ox) * 64 + oct * 8) = pack8(o);
   }
 }
 
@@ -78,39 +85,39 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ dy,
                                                           float* __restrict__ dw, float* __restrict__ db, int n_img,
-                                                          int H, int W) {
+                                                          int H, int W, int rows_per_block) {
+  // grid = (ceil(Ho / rows_per_block), n): a block sweeps its rows with 32 pixels x 8 channel octets per
+  // pass -- no index divisions; every thread keeps its octet.
   const int Ho = H - 2, Wo = W - 2;
-  const long long total = (long long)n_img * Ho * Wo * 8;
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x & 7, px = threadIdx.x >> 3;
   float acc[8][10];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 10; ++t) acc[c][t] = 0.0f;
-  const int oct = threadIdx.x & 7;  // blockDim.x multiple of 8 and stride multiple of 8 keeps oct fixed
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (long long)gridDim.x * blockDim.x) {
-    long long pix = gid >> 3;
-    const int ox = (int)(pix % Wo);
-    long long r2 = pix / Wo;
-    const int oy = (int)(r2 % Ho);
-    const int n = (int)(r2 / Ho);
-    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(dy + pix * 64 + oct * 8));
-    float g[8];
-    unpack8(g4, g);
-    const float* xp = x + ((long long)n * H + oy) * W + ox;
-    float in[9];
+  const int y_begin = blockIdx.x * rows_per_block;
+  const int y_end = min(Ho, y_begin + rows_per_block);
+  for (int oy = y_begin; oy < y_end; ++oy) {
+    const float* xrow = x + ((long long)n * H + oy) * W;
+    const __nv_bfloat16* grow = dy + (((long long)n * Ho + oy) * Wo) * 64 + oct * 8;
+    for (int ox = px; ox < Wo; ox += 32) {
+      float g[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(grow + (long long)ox * 64)), g);
+      float in[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) in[r * 3 + s] = __ldg(xp + r * W + s);
+        for (int s2 = 0; s2 < 3; ++s2) in[r * 3 + s2] = __ldg(xrow + r * W + ox + s2);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 8; ++c) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
-      acc[c][9] += g[c];
+        for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
+        acc[c][9] += g[c];
+      }
     }
   }
-  // reduce over the 32 threads of the block that share `oct` within each warp (lanes with equal lane&7)
+  // lanes with equal (lane & 7) share the octet: reduce over xor 8, 16; then across warps through smem
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -121,7 +128,6 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
       acc[c][t] = v;
     }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // lanes 0..7 hold the warp sums for octets 0..7
   __shared__ float sred[8][64][10];  // [warp][channel][tap]
   if (lane < 8) {
 #pragma unroll
@@ -267,15 +273,15 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
     w1[c] = __ldg(w + 64 + oct * 8 + c);
   }
   const float b0 = __ldg(b), b1 = __ldg(b + 1);
-  const long long total = n_pix_per_img * n_img * 8;
-  const long long total_r = (total + 31) & ~31ll;  // keep whole warps in the loop for the shuffles
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total_r;
-       gid += (long long)gridDim.x * blockDim.x) {
-    const long long pix = gid >> 3;
+  const unsigned int total = (unsigned int)(n_pix_per_img * n_img * 8);
+  const unsigned int total_r = (total + 31u) & ~31u;  // keep whole warps in the loop for the shuffles
+  const unsigned int npp = (unsigned int)n_pix_per_img;
+  for (unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total_r; gid += gridDim.x * blockDim.x) {
+    const unsigned int pix = gid >> 3;
     float s0 = 0.0f, s1 = 0.0f;
     if (gid < total) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * 64 + oct * 8)), v);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (long long)pix * 64 + oct * 8)), v);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         s0 = fmaf(v[c], w0[c], s0);
@@ -290,10 +296,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
     if (gid < total && oct == 0) {
       s0 += b0;
       s1 += b1;
-      const long long n = pix / n_pix_per_img, r = pix - n * n_pix_per_img;
+      const unsigned int n = pix / npp, r = pix - n * npp;
       if (logits != nullptr) {
-        logits[(n * 2) * n_pix_per_img + r] = s0;
-        logits[(n * 2 + 1) * n_pix_per_img + r] = s1;
+        logits[(long long)(n * 2) * npp + r] = s0;
+        logits[(long long)(n * 2 + 1) * npp + r] = s1;
       }
       if (amax != nullptr) amax[pix] = (s1 > s0) ? 1 : 0;
     }
@@ -317,15 +323,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
   float a0[8], a1[8], sb0 = 0.0f, sb1 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) a0[c] = a1[c] = 0.0f;
-  const long long total = n_pix_per_img * n_img * 8;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (long long)gridDim.x * blockDim.x) {
-    const long long pix = gid >> 3;
-    const long long n = pix / n_pix_per_img, r = pix - n * n_pix_per_img;
-    const float d0 = __ldg(dlogits + (n * 2) * n_pix_per_img + r);
-    const float d1 = __ldg(dlogits + (n * 2 + 1) * n_pix_per_img + r);
+  const unsigned int total = (unsigned int)(n_pix_per_img * n_img * 8);
+  const unsigned int npp = (unsigned int)n_pix_per_img;
+  for (unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+    const unsigned int pix = gid >> 3;
+    const unsigned int n = pix / npp, r = pix - n * npp;
+    const float d0 = __ldg(dlogits + (long long)(n * 2) * npp + r);
+    const float d1 = __ldg(dlogits + (long long)(n * 2 + 1) * npp + r);
     float v[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * 64 + oct * 8)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (long long)pix * 64 + oct * 8)), v);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       o[c] = v[c] > 0.0f ? fmaf(d0, w0[c], d1 * w1[c]) : 0.0f;
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
       sb0 += d0;
       sb1 += d1;
     }
-    *reinterpret_cast<uint4*>(dx + pix * 64 + oct * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(dx + (long long)pix * 64 + oct * 8) = pack8(o);
   }
   // reduce lanes with equal oct (xor 8, 16), then across warps through smem
 #pragma unroll
@@ -384,45 +390,82 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
                                                    const float* __restrict__ weight, float* __restrict__ dlogits,
                                                    float* __restrict__ loss_out, float* __restrict__ partials,
                                                    unsigned int* __restrict__ counter, int B, int Hp, int Wp, int L,
-                                                   int pad, int kind, float grad_scale) {
-  const long long total = (long long)B * L * L;
+                                                   int pad, int kind, float grad_scale, int vec4) {
+  // A thread owns 4 consecutive pixels of one row (vec4 = 1: 128-bit loads/stores; vec4 = 0: the same
+  // loop with scalar accesses when L, pad or the row pitch break 16-byte alignment).
+  const unsigned int qpr = (unsigned int)(L + 3) >> 2;            // quads per row
+  const unsigned int total_q = (unsigned int)B * L * qpr;
   const long long plane = (long long)Hp * Wp;
   float acc = 0.0f;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (long long)gridDim.x * blockDim.x) {
-    const int xx = (int)(gid % L);
-    long long r = gid / L;
-    const int yy = (int)(r % L);
-    const int n = (int)(r / L);
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < total_q; q += gridDim.x * blockDim.x) {
+    const unsigned int xq = q % qpr;
+    const unsigned int r = q / qpr;
+    const unsigned int yy = r % (unsigned int)L;
+    const unsigned int n = r / (unsigned int)L;
+    const int xx = (int)xq * 4;
     const long long off = (long long)(yy + pad) * Wp + (xx + pad);
-    const float z0 = __ldg(logits + (n * 2ll) * plane + off);
-    const float z1 = __ldg(logits + (n * 2ll + 1) * plane + off);
-    const float wv = __ldg(weight + gid);
-    const int lab = (int)label[gid];
-    float g0, g1;
-    if (kind == 0) {
-      // softplus(z) - y z, stable: max(z,0) - y z + log1p(exp(-|z|))
-      const float y0 = lab ? 0.0f : 1.0f, y1 = lab ? 1.0f : 0.0f;
-      const float l0 = fmaxf(z0, 0.0f) - y0 * z0 + log1pf(expf(-fabsf(z0)));
-      const float l1 = fmaxf(z1, 0.0f) - y1 * z1 + log1pf(expf(-fabsf(z1)));
-      acc += wv * (l0 + l1);
-      const float s0 = 1.0f / (1.0f + expf(-z0)), s1 = 1.0f / (1.0f + expf(-z1));
-      g0 = wv * (s0 - y0);
-      g1 = wv * (s1 - y1);
+    const long long lin = ((long long)n * L + yy) * L + xx;
+    const float* z0p = logits + (n * 2ll) * plane + off;
+    const float* z1p = z0p + plane;
+    float z0[4], z1[4], wv[4], g0[4], g1[4];
+    int lab[4];
+    const int cnt = min(4, L - xx);
+    if (vec4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(z0p));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(z1p));
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(weight + lin));
+      z0[0] = a.x; z0[1] = a.y; z0[2] = a.z; z0[3] = a.w;
+      z1[0] = b4.x; z1[1] = b4.y; z1[2] = b4.z; z1[3] = b4.w;
+      wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lab[i] = (int)label[lin + i];
     } else {
-      const float m = fmaxf(z0, z1);
-      const float e0 = expf(z0 - m), e1 = expf(z1 - m);
-      const float s = e0 + e1;
-      const float lse = m + logf(s);
-      acc += wv * (lse - (lab ? z1 : z0));
-      const float p0 = e0 / s, p1 = e1 / s;
-      g0 = wv * (p0 - (lab ? 0.0f : 1.0f));
-      g1 = wv * (p1 - (lab ? 1.0f : 0.0f));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = i < cnt;
+        z0[i] = ok ? __ldg(z0p + i) : 0.0f;
+        z1[i] = ok ? __ldg(z1p + i) : 0.0f;
+        wv[i] = ok ? __ldg(weight + lin + i) : 0.0f;
+        lab[i] = ok ? (int)label[lin + i] : 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (kind == 0) {
+        // softplus(z) - y z = max(z,0) - y z + log1p(exp(-|z|));  sigmoid from the same exponential
+        const float y0 = lab[i] ? 0.0f : 1.0f, y1 = lab[i] ? 1.0f : 0.0f;
+        const float e0 = __expf(-fabsf(z0[i])), e1 = __expf(-fabsf(z1[i]));
+        // e in (0, 1]: log(1 + e) through the fast log keeps ~1e-7 absolute error on a term that is >= e/2
+        const float l0 = fmaxf(z0[i], 0.0f) - y0 * z0[i] + __logf(1.0f + e0);
+        const float l1 = fmaxf(z1[i], 0.0f) - y1 * z1[i] + __logf(1.0f + e1);
+        acc += wv[i] * (l0 + l1);
+        const float r0 = __fdividef(1.0f, 1.0f + e0), r1 = __fdividef(1.0f, 1.0f + e1);
+        const float s0 = z0[i] >= 0.0f ? r0 : e0 * r0, s1 = z1[i] >= 0.0f ? r1 : e1 * r1;
+        g0[i] = wv[i] * (s0 - y0) * grad_scale;
+        g1[i] = wv[i] * (s1 - y1) * grad_scale;
+      } else {
+        const float m = fmaxf(z0[i], z1[i]);
+        const float e0 = __expf(z0[i] - m), e1 = __expf(z1[i] - m);
+        const float ssum = e0 + e1;   // in [1, 2]
+        acc += wv[i] * (m + __logf(ssum) - (lab[i] ? z1[i] : z0[i]));
+        const float inv = __fdividef(1.0f, ssum);
+        g0[i] = wv[i] * (e0 * inv - (lab[i] ? 0.0f : 1.0f)) * grad_scale;
+        g1[i] = wv[i] * (e1 * inv - (lab[i] ? 1.0f : 0.0f)) * grad_scale;
+      }
     }
     if (dlogits != nullptr) {
       // dlogits has the logits' own (uncropped) shape; the cropped-away border stays zero
-      dlogits[(n * 2ll) * plane + off] = g0 * grad_scale;
-      dlogits[(n * 2ll + 1) * plane + off] = g1 * grad_scale;
+      float* d0p = dlogits + (n * 2ll) * plane + off;
+      float* d1p = d0p + plane;
+      if (vec4) {
+        *reinterpret_cast<float4*>(d0p) = make_float4(g0[0], g0[1], g0[2], g0[3]);
+        *reinterpret_cast<float4*>(d1p) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+      } else {
+        for (int i = 0; i < cnt; ++i) {
+          d0p[i] = g0[i];
+          d1p[i] = g1[i];
+        }
+      }
     }
   }
   acc = warp_sum(acc);
@@ -451,7 +494,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
     if (threadIdx.x == 0) {
       float t = 0.0f;
       for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sw[i];
-      const float denom = (kind == 0) ? 2.0f * (float)total : (float)total;
+      const float npx = (float)B * (float)L * (float)L;
+      const float denom = (kind == 0) ? 2.0f * npx : npx;
       *loss_out = t / denom;
       *counter = 0;  // re-arm for the next launch (graph replays included)
     }

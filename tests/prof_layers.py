@@ -31,7 +31,7 @@ def rnd(*shape):
 
 
 tot = {}
-print(f"{'layer':10s} {'Hin':>4s} {'Cin':>5s} {'Cout':>5s} | {'fwd us':>8s} {'TF/s':>7s} | {'dgrad us':>8s} {'TF/s':>7s} | {'wg0 us':>8s} {'TF/s':>7s} | {'wg2 us':>8s} {'TF/s':>7s}")
+print(f"{'layer':10s} {'Hin':>4s} {'Cin':>5s} {'Cout':>5s} | {'fwd us':>8s} {'TF/s':>7s} | {'dgrad us':>8s} {'TF/s':>7s} | {'wg0 us':>8s} {'TF/s':>7s} | {'wg2 us':>8s} {'TF/s':>7s} | {'wg5 us':>8s} {'TF/s':>7s}")
 for (name, kind, cin, cout) in LAYERS:
     if kind == "conv":
         lvl, pos, side = int(name[4]), int(name[5]), name[6]
@@ -49,6 +49,9 @@ for (name, kind, cin, cout) in LAYERS:
         t_w0 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
         ops.set_option(1, 2)
         t_w2 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        ops.set_option(1, 4)
+        t_w5 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        ops.set_option(1, 3)
     elif kind == "up":
         lvl = int(name[-1])
         hin = g.up[lvl] // 2
@@ -61,11 +64,11 @@ for (name, kind, cin, cout) in LAYERS:
         fl = 2.0 * B * hin * hin * cin * cout * 4
         t_f = timeit(lambda: ops.upconv2x2_fwd(x, wf, bias, cat[..., cout:]))
         t_d = timeit(lambda: ops.upconv2x2_dgrad(dcat[..., cout:], wd, dx, x))
-        t_w0 = t_w2 = timeit(lambda: ops.upconv2x2_wgrad(x, dcat[..., cout:], dwp))
+        t_w0 = t_w2 = t_w5 = timeit(lambda: ops.upconv2x2_wgrad(x, dcat[..., cout:], dwp))
     else:
         continue
-    for k, v in (("fwd", t_f), ("dgrad", t_d), ("wg0", t_w0), ("wg2", t_w2), ("wgbest", min(t_w0, t_w2))):
+    for k, v in (("fwd", t_f), ("dgrad", t_d), ("wg0", t_w0), ("wg2", t_w2), ("wg5", t_w5), ("wgbest", min(t_w0, t_w2, t_w5))):
         tot[k] = tot.get(k, 0.0) + v
     print(f"{name:10s} {hin:4d} {cin:5d} {cout:5d} | {t_f:8.1f} {fl / t_f / 1e6:7.1f} | {t_d:8.1f} {fl / t_d / 1e6:7.1f} | "
-          f"{t_w0:8.1f} {fl / t_w0 / 1e6:7.1f} | {t_w2:8.1f} {fl / t_w2 / 1e6:7.1f}", flush=True)
+          f"{t_w0:8.1f} {fl / t_w0 / 1e6:7.1f} | {t_w2:8.1f} {fl / t_w2 / 1e6:7.1f} | {t_w5:8.1f} {fl / t_w5 / 1e6:7.1f}", flush=True)
 print("totals (ms):", {k: round(v / 1e3, 2) for k, v in tot.items()})

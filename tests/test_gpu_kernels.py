@@ -224,8 +224,8 @@ def test_losses_fwd_bwd(ops, case):
                 out = torch.zeros(1, device=DEV)
                 dz = torch.zeros_like(z)
                 ops.loss_fwd_bwd(kind, z.detach(), lt, wm, dz, out, ws, gs)
-                assert abs(out.item() - ref.item()) <= 2e-6 * abs(ref.item())      # tolerance: fp32 sum order
-                assert rel_l2(dz, gz) < 1e-6
+                assert abs(out.item() - ref.item()) <= 2e-5 * abs(ref.item())      # tolerance: fp32 sum order + fast exp/log
+                assert rel_l2(dz, gz) < 1e-5
 
 
 def test_colsum_sgd(ops):
