@@ -542,12 +542,17 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
   if (dy->n != x->n || dy->h != x->h - 2 || dy->w != x->w - 2) return UB_E_SHAPE;
   // measured on B200 (profiles/r1_layer_table.log): the haloed-patch kernel wins while the input has few
   // channels (dY is re-read Cin/32 times), the tap-per-CTA kernel wins for the deep, spatially small layers
-  // kernel choice measured per layer on B200 (profiles/r1_layer_table_*.log):
-  //   64 -> 64 channels            : haloed patch, all nine taps, 32-channel tile (wgrad3)
-  //   Cin <= 256 on maps >= 100 px : one tap row per CTA, N = 192 (wgrad5)
-  //   deep, spatially small layers : one tap per CTA, N = 256 (wgrad_kernel)
+  // kernel choice measured per layer on B200 with wave-aware split-K (profiles/r1_layer_table_batch16_v3.log):
+  //   Cin <= 128                          : haloed patch, all nine taps, 32-channel tile (wgrad3)
+  //   128 -> 64 and 256-channel wide maps  : one tap row per CTA, N = 192 (wgrad5)
+  //   everything deeper                    : one tap per CTA, N = 256 (wgrad_kernel)
   int mode = g_wgrad_mode;
-  if (mode == 3) mode = (x->c == 64 && dy->c == 64) ? 2 : (x->c <= 256 && dy->w >= 100) ? 4 : 0;
+  if (mode == 3) {
+    if (x->c == 128 && dy->c == 64) mode = 4;
+    else if (x->c <= 128) mode = 2;
+    else if (x->c <= 256 && dy->w >= 160) mode = 4;
+    else mode = 0;
+  }
   if (mode == 4) return launch_wgrad5(x, dy, dw_packed, (cudaStream_t)stream);
   if (mode == 1 || mode == 2) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
   WgradParams P;
