@@ -23,6 +23,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
 
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep the real fd for it and route everything else that
+    writes to fd 1 (e.g. NCCL's "NCCL version ..." banner) to stderr."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+JSON_OUT = _claim_stdout()
+
 METRIC = "572x572 train tiles/sec (fwd+bwd)"
 UNIT = "tiles/s"
 TILE = 572
@@ -115,7 +127,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }), file=JSON_OUT, flush=True)
 
 
 def main():
@@ -261,7 +273,7 @@ def main():
                                              "oracle/unet_oracle.py on all host threads, after 1 warm-up"}
         else:
             out["cpu_baseline"] = None
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

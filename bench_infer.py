@@ -14,6 +14,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep the real fd for it and route everything else that
+    writes to fd 1 (e.g. NCCL's "NCCL version ..." banner) to stderr."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+JSON_OUT = _claim_stdout()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -78,12 +90,16 @@ def main():
     t0 = time.perf_counter()
     out = run(image.to(dev, non_blocking=True))
     if world > 1:
-        parts = [torch.empty(len(range(r, n_tiles, world)), tile_out, tile_out, dtype=torch.uint8, device=dev) for r in range(world)] if rank == 0 else None
-        dist.gather(out, parts, dst=0)
+        cap = -(-n_tiles // world)                                    # gather needs equal shapes: pad to the max share
+        padded = torch.zeros(cap, tile_out, tile_out, dtype=torch.uint8, device=dev)
+        padded[:out.shape[0]] = out
+        parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, parts, dst=0)
         if rank == 0:
             full = torch.empty(n_tiles, tile_out, tile_out, dtype=torch.uint8, device=dev)
             for r in range(world):
-                full[r::world] = parts[r]
+                cnt = len(range(r, n_tiles, world))
+                full[r::world] = parts[r][:cnt]
     else:
         full = out
     if rank == 0:
@@ -102,7 +118,7 @@ def main():
             "fwd_tflops": 300.86e9 * n_tiles * args.steps / (ms * 1e-3) / 1e12,
             "e2e": {"value": mpix / e2e_s, "unit": "Mpix/s", "h2d_bytes_per_step": H * W * 4, "d2h_bytes_per_step": H * W},
             "gpu_launches": launches, "mask_foreground_frac": float(mask.float().mean()),
-        }), flush=True)
+        }), file=JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
