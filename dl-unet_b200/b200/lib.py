@@ -71,6 +71,10 @@ def load():
             fn.restype = res
             fn.argtypes = args
         _lib = lib
+        # experiment switches, e.g. UB_OPTIONS="3=1,1=0" (see ub_set_option in include/unet_b200.h)
+        for kv in filter(None, os.environ.get("UB_OPTIONS", "").split(",")):
+            k, v = kv.split("=")
+            lib.ub_set_option(int(k), int(v))
     return _lib
 
 

@@ -162,7 +162,7 @@ int launch_igemm_t(const IgemmParams& P, cudaStream_t st) {
   }
   const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm_kernel<BN><<<grid, 256, C::SMEM_BYTES, st>>>(P);
+  igemm_kernel<BN><<<grid, 384, C::SMEM_BYTES, st>>>(P);
   return (int)cudaGetLastError();
 }
 int launch_igemm(const IgemmParams& P, int BN, cudaStream_t st) {
@@ -248,7 +248,7 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
   const int b_slot = BN * 128;
-  const int limit = 232448 - 1024 /*align*/ - 1024 /*barriers*/ - 2 * 16384 /*epilogue staging*/;
+  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/;
   const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
   const int nb_stat = 9 * P.kchunks;
   P.stationary = (P.n_tiles_n == 1 && nb_stat <= IG2_MAX_B && nb_stat * b_slot + 2 * a_slot1 <= limit) ? 1 : 0;
@@ -283,11 +283,12 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
     P.mask_sn = relu_src->sn;
     P.mask_sy = relu_src->sy;
     P.mask_sx = relu_src->sx;
+    if ((e = make_map4(&P.m_map, relu_src, 8, 16))) return e;
   }
   if ((e = make_map4(&P.a_map, in, 8 * MT + 2, 18))) return e;
   if ((e = make_map2(&P.b_map, w, 9ll * K, N, BN))) return e;
   if ((e = make_map4(&P.o_map, out, 8, 16))) return e;
-  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 1024 + 1024;
+  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024;
   if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
@@ -416,7 +417,7 @@ int set_mask(IgemmParams& P, const ub_tensor4* relu_src, const ub_tensor4* dx) {
   P.mask_sn = relu_src->sn;
   P.mask_sy = relu_src->sy;
   P.mask_sx = relu_src->sx;
-  return 0;
+  return make_map4(&P.m_map, relu_src, P.BW, P.BH);
 }
 
 }  // namespace

@@ -1,0 +1,61 @@
+// Shared epilogue step of the conv kernels: one thread's 32 columns of one 128-row x 64-column chunk.
+//   TMEM -> registers -> (+bias from smem) -> ReLU -> bf16 -> ReLU-backward mask -> swizzled smem row.
+// The 128 B rows of the staging buffer use the SWIZZLE_128B pattern the TMA store expects.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on,
+                                          const __nv_bfloat16* mcols, uint8_t* ebuf, int row, int h) {
+  // the mask row (64 B of this thread's pixel) is requested first: its latency overlaps the TMEM load
+  uint4 m4[4];
+  if (mask_on && mcols != nullptr) {
+    const uint4* mp = reinterpret_cast<const uint4*>(mcols);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
+  }
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(taddr, v);
+  tmem_ld_wait();
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (sbias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);  // same address in every lane: broadcast
+      f[i] += b4.x;
+      f[i + 1] += b4.y;
+      f[i + 2] += b4.z;
+      f[i + 3] += b4.w;
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
+    o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+    o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
+    o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+    if (mask_on) {
+      // ReLU backward on packed bf16 pairs: a bf16 is > 0 exactly when its bits, read as int16, are > 0
+      if (mcols != nullptr) {
+        o.x &= __vcmpgts2(m4[c].x, 0u);
+        o.y &= __vcmpgts2(m4[c].y, 0u);
+        o.z &= __vcmpgts2(m4[c].z, 0u);
+        o.w &= __vcmpgts2(m4[c].w, 0u);
+      } else {
+        o = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    const int chunk = (h * 4 + c) ^ (row & 7);
+    *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
+  }
+}
+
+}  // namespace ub

@@ -19,6 +19,7 @@
 // swizzled smem -> TMA store).  Two TMEM accumulators so the epilogue of tile i
 // overlaps the MMAs of tile i+1; persistent over tiles.
 #pragma once
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub {
@@ -29,6 +30,7 @@ struct alignas(64) IgemmParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
   CUtensorMap o_map[4];
+  CUtensorMap m_map;  // ReLU-mask source view, box {64, BW, BH, 1}: L2 prefetch only
   int n_taps, kchunks;
   int tiles_x, tiles_y, n_img, n_tiles_n;
   int BW, BH;
@@ -52,7 +54,7 @@ struct IgemmCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 2 * 16384;
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 2048;  // mbarriers, TMEM slot, 256 floats of per-tile bias
   static constexpr int SMEM_LIMIT = 232448 - 1024;
   static constexpr int NSTAGE_RAW = (SMEM_LIMIT - EPI_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
@@ -62,7 +64,7 @@ struct IgemmCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   using C = IgemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
   uint64_t* tfull = empty + C::NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(epi + C::EPI_BYTES + 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_barrier_init();
   }
@@ -122,6 +125,13 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         const int ty = mt % p.tiles_y;
         const int img = mt / p.tiles_y;
         const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+        if (p.mask != nullptr) {
+          // the epilogue reads the ReLU-mask rows of this tile later: pull them into L2 now
+          if (elect_one()) {
+            for (int j = 0; j < BN / 64; ++j) tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, x0, y0, img);
+          }
+          __syncwarp();
+        }
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const CUtensorMap* am = &p.a_map[p.tap_map[tap]];
           const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
@@ -182,11 +192,14 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     }
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // 8 warps: warp w may read TMEM lanes 32*(w%4).. and owns the 32-column half hw = (w-4)/4 of every chunk
+    const int q = warp & 3;
+    const int hw = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
     const int by = row / p.BW, bx = row - by * p.BW;
     const bool row_in_box = row < p.BW * p.BH;
+    const bool mask_on = p.mask != nullptr;
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -199,79 +212,31 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
       const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
+        // per-tile bias slice -> smem (every read of the previous slice happened before the last chunk barrier)
+        if (et < BN) sbias[et] = __ldg(p.bias + (n0 + et) % p.bias_mod);
+        named_bar_sync(1, 256);
+      }
       mbar_wait(&tfull[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const bool px_valid = row_in_box && (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
       const __nv_bfloat16* mrow = nullptr;
-      if (p.mask != nullptr && px_valid)
-        mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx;
+      if (mask_on && px_valid)
+        mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx +
+               n0 + hw * 32;
 #pragma unroll 1
       for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
+        // Two staging buffers, ONE barrier per chunk: before the barrier thread 0 waits until every earlier
+        // TMA store has finished reading smem, so after it the other buffer is free for the next chunk.
         uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-        // the TMA store that last read this buffer (two chunks ago) must be done reading
-        if (et == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        const int col0 = n0 + j * 64;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + j * 64 + h * 32, v);
-          tmem_ld_wait();
-          const int cbase = col0 + h * 32;
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias != nullptr) {
-            const float* bp = p.bias + (cbase % p.bias_mod);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-              f[i] += b4.x;
-              f[i + 1] += b4.y;
-              f[i + 2] += b4.z;
-              f[i + 3] += b4.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-          }
-          if (p.mask != nullptr) {
-            if (mrow != nullptr) {
-              const uint4* mp = reinterpret_cast<const uint4*>(mrow + cbase);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 m4 = __ldg(mp + i);
-                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  const uint32_t lo = mw[w] & 0xffffu, hi = mw[w] >> 16;
-                  if (!(lo != 0 && lo < 0x8000u)) f[i * 8 + w * 2] = 0.0f;
-                  if (!(hi != 0 && hi < 0x8000u)) f[i * 8 + w * 2 + 1] = 0.0f;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = 0.0f;
-            }
-          }
-          // 32 channels = 64 B = four 16 B chunks of this row's 128 B swizzle line
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 o;
-            o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
-            o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
-            o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
-            o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
-            const int chunk = (h * 4 + c) ^ (row & 7);
-            *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
-          }
-        }
+        epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
+                  mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, hw);
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        if (et == 0) tma_store_wait_read<0>();
+        named_bar_sync(1, 256);
         if (et == 0) {
+          const int col0 = n0 + j * 64;
           const int mi = col0 / p.omap_div;
           const int cc = col0 - mi * p.omap_div;
           tma_store_4d(&p.o_map[mi], ebuf, cc, x0, y0, img);

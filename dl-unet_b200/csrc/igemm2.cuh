@@ -15,6 +15,7 @@
 //   dgrad: taps read dy[y0 + r - 2, x0 + s - 2]  (base offset -2, TMA zero fill = the padding), weights
 //          pre-rotated by ub_pack_weight mode 1; optional fused ReLU-backward mask in the epilogue.
 #pragma once
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub {
@@ -23,6 +24,7 @@ struct alignas(64) Igemm2Params {
   CUtensorMap a_map;  // input view, box {64, 8*MT+2, 18, 1}
   CUtensorMap b_map;  // packed weights [N][9*K], box {64, BN}
   CUtensorMap o_map;  // output view, box {64, 8, 16, 1}
+  CUtensorMap m_map;  // ReLU-mask source view (same geometry as the output), used for L2 prefetch only
   int kchunks;
   int tiles_x, tiles_y, n_img, n_tiles_n;
   int base_off;  // 0 or -2
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   uint64_t* tfull = b_empty + IG2_MAX_B;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(epi + 2 * 16384 + 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +107,15 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
       const int x0 = tx * 8 * MT + p.base_off, y0 = ty * 16 + p.base_off, n0 = nt * BN;
+      if (p.mask != nullptr) {
+        // the epilogue reads the ReLU-mask rows of this tile a few microseconds from now: pull them into L2
+        if (elect_one()) {
+          for (int sub = 0; sub < MT; ++sub)
+            for (int j = 0; j < BN / 64; ++j)
+              tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, (tx * MT + sub) * 8, ty * 16, img);
+        }
+        __syncwarp();
+      }
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&a_empty[as], aph ^ 1, 20);
         if (elect_one()) {
@@ -231,6 +243,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
     const int by = row >> 3, bx = row & 7;
+    const bool mask_on = p.mask != nullptr;
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -243,6 +256,10 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       const int y0 = ty * 16, n0 = nt * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
+        if (et < BN) sbias[et] = __ldg(p.bias + n0 + et);
+        named_bar_sync(1, 256);
+      }
       mbar_wait(&tfull[acc], acc_phase, 25);
       tc_fence_after();
 #pragma unroll 1
@@ -251,75 +268,20 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + sub) * BN;
         const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
         const __nv_bfloat16* mrow = nullptr;
-        if (p.mask != nullptr && px_valid)
-          mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx;
+        if (mask_on && px_valid)
+          mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx +
+                 n0 + h * 32;
 #pragma unroll 1
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
+          // two staging buffers, one barrier per chunk (see igemm.cuh)
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-          const int col0 = n0 + j * 64;
-          // ReLU-backward mask: issue this thread's 64 B of the mask row now, consume after the TMEM load
-          uint4 m4[4];
-          if (mrow != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(mrow + col0 + h * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
-          }
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 256);
-          {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_addr + j * 64 + h * 32, v);
-            tmem_ld_wait();
-            const int cbase = col0 + h * 32;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + i));
-                f[i] += b4.x;
-                f[i + 1] += b4.y;
-                f[i + 2] += b4.z;
-                f[i + 3] += b4.w;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            if (p.mask != nullptr) {
-              if (mrow != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint32_t mw[4] = {m4[i].x, m4[i].y, m4[i].z, m4[i].w};
-#pragma unroll
-                  for (int w = 0; w < 4; ++w) {
-                    const uint32_t lo = mw[w] & 0xffffu, hi = mw[w] >> 16;
-                    if (!(lo != 0 && lo < 0x8000u)) f[i * 8 + w * 2] = 0.0f;
-                    if (!(hi != 0 && hi < 0x8000u)) f[i * 8 + w * 2 + 1] = 0.0f;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = 0.0f;
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 o;
-              o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
-              o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
-              o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
-              o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
-              const int chunk = (h * 4 + c) ^ (row & 7);
-              *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
-            }
-          }
+          epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
+                    mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, h);
           fence_proxy_async_smem();
+          if (et == 0) tma_store_wait_read<0>();
           named_bar_sync(1, 256);
           if (et == 0) {
-            tma_store_4d(&p.o_map, ebuf, col0, x0, y0, img);
+            tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
             tma_store_commit();
           }
         }
