@@ -18,6 +18,7 @@
 #include "probe.cuh"
 #include "wgrad.cuh"
 #include "wgrad3.cuh"
+#include "wgrad4.cuh"
 #include "wgrad5.cuh"
 
 using namespace ub;
@@ -364,6 +365,45 @@ int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   return (int)cudaGetLastError();
 }
 
+int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+  Wgrad4Params P;
+  memset(&P, 0, sizeof(P));
+  long long best = -1;
+  for (int kh = 8; kh >= 2; kh >>= 1) {
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (best < 0 || padded < best) best = padded;
+  }
+  for (int kh = 8; kh >= 2; kh >>= 1) {
+    const long long padded = (long long)((dy->h + kh - 1) / kh) * kh;
+    if (padded * 100 <= best * 106) {
+      P.KH = kh;
+      break;
+    }
+  }
+  P.chunks_x = (dy->w + 1 + 15) / 16;  // x in [0, W]: the one-pixel-shifted dY copy must also see column W-1
+  P.chunks_y = (dy->h + P.KH - 1) / P.KH;
+  P.n_img = dy->n;
+  P.Cin = x->c;
+  P.ci_tiles = x->c / 64;
+  P.dw = dw;
+  const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
+  P.splits = pick_splits(P.ci_tiles, chunks, 6);
+  P.nstage = Wgrad4Cfg::nstage(P.KH);
+  P.stage_bytes = Wgrad4Cfg::stage_bytes(P.KH);
+  P.g_bytes = Wgrad4Cfg::g_bytes(P.KH);
+  int e;
+  if ((e = make_map4(&P.g_map, dy, 17, P.KH, 64))) return e;
+  if ((e = make_map4(&P.x_map, x, 18, P.KH + 2, 64))) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (ce != cudaSuccess) return (int)ce;
+    attr_set = true;
+  }
+  wgrad4_kernel<<<(int)(P.ci_tiles * P.splits), 256, Wgrad4Cfg::smem_bytes(P.KH), st>>>(P);
+  return (int)cudaGetLastError();
+}
+
 int launch_wgrad5(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
   Wgrad5Params P;
   memset(&P, 0, sizeof(P));
@@ -545,15 +585,18 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
   // channels (dY is re-read Cin/32 times), the tap-per-CTA kernel wins for the deep, spatially small layers
   // kernel choice measured per layer on B200 with wave-aware split-K (profiles/r1_layer_table_batch16_v3.log):
   //   Cin <= 128                          : haloed patch, all nine taps, 32-channel tile (wgrad3)
-  //   128 -> 64 and 256-channel wide maps  : one tap row per CTA, N = 192 (wgrad5)
+  //   Cout == 64                          : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
+  //   256-channel wide maps                : one tap row per CTA, N = 192 (wgrad5)
   //   everything deeper                    : one tap per CTA, N = 256 (wgrad_kernel)
   int mode = g_wgrad_mode;
   if (mode == 3) {
-    if (x->c == 128 && dy->c == 64) mode = 4;
+    if (dy->c == 64) mode = 5;                       // 64 output channels: shifted-dY trick (wgrad4)
     else if (x->c <= 128) mode = 2;
     else if (x->c <= 256 && dy->w >= 160) mode = 4;
     else mode = 0;
   }
+  if (mode == 5 && dy->c == 64) return launch_wgrad4(x, dy, dw_packed, (cudaStream_t)stream);
+  if (mode == 5) mode = 2;
   if (mode == 4) return launch_wgrad5(x, dy, dw_packed, (cudaStream_t)stream);
   if (mode == 1 || mode == 2) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
   WgradParams P;

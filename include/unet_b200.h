@@ -44,7 +44,7 @@ const char* ub_error_string(int code);
 int ub_device_error(unsigned int* out_code);
 /* Tuning overrides for experiments: <=0 restores the heuristic. */
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
-/* Experiment switches.  key 1: 3x3 wgrad kernel (0 = tap-per-CTA, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto [default], 4 = tap-row-per-CTA N=192).
+/* Experiment switches.  key 1: 3x3 wgrad kernel (0 = tap-per-CTA, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto [default], 4 = tap-row-per-CTA N=192, 5 = shifted-dY kernel for 64 output channels).
  * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default], 2 = wherever legal). */
 void ub_set_option(int key, int value);
 

@@ -146,7 +146,7 @@ def sec_wgrad_modes():
         F.conv2d(bf(x).float(), wt).backward(bf(dy).float())
         ref = wt.grad
         xh, dyh = nhwc(x), nhwc(dy)
-        for mode in (0, 1, 2, 4):
+        for mode in (0, 1, 2, 4, 5):
             ops.set_option(1, mode)
             dwp = torch.zeros(cout, 9 * cin, dtype=torch.float32, device=DEV)
             ops.conv3x3_wgrad(xh, dyh, dwp)

@@ -51,7 +51,10 @@ for (name, kind, cin, cout) in LAYERS:
         t_w2 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
         ops.set_option(1, 4)
         t_w5 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        ops.set_option(1, 5)
+        t_w4 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp)) if cout == 64 else 0.0
         ops.set_option(1, 3)
+        t_auto = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
     elif kind == "up":
         lvl = int(name[-1])
         hin = g.up[lvl] // 2
@@ -64,11 +67,12 @@ for (name, kind, cin, cout) in LAYERS:
         fl = 2.0 * B * hin * hin * cin * cout * 4
         t_f = timeit(lambda: ops.upconv2x2_fwd(x, wf, bias, cat[..., cout:]))
         t_d = timeit(lambda: ops.upconv2x2_dgrad(dcat[..., cout:], wd, dx, x))
-        t_w0 = t_w2 = t_w5 = timeit(lambda: ops.upconv2x2_wgrad(x, dcat[..., cout:], dwp))
+        t_w0 = t_w2 = t_w5 = t_auto = timeit(lambda: ops.upconv2x2_wgrad(x, dcat[..., cout:], dwp))
+        t_w4 = 0.0
     else:
         continue
-    for k, v in (("fwd", t_f), ("dgrad", t_d), ("wg0", t_w0), ("wg2", t_w2), ("wg5", t_w5), ("wgbest", min(t_w0, t_w2, t_w5))):
+    for k, v in (("fwd", t_f), ("dgrad", t_d), ("wg0", t_w0), ("wg2", t_w2), ("wg5", t_w5), ("wgbest", min(t_w0, t_w2, t_w5)), ("wgauto", t_auto)):
         tot[k] = tot.get(k, 0.0) + v
     print(f"{name:10s} {hin:4d} {cin:5d} {cout:5d} | {t_f:8.1f} {fl / t_f / 1e6:7.1f} | {t_d:8.1f} {fl / t_d / 1e6:7.1f} | "
-          f"{t_w0:8.1f} {fl / t_w0 / 1e6:7.1f} | {t_w2:8.1f} {fl / t_w2 / 1e6:7.1f} | {t_w5:8.1f} {fl / t_w5 / 1e6:7.1f}", flush=True)
+          f"{t_w0:8.1f} {fl / t_w0 / 1e6:7.1f} | {t_w2:8.1f} {fl / t_w2 / 1e6:7.1f} | {t_w5:8.1f} {fl / t_w5 / 1e6:7.1f} | w4 {t_w4:7.1f} auto {t_auto:7.1f}", flush=True)
 print("totals (ms):", {k: round(v / 1e3, 2) for k, v in tot.items()})
