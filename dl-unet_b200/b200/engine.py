@@ -87,6 +87,8 @@ class ParamStore:
         self.g_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.m_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.dwp_arena = None
+        self.jobs = None
+        self.packs = {}
         self.device = device
         self.dirty = True
         self.first_step = True
@@ -105,21 +107,30 @@ class ParamStore:
     def versions(self):
         return tuple(p._version for p in self.params().values())
 
+    def _job_table(self):
+        """One-launch pack / unpack over all 21 conv / up-conv layers (ops.JobTable); rebuilt with the arenas."""
+        if getattr(self, "jobs", None) is None:
+            self.packed_grad_arena()
+            entries = []
+            for (lname, kind, cin, cout) in LAYERS:
+                if kind not in ("conv", "up"):
+                    continue
+                w = self.p(lname + ".weight")
+                fshape = (cout, 9 * cin) if kind == "conv" else (4 * cout, cin)
+                dshape = (cin, 9 * cout) if kind == "conv" else (cin, 4 * cout)
+                self.packs[lname] = (torch.empty(fshape, dtype=torch.bfloat16, device=self.device),
+                                     torch.empty(dshape, dtype=torch.bfloat16, device=self.device))
+                entries.append((w, self.packs[lname][0], self.packs[lname][1], self.dwp(lname), self.g(lname + ".weight"),
+                                0 if kind == "conv" else 2, cout, cin))
+            self.jobs = ops.JobTable(entries, self.device)
+        return self.jobs
+
     def refresh_packs(self):
-        """Re-derive the bf16 GEMM operands when the fp32 masters changed."""
+        """Re-derive the bf16 GEMM operands (one launch for all layers) when the fp32 masters changed."""
         v = self.versions()
         if not self.dirty and v == self.pack_versions:
             return
-        for (lname, kind, cin, cout) in LAYERS:
-            w = self.p(lname + ".weight").view(weight_shape(lname))
-            if kind == "conv":
-                old = self.packs.get(lname, (None, None))
-                self.packs[lname] = (ops.pack_weight(w, ops.PACK_CONV_FWD, old[0]),
-                                     ops.pack_weight(w, ops.PACK_CONV_DGRAD, old[1]))
-            elif kind == "up":
-                old = self.packs.get(lname, (None, None))
-                self.packs[lname] = (ops.pack_weight(w, ops.PACK_UP_FWD, old[0]),
-                                     ops.pack_weight(w, ops.PACK_UP_DGRAD, old[1]))
+        self._job_table().pack_all()
         self.pack_versions = v
         self.dirty = False
 
@@ -245,7 +256,8 @@ class Engine:
         st = self.store
         dwp = st.dwp(lname)
         ops.conv3x3_wgrad(x, dy, dwp)
-        ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
+        if self.grad_ready_hook is not None:  # data parallel: the layer's gradient must be final now
+            ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
         ops.colsum(dy, st.g(lname + ".bias"))
         self._ready(lname)
         if dx is not None:
@@ -280,7 +292,8 @@ class Engine:
             dyu = gr[f"cat{l}"][..., C:]
             dwp = st.dwp(up_name)
             ops.upconv2x2_wgrad(src, dyu, dwp)
-            ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
+            if self.grad_ready_hook is not None:
+                ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
             ops.colsum(dyu, st.g(up_name + ".bias"))
             self._ready(up_name)
             ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
@@ -300,6 +313,8 @@ class Engine:
             else:
                 ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
                 self._ready("conv11c")
+        if self.grad_ready_hook is None:
+            st._job_table().unpack_all(self._accumulate)   # single device: all 21 layers in one launch
         if self.grad_done_hook is not None:
             self.grad_done_hook()
 

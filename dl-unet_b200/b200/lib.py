@@ -34,6 +34,11 @@ SIGNATURES = {
     "ub_set_option": (None, [_i, _i]),
     "ub_pack_weight": (_i, [_P, _P, _i, _i, _i, _P]),
     "ub_unpack_grad": (_i, [_P, _P, _i, _i, _i, _i, _P]),
+    "ub_job_table_bytes": (_i, [_i]),
+    "ub_job_table_fill": (_i, [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                               C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ub_pack_all": (_i, [_P, _i, _ll, _P]),
+    "ub_unpack_all": (_i, [_P, _i, _ll, _i, _P]),
     "ub_conv3x3_fwd": (_i, [_T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
     "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),

@@ -133,6 +133,33 @@ def unpack_grad(packed, dw, mode, accumulate=False):
     return dw
 
 
+class JobTable:
+    """Device-side table of all conv / up-conv layers for the one-launch pack / unpack kernels."""
+
+    def __init__(self, entries, device):
+        """entries: list of (w fp32 torch-layout, dst_fwd bf16, dst_dgrad bf16, packed_grad fp32, dw fp32, kind, cout, cin)."""
+        import numpy as np
+        n = len(entries)
+        lib = _lib.load()
+        nbytes = lib.ub_job_table_bytes(n)
+        host = torch.empty(nbytes, dtype=torch.uint8)
+        arr = lambda col: (C.c_void_p * n)(*[e[col].data_ptr() for e in entries])
+        iarr = lambda col: (C.c_int * n)(*[int(e[col]) for e in entries])
+        tiles = lib.ub_job_table_fill(C.c_void_p(host.data_ptr()), n, arr(0), arr(1), arr(2), arr(3), arr(4), iarr(5), iarr(6), iarr(7))
+        if tiles < 0:
+            check(tiles, "job_table_fill")
+        self.table = host.to(device)
+        self.n = n
+        self.total = tiles
+        self.keep = entries  # keep the tensors alive
+
+    def pack_all(self):
+        _chk(_lib.load().ub_pack_all(_ptr(self.table), self.n, self.total, _stream()), "pack_all")
+
+    def unpack_all(self, accumulate=False):
+        _chk(_lib.load().ub_unpack_all(_ptr(self.table), self.n, self.total, int(accumulate), _stream()), "unpack_all")
+
+
 # ---------------------------------------------------------------- tensor-pipe ops
 def conv3x3_fwd(x, w_fwd, bias, y, relu=True):
     _need_cuda(x, w_fwd, y)

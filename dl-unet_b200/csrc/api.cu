@@ -508,6 +508,46 @@ int ub_pack_weight(const float* w, void* dst, int mode, int cout, int cin, void*
   return (int)cudaGetLastError();
 }
 
+int ub_job_table_bytes(int n_jobs) { return (int)(n_jobs * sizeof(PackJob)); }
+
+int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* const* dst_a, void* const* dst_b,
+                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin) {
+  if (!table_host || n_jobs <= 0) return UB_E_ARG;
+  PackJob* t = reinterpret_cast<PackJob*>(table_host);
+  long long begin = 0;
+  int tiles = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    t[i].w = (const float*)w[i];
+    t[i].dst_a = (__nv_bfloat16*)dst_a[i];
+    t[i].dst_b = (__nv_bfloat16*)dst_b[i];
+    t[i].packed = (const float*)packed[i];
+    t[i].dw = (float*)dw[i];
+    t[i].kind = kind[i];
+    t[i].cout = cout[i];
+    t[i].cin = cin[i];
+    t[i].elem_begin = begin;
+    begin += (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
+    if ((cout[i] % 32) || (cin[i] % 32)) return UB_E_SHAPE;
+    t[i].tile_begin = tiles;
+    tiles += (cout[i] / 32) * (cin[i] / 32);
+  }
+  return tiles;  // >= 0: total tile count, to be passed back as `total`
+}
+
+int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream) {
+  if (!table_dev || n_jobs <= 0) return UB_E_ARG;
+  const int grid = (int)(total < 16ll * num_sms() ? total : 16ll * num_sms());
+  pack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, (int)total);
+  return (int)cudaGetLastError();
+}
+
+int ub_unpack_all(const void* table_dev, int n_jobs, long long total, int accumulate, void* stream) {
+  if (!table_dev || n_jobs <= 0) return UB_E_ARG;
+  const int grid = (int)(total < 16ll * num_sms() ? total : 16ll * num_sms());
+  unpack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, (int)total, accumulate);
+  return (int)cudaGetLastError();
+}
+
 int ub_unpack_grad(const float* packed, float* dw, int mode, int cout, int cin, int accumulate, void* stream) {
   if (!packed || !dw || (mode != 0 && mode != 2)) return UB_E_ARG;
   const long long total = (long long)cout * cin * (mode == 0 ? 9 : 4);
@@ -731,7 +771,7 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(y)) return UB_E_ALIGN;
   if (n > 65535 || h - 2 > 65535) return UB_E_SHAPE;
-  const int rpb = 24;
+  const int rpb = 96;  // amortises the 80 weight/bias register loads of every thread
   const dim3 grid(((w_ - 2) * 8 + 255) / 256, (h - 2 + rpb - 1) / rpb, n);
   conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_, rpb);
   return (int)cudaGetLastError();
@@ -742,7 +782,7 @@ int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
   if (n > 65535) return UB_E_SHAPE;
-  // aim for ~8 blocks per SM: rows_per_block = ceil(Ho * n / (8 * SMs))
+  // ~8 blocks per SM
   int rpb = (int)(((long long)(h - 2) * n + 8ll * num_sms() - 1) / (8ll * num_sms()));
   if (rpb < 1) rpb = 1;
   const dim3 grid((h - 2 + rpb - 1) / rpb, n);

@@ -53,20 +53,25 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   const int y_begin = blockIdx.y * rows_per_block;
   const int y_end = min(Ho, y_begin + rows_per_block);
   const float* xp = x + ((long long)n * H + y_begin) * W + ox;
-  float in[9];
+  float in[9], nxt[3];
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
     in[3 + s] = __ldg(xp + s);
     in[6 + s] = __ldg(xp + W + s);
+    nxt[s] = __ldg(xp + 2 * W + s);
   }
   for (int oy = y_begin; oy < y_end; ++oy) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       in[s] = in[3 + s];
       in[3 + s] = in[6 + s];
-      in[6 + s] = __ldg(xp + 2 * W + s);
+      in[6 + s] = nxt[s];
     }
     xp += W;
+    if (oy + 1 < y_end) {  // input row of the NEXT output row: in flight while this row's 72 FMAs run
+#pragma unroll
+      for (int s = 0; s < 3; ++s) nxt[s] = __ldg(xp + 2 * W + s);
+    }
     float o[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -101,14 +106,29 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
   for (int oy = y_begin; oy < y_end; ++oy) {
     const float* xrow = x + ((long long)n * H + oy) * W;
     const __nv_bfloat16* grow = dy + (((long long)n * Ho + oy) * Wo) * 64 + oct * 8;
-    for (int ox = px; ox < Wo; ox += 32) {
-      float g[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(grow + (long long)ox * 64)), g);
-      float in[9];
+    // software pipeline: the loads of pixel ox+32 are in flight while the 80 FMAs of pixel ox run
+    uint4 g4n = make_uint4(0u, 0u, 0u, 0u);
+    float inn[9];
+    if (px < Wo) {
+      g4n = __ldg(reinterpret_cast<const uint4*>(grow + (long long)px * 64));
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) in[r * 3 + s2] = __ldg(xrow + r * W + ox + s2);
+        for (int s2 = 0; s2 < 3; ++s2) inn[r * 3 + s2] = __ldg(xrow + r * W + px + s2);
+    }
+    for (int ox = px; ox < Wo; ox += 32) {
+      float g[8], in[9];
+      unpack8(g4n, g);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) in[t] = inn[t];
+      const int oxn = ox + 32;
+      if (oxn < Wo) {
+        g4n = __ldg(reinterpret_cast<const uint4*>(grow + (long long)oxn * 64));
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) inn[r * 3 + s2] = __ldg(xrow + r * W + oxn + s2);
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
 #pragma unroll
@@ -576,6 +596,121 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
       src = ((long long)ci * Cout + co) * 4 + ab;
     }
     dst[i] = __float2bfloat16_rn(__ldg(w + src));
+  }
+}
+
+// All layers in ONE launch: a device-side job table replaces 42 (pack) / 21 (unpack) tiny launches per step.
+struct PackJob {
+  const float* w;          // fp32 master / gradient in torch layout
+  __nv_bfloat16* dst_a;    // forward operand   (pack)
+  __nv_bfloat16* dst_b;    // dgrad operand     (pack)
+  const float* packed;     // packed fp32 gradient (unpack source)
+  float* dw;               // torch-layout gradient (unpack destination)
+  int kind;                // 0 = 3x3 conv, 2 = 2x2 up-conv
+  int cout, cin;
+  long long elem_begin;    // prefix sum of element counts over the jobs
+  int tile_begin;          // prefix sum of 32x32-channel tile counts
+};
+
+// Tiled through shared memory so that the fp32 side is read/written in long contiguous runs and the
+// packed side in 64-128 B segments (the naive gather moved 8x the bytes through 32 B sectors).
+//   conv   tile = 32 co x 32 ci x 9 taps   (W[co][ci][t]: 288 contiguous floats per co)
+//   upconv tile = 32 ci x 32 co x 4 taps   (W[ci][co][ab]: 128 contiguous floats per ci)
+__device__ __forceinline__ int find_tile_job(const PackJob* jobs, int n_jobs, int tile) {
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int n_tiles) {
+  __shared__ float T[32 * 289];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const PackJob jb = jobs[find_tile_job(jobs, n_jobs, tile)];
+    const int lt = tile - jb.tile_begin;
+    const int Cin = jb.cin, Cout = jb.cout;
+    __syncthreads();
+    if (jb.kind == 0) {
+      const int ci_tiles = Cin >> 5;
+      const int co0 = (lt / ci_tiles) * 32, ci0 = (lt % ci_tiles) * 32;
+      for (int e = threadIdx.x; e < 32 * 288; e += 256) {
+        const int co = e / 288, k = e - co * 288;
+        T[co * 289 + k] = __ldg(jb.w + ((long long)(co0 + co) * Cin + ci0) * 9 + k);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // forward operand [co][t][ci]
+        const int ci = e & 31, r = e >> 5;
+        const int t = r % 9, co = r / 9;
+        jb.dst_a[((long long)(co0 + co) * 9 + t) * Cin + ci0 + ci] = __float2bfloat16_rn(T[co * 289 + ci * 9 + t]);
+      }
+      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // dgrad operand [ci][8-t][co]
+        const int co = e & 31, r = e >> 5;
+        const int t = r % 9, ci = r / 9;
+        jb.dst_b[((long long)(ci0 + ci) * 9 + (8 - t)) * Cout + co0 + co] = __float2bfloat16_rn(T[co * 289 + ci * 9 + t]);
+      }
+    } else {
+      const int co_tiles = Cout >> 5;
+      const int ci0 = (lt / co_tiles) * 32, co0 = (lt % co_tiles) * 32;
+      for (int e = threadIdx.x; e < 32 * 128; e += 256) {
+        const int ci = e >> 7, k = e & 127;
+        T[ci * 129 + k] = __ldg(jb.w + ((long long)(ci0 + ci) * Cout + co0) * 4 + k);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // forward operand [(ab,co)][ci]
+        const int ci = e & 31, r = e >> 5;
+        const int co = r & 31, ab = r >> 5;
+        jb.dst_a[((long long)ab * Cout + co0 + co) * Cin + ci0 + ci] = __float2bfloat16_rn(T[ci * 129 + co * 4 + ab]);
+      }
+      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // dgrad operand [ci][(ab,co)]
+        const int co = e & 31, r = e >> 5;
+        const int ab = r & 3, ci = r >> 2;
+        jb.dst_b[((long long)(ci0 + ci) * 4 + ab) * Cout + co0 + co] = __float2bfloat16_rn(T[ci * 129 + co * 4 + ab]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int n_tiles,
+                                                         int accumulate) {
+  __shared__ float T[32 * 289];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const PackJob jb = jobs[find_tile_job(jobs, n_jobs, tile)];
+    const int lt = tile - jb.tile_begin;
+    const int Cin = jb.cin, Cout = jb.cout;
+    __syncthreads();
+    if (jb.kind == 0) {
+      const int ci_tiles = Cin >> 5;
+      const int co0 = (lt / ci_tiles) * 32, ci0 = (lt % ci_tiles) * 32;
+      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // packed [co][t][ci]: 32 contiguous ci per (co, t)
+        const int ci = e & 31, r = e >> 5;
+        const int t = r % 9, co = r / 9;
+        T[co * 289 + ci * 9 + t] = __ldg(jb.packed + ((long long)(co0 + co) * 9 + t) * Cin + ci0 + ci);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // torch [co][ci][t]: 288 contiguous floats per co
+        const int co = e / 288, k = e - co * 288;
+        float* d = jb.dw + ((long long)(co0 + co) * Cin + ci0) * 9 + k;
+        const float v = T[co * 289 + k];
+        *d = accumulate ? *d + v : v;
+      }
+    } else {
+      const int co_tiles = Cout >> 5;
+      const int ci0 = (lt / co_tiles) * 32, co0 = (lt % co_tiles) * 32;
+      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // packed [(ab,co)][ci]
+        const int ci = e & 31, r = e >> 5;
+        const int co = r & 31, ab = r >> 5;
+        T[ci * 129 + co * 4 + ab] = __ldg(jb.packed + ((long long)ab * Cout + co0 + co) * Cin + ci0 + ci);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // torch [ci][co][ab]
+        const int ci = e >> 7, k = e & 127;
+        float* d = jb.dw + ((long long)(ci0 + ci) * Cout + co0) * 4 + k;
+        const float v = T[ci * 129 + k];
+        *d = accumulate ? *d + v : v;
+      }
+    }
   }
 }
 

@@ -57,6 +57,15 @@ int ub_pack_weight(const float* w, void* dst_bf16, int mode, int cout, int cin, 
 /* inverse of modes 0 / 2 for the fp32 packed gradient the wgrad kernels produce */
 int ub_unpack_grad(const float* packed, float* dw, int mode, int cout, int cin, int accumulate, void* stream);
 
+/* All conv / up-conv layers in one launch.  A job table (ub_job_table_bytes(n) bytes) is filled on the host by
+ * ub_job_table_fill (returns the total number of 32x32-channel tiles, or a negative error) from per-layer pointer
+ * arrays and copied to the device by the caller; pass that tile count as `total`.  ub_pack_all writes both bf16 operands of every layer, ub_unpack_all the torch-layout gradients. */
+int ub_job_table_bytes(int n_jobs);
+int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* const* dst_a, void* const* dst_b,
+                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin);
+int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream);
+int ub_unpack_all(const void* table_dev, int n_jobs, long long total, int accumulate, void* stream);
+
 /* ---- 3x3 valid convolution (nn.Conv2d(k=3) + F.relu; network.py:131-188) -------------
  * y[n,oy,ox,co] = act(bias[co] + sum_{r,s,ci} x[n,oy+r,ox+s,ci] * W[co,ci,r,s]);  y is (h-2)x(w-2). */
 int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, int relu,
