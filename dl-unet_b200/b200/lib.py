@@ -66,6 +66,10 @@ def load():
     """Load libunet_b200.so (once) and attach the prototypes.  Raises if it is not built."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+            # a source-only checkout on a box with the toolkit: build in-tree once (still no fallback path)
+            import subprocess
+            subprocess.run(["make", "-C", os.path.dirname(LIB_PATH), "libunet_b200.so"], capture_output=True)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -257,3 +257,42 @@ def test_bad_arguments_raise(ops):
     with pytest.raises(RuntimeError, match="unsupported shape"):
         ops.conv3x3_fwd(x, torch.zeros(64, 576, dtype=torch.bfloat16, device=DEV), None,
                         torch.zeros(1, 5, 6, 64, dtype=torch.bfloat16, device=DEV))
+
+
+def test_guard_bands_untouched(ops):
+    """compute-sanitizer is closed on this pool; instead every tensor-pipe output is carved out of a larger
+    sentinel-filled buffer (guard rows before/after, guard channels either side) and the guards are checked:
+    TMA stores must clip tile tails exactly and never touch neighbouring channels / pixels."""
+    torch.manual_seed(11)
+    SENT = 12345.0
+
+    def carve(n, h, w, c):
+        big = torch.full((n, h + 4, w + 4, c + 128), SENT, dtype=torch.bfloat16, device=DEV)
+        return big, big[:, 2:2 + h, 2:2 + w, 64:64 + c]
+
+    def guards_ok(big, n, h, w, c):
+        inner = torch.zeros_like(big, dtype=torch.bool)
+        inner[:, 2:2 + h, 2:2 + w, 64:64 + c] = True
+        return bool((big[~inner] == SENT).all())
+
+    for mode in (0, 2):
+        ops.set_option(2, mode)
+        for (n, h, w, cin, cout) in [(2, 21, 37, 64, 64), (1, 19, 23, 128, 128), (1, 30, 11, 64, 128)]:
+            x = bf(torch.randn(n, h, w, cin, device=DEV))
+            wf = bf(torch.randn(cout, 9 * cin, device=DEV) / 30)
+            wd = bf(torch.randn(cin, 9 * cout, device=DEV) / 30)
+            big, y = carve(n, h - 2, w - 2, cout)
+            ops.conv3x3_fwd(x, wf, torch.zeros(cout, device=DEV), y, relu=True)
+            assert guards_ok(big, n, h - 2, w - 2, cout) and not bool((y == SENT).any())
+            dy = bf(torch.randn(n, h - 2, w - 2, cout, device=DEV))
+            big, dx = carve(n, h, w, cin)
+            ops.conv3x3_dgrad(dy, wd, dx, x)
+            assert guards_ok(big, n, h, w, cin) and not bool((dx == SENT).any())
+    ops.set_option(2, 1)
+    # up-conv writes only its channel half, every pixel of it
+    n, h, w, cin, cout = 1, 13, 9, 128, 64
+    x = bf(torch.randn(n, h, w, cin, device=DEV))
+    big, cat = carve(n, 2 * h, 2 * w, 2 * cout)
+    ops.upconv2x2_fwd(x, bf(torch.randn(4 * cout, cin, device=DEV) / 12), torch.zeros(cout, device=DEV), cat[..., cout:])
+    assert guards_ok(big, n, 2 * h, 2 * w, 2 * cout)
+    assert bool((cat[..., :cout] == SENT).all()) and not bool((cat[..., cout:] == SENT).any())
