@@ -99,3 +99,92 @@ class FusedSGD(torch.optim.SGD):
         ops.sgd_momentum(st.p_arena, st.g_arena, st.m_arena, float(grp["lr"]), float(grp["momentum"]), st.first_step)
         st.first_step = False
         st.dirty = True
+
+
+class TrainStep:
+    """The whole hot-loop body of trainer.py:54-78 -- zero_grad, forward, crop + one-hot + weighted loss, backward,
+    SGD-momentum step -- issued as one explicit kernel schedule without autograd bookkeeping, and (graph=True)
+    captured into a CUDA graph and replayed, so a step costs one host call regardless of its ~100 kernel launches.
+    The reference trains with batch 2 (main_main.py:136), where host launch overhead, not the GPU, bounds the step.
+
+        step = TrainStep(unet, optimizer, graph=True)
+        loss = step(images, labels, weight_maps)        # device tensors; returns a 0-dim device tensor
+
+    The graph is keyed on the input shapes and on (lr, momentum): a ReduceLROnPlateau change re-captures."""
+
+    def __init__(self, unet, optimizer, kind="bce", graph=True, global_batch=None):
+        self.unet, self.opt = unet, optimizer
+        self.kind = ops.LOSS_BCE if kind == "bce" else ops.LOSS_SOFTMAX_CE
+        self.use_graph = graph
+        self.global_batch = global_batch
+        self.graphs = {}
+        self._loss_ws = None
+
+    def _eager(self, images, labels, weight, out_loss, dlogits_cache):
+        eng = self.unet.engine
+        st = eng.store
+        logits, ws = eng.forward(images, train=True)
+        b, _, hp, wp = logits.shape
+        l = labels.shape[-1]
+        nb = self.global_batch or b
+        scale = 1.0 / ((2.0 if self.kind == ops.LOSS_BCE else 1.0) * nb * l * l)
+        key = tuple(logits.shape)
+        dlogits = dlogits_cache.get(key)
+        if dlogits is None:
+            dlogits = dlogits_cache[key] = torch.zeros_like(logits)   # cropped-away border (if any) stays zero
+        if self._loss_ws is None:
+            self._loss_ws = ops.loss_workspace(logits.device)
+        ops.loss_fwd_bwd(self.kind, logits, labels, weight, dlogits, out_loss, self._loss_ws, scale)
+        for p in self.unet.parameters():   # zero_grad(): backward() refills the arena from scratch
+            p.grad = None
+        eng.backward(ws, dlogits)
+        eng.assign_grads()
+        grp = self.opt.param_groups[0]
+        ops.sgd_momentum(st.p_arena, st.g_arena, st.m_arena, float(grp["lr"]), float(grp["momentum"]), st.first_step)
+        st.first_step = False
+        st.dirty = True
+
+    def __call__(self, images, labels, weight):
+        if labels.dim() == 4:
+            labels = labels[:, 0]
+        if labels.dtype not in (torch.uint8, torch.int64):
+            labels = labels.to(torch.int64)
+        labels, weight = labels.contiguous(), weight.contiguous().float()
+        st = self.unet.engine.store
+        if not self.use_graph or st.p_arena is None or st.first_step or self.unet.engine.grad_ready_hook is not None:
+            out = torch.zeros(1, device=images.device)
+            self._eager(images, labels, weight, out, self.__dict__.setdefault("_dl", {}))
+            return out[0]
+        grp = self.opt.param_groups[0]
+        key = (tuple(images.shape), tuple(labels.shape), labels.dtype, float(grp["lr"]), float(grp["momentum"]))
+        g = self.graphs.get(key)
+        if g is None:
+            g = self.graphs[key] = self._capture(images, labels, weight)
+        g["img"].copy_(images, non_blocking=True)
+        g["lab"].copy_(labels, non_blocking=True)
+        g["w"].copy_(weight, non_blocking=True)
+        g["graph"].replay()
+        return g["loss"][0]
+
+    def _capture(self, images, labels, weight):
+        dev = images.device
+        img, lab, w = images.clone(), labels.clone(), weight.clone()
+        loss = torch.zeros(1, device=dev)
+        dl = {}
+        # warm-up on a side stream (allocates the workspace, job tables, dlogits), then capture the same schedule.
+        # NOTE: the warm-up performs a real optimizer step; it is undone by restoring parameters and momentum.
+        st = self.unet.engine.store
+        p0, m0 = st.p_arena.clone(), st.m_arena.clone()
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._eager(img, lab, w, loss, dl)
+        torch.cuda.current_stream().wait_stream(s)
+        st.p_arena.copy_(p0)
+        st.m_arena.copy_(m0)
+        st.dirty = True
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._eager(img, lab, w, loss, dl)
+        # the capture itself executed nothing; parameters are still p0
+        return {"graph": graph, "img": img, "lab": lab, "w": w, "loss": loss}

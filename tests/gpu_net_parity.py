@@ -108,6 +108,25 @@ def timing(S, B, steps=5):
           f"bwd TFLOP/s={601.3e9 * B * (S == 572) / (tb / steps * 1e-3) / 1e12:.1f}", flush=True)
 
 
+def timing_graph(S, B, steps=20):
+    torch.manual_seed(0)
+    net = Unet().to(DEV)
+    opt = T.FusedSGD(net)
+    images, labels, weight = O.synthetic_batch(B, S, seed=1)
+    x, y, w = images.to(DEV), labels.to(DEV).to(torch.uint8), weight.to(DEV)
+    for graph in (False, True):
+        step = T.TrainStep(net, opt, graph=graph)
+        for _ in range(4):
+            step(x, y, w)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(steps):
+            loss = step(x, y, w)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / steps
+        print(f"TrainStep S={S} B={B} graph={graph}: {dt * 1e3:.2f} ms/step -> {B / dt:.1f} tiles/s loss={loss.item():.4f}", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "small"):
@@ -116,6 +135,9 @@ if __name__ == "__main__":
         parity(252, 2, 2, True)
     if which in ("all", "full"):
         parity(572, 1, 0, True)
+    if which in ("all", "graph"):
+        for b in (1, 2, 4, 16):
+            timing_graph(572, b)
     if which in ("all", "time"):
         timing(572, 1)
         timing(572, 4)

@@ -146,3 +146,33 @@ def test_linearity_property_full_size_conv(tmp_path):
     ops.conv3x3_fwd(x, wp, None, y1, relu=False)
     ops.conv3x3_fwd(x * 4, wp, None, y2, relu=False)
     assert torch.equal(y2, y1 * 4)
+
+
+def test_graphed_train_step_matches_autograd_path():
+    """TrainStep (explicit schedule, CUDA-graph replay) follows the same trajectory as the autograd path
+    (network.Unet + weighted_bce_with_logits + FusedSGD) over several optimizer steps."""
+    import unet_oracle as O
+    from network import Unet
+    from b200 import train as T
+    images, labels, weight = O.synthetic_batch(2, 220, seed=21)
+    x, y, w = images.to(DEV), labels.to(DEV), weight.to(DEV)
+    torch.manual_seed(5)
+    ref = Unet().to(DEV)
+    ropt = T.FusedSGD(ref)
+    torch.manual_seed(5)
+    net = Unet().to(DEV)
+    opt = T.FusedSGD(net)
+    step = T.TrainStep(net, opt, graph=True)
+    for i in range(5):
+        ropt.zero_grad()
+        rl = T.weighted_bce_with_logits(ref(x), y, w)
+        rl.backward()
+        ropt.step()
+        gl = step(x, y, w)
+        assert abs(gl.item() - rl.item()) <= 5e-3 * abs(rl.item()), (i, gl.item(), rl.item())
+    assert len(step.graphs) == 1                                   # steps 2.. replayed one captured graph
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert max_rel(p.detach(), q.detach()) < 5e-3, k
+    opt.param_groups[0]["lr"] = 1e-5                              # ReduceLROnPlateau-style change -> new capture
+    step(x, y, w)
+    assert len(step.graphs) == 2
