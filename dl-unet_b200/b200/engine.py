@@ -235,12 +235,16 @@ class Engine:
             C = LEVEL_C[l]
             ops.upconv2x2_fwd(x, pk[f"upconv{l}"][0], P(f"upconv{l}.bias"), a[f"cat{l}"][..., C:])
             ops.conv3x3_fwd(a[f"cat{l}"], pk[f"conv{l}1e"][0], P(f"conv{l}1e.bias"), a[f"d{l}1"])
-            ops.conv3x3_fwd(a[f"d{l}1"], pk[f"conv{l}2e"][0], P(f"conv{l}2e.bias"), a[f"d{l}2"])
+            if l > 1:
+                ops.conv3x3_fwd(a[f"d{l}1"], pk[f"conv{l}2e"][0], P(f"conv{l}2e.bias"), a[f"d{l}2"])
             x = a[f"d{l}2"]
         logits = None
         if want_logits:
             logits = torch.empty(B, 2, g.out, g.out, dtype=torch.float32, device=image.device)
-        ops.head_fwd(x, P("finalconv.weight"), P("finalconv.bias"), logits, argmax_out)
+        # conv12e + finalconv in one launch: the head reads the fp32 accumulators (one bf16 rounding less on the
+        # logits); inference never writes the 64-channel activation to HBM
+        ops.conv3x3_fwd_head(a["d11"], pk["conv12e"][0], P("conv12e.bias"), a["d12"] if train else None,
+                             P("finalconv.weight"), P("finalconv.bias"), logits, argmax_out)
         return logits, ws
 
     # ------------------------------------------------------------------ backward

@@ -169,6 +169,16 @@ def conv3x3_fwd(x, w_fwd, bias, y, relu=True):
     return y
 
 
+def conv3x3_fwd_head(x, w_fwd, bias, y, head_w, head_b, logits=None, argmax=None):
+    """conv12e (bias + ReLU) with finalconv evaluated in the epilogue on the fp32 accumulators
+    (network.py:187-190).  y = None: the 64-channel activation is not stored (inference)."""
+    _need_cuda(x, w_fwd, head_w, head_b, y, logits, argmax)
+    n, h, w, ci = x.shape
+    with _timed("igemm", 2.0 * n * (h - 2) * (w - 2) * 64 * 9 * ci):
+        _chk(_lib.load().ub_conv3x3_fwd_head(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _ptr(head_w), _ptr(head_b),
+                                             _ptr(logits), _ptr(argmax), _stream()), "conv3x3_fwd_head")
+
+
 def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None):
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, co = dy.shape

@@ -240,16 +240,26 @@ bool igemm2_eligible(const ub_tensor4* in, const ub_tensor4* out) {
   return true;
 }
 
+struct HeadArgs {
+  const float* w;
+  const float* b;
+  float* logits;
+  unsigned char* argmax;
+  int store_out;
+};
+
 int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const ub_tensor4* out, int relu,
-                  const ub_tensor4* relu_src, int base_off, cudaStream_t st) {
+                  const ub_tensor4* relu_src, int base_off, cudaStream_t st, const HeadArgs* head = nullptr) {
   Igemm2Params P;
   memset(&P, 0, sizeof(P));
+  P.store_out = 1;
+  const int head_smem = head ? 3072 : 0;   // head weights + two buffers of per-row partial sums
   const int K = in->c, N = out->c;
   const int BN = (N % 128 == 0) ? 128 : 64;
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
   const int b_slot = BN * 128;
-  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/;
+  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem;
   const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
   const int nb_stat = 9 * P.kchunks;
   P.stationary = (P.n_tiles_n == 1 && nb_stat <= IG2_MAX_B && nb_stat * b_slot + 2 * a_slot1 <= limit) ? 1 : 0;
@@ -288,8 +298,16 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   }
   if ((e = make_map4(&P.a_map, in, 8 * MT + 2, 18))) return e;
   if ((e = make_map2(&P.b_map, w, 9ll * K, N, BN))) return e;
-  if ((e = make_map4(&P.o_map, out, 8, 16))) return e;
-  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024;
+  if (head) {
+    if (BN != 64 || P.n_tiles_n != 1) return UB_E_SHAPE;
+    P.head_w = head->w;
+    P.head_b = head->b;
+    P.logits = head->logits;
+    P.argmax = head->argmax;
+    P.store_out = head->store_out;
+  }
+  if (P.store_out && (e = make_map4(&P.o_map, out, 8, 16))) return e;
+  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem;
   if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
@@ -583,6 +601,30 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
   P.relu = relu;
   P.omap_div = 1 << 30;
   return launch_igemm(P, BN, (cudaStream_t)stream);
+}
+
+int ub_conv3x3_fwd_head(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y,
+                        const float* head_w, const float* head_b, float* logits, unsigned char* argmax, void* stream) {
+  int e;
+  if ((e = check_view(x))) return e;
+  if (!w_fwd || !head_w || !head_b || (!logits && !argmax)) return UB_E_ARG;
+  if (!aligned16(w_fwd) || (bias && !aligned16(bias))) return UB_E_ALIGN;
+  if (x->c > 256 || x->h < 3 || x->w < 3) return UB_E_SHAPE;
+  ub_tensor4 out;
+  if (y) {
+    if ((e = check_view(y))) return e;
+    if (y->n != x->n || y->h != x->h - 2 || y->w != x->w - 2 || y->c != 64) return UB_E_SHAPE;
+    out = *y;
+  } else {
+    // no activation store: only the geometry of the (never written) output is needed
+    out = *x;
+    out.ptr = nullptr;
+    out.h = x->h - 2;
+    out.w = x->w - 2;
+    out.c = 64;
+  }
+  HeadArgs h{head_w, head_b, logits, argmax, y ? 1 : 0};
+  return launch_igemm2(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, &h);
 }
 
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
@@ -882,6 +924,22 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
                        : 0;
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
   float* partials = reinterpret_cast<float*>(workspace) + 4;
+  const long long plane = (long long)l * l;
+  if (pad == 0 && hp == l && plane % 8 == 0 && aligned16(logits) && aligned16(weight) && aligned16(label) &&
+      (!dlogits || aligned16(dlogits))) {
+    // no crop: every image plane is one linear run -> 8 pixels per thread, all loads issued up front
+    long long lb = (total / 8 + 255) / 256;
+    if (lb > kLossMaxBlocks) lb = kLossMaxBlocks;
+    if (label_bytes == 1)
+      loss_linear_kernel<uint8_t><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(
+          logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, (unsigned int)(plane / 8), kind,
+          grad_scale);
+    else
+      loss_linear_kernel<long long><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(
+          logits, (const long long*)label, weight, dlogits, loss_out, partials, counter, b, (unsigned int)(plane / 8),
+          kind, grad_scale);
+    return (int)cudaGetLastError();
+  }
   if (label_bytes == 1)
     loss_kernel<uint8_t><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, hp, wp, l, pad, kind, grad_scale, vec4);

@@ -6,8 +6,14 @@
 
 namespace ub {
 
+// Optional fused 1x1 head (finalconv, network.py:190): `shead` = this thread's 32-column slice of the two head
+// weight rows in smem ([2][64] floats, row pitch 64); the partial dot products of the fp32, post-ReLU, NOT yet
+// bf16-rounded activations are returned in *head_part.  `stage` = false skips the bf16 staging write (inference:
+// the activation itself is never stored).
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on,
-                                          const __nv_bfloat16* mcols, uint8_t* ebuf, int row, int h) {
+                                          const __nv_bfloat16* mcols, uint8_t* ebuf, int row, int h,
+                                          const float* shead = nullptr, float2* head_part = nullptr,
+                                          bool stage = true) {
   // the mask row (64 B of this thread's pixel) is requested first: its latency overlaps the TMEM load
   uint4 m4[4];
   if (mask_on && mcols != nullptr) {
@@ -35,6 +41,18 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, in
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
   }
+  if (shead != nullptr) {
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(shead + i);       // broadcast reads
+      const float4 w1 = *reinterpret_cast<const float4*>(shead + 64 + i);
+      s0 = fmaf(f[i], w0.x, s0); s0 = fmaf(f[i + 1], w0.y, s0); s0 = fmaf(f[i + 2], w0.z, s0); s0 = fmaf(f[i + 3], w0.w, s0);
+      s1 = fmaf(f[i], w1.x, s1); s1 = fmaf(f[i + 1], w1.y, s1); s1 = fmaf(f[i + 2], w1.z, s1); s1 = fmaf(f[i + 3], w1.w, s1);
+    }
+    *head_part = make_float2(s0, s1);
+  }
+  if (!stage) return;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 o;

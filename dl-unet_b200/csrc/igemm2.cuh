@@ -34,6 +34,12 @@ struct alignas(64) Igemm2Params {
   const __nv_bfloat16* mask;
   long long mask_sn, mask_sy, mask_sx;
   int out_W, out_H;
+  // fused 1x1 head (BN = 64 = all channels of the layer): logits / argmax from the fp32 accumulators
+  const float* head_w;     // [2][64] fp32, nullptr = no head
+  const float* head_b;     // [2]
+  float* logits;           // [n][2][out_H][out_W] fp32 or nullptr
+  uint8_t* argmax;         // [n][out_H][out_W] or nullptr (class 1 iff z1 > z0: ties -> 0, tester.py:30)
+  int store_out;           // 0 = do not store the bf16 activation (inference)
 };
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
@@ -57,6 +63,8 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sbias = reinterpret_cast<float*>(epi + 2 * 16384 + 1024);
+  float* shead = reinterpret_cast<float*>(epi + 2 * 16384 + 2048);       // [2][64] weights + [2] bias (head only)
+  float2* hpart = reinterpret_cast<float2*>(epi + 2 * 16384 + 2048 + 1024);  // [2 buffers][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
-    tma_prefetch_desc(&p.o_map);
+    if (p.store_out) tma_prefetch_desc(&p.o_map);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.n_a; ++i) {
@@ -244,6 +252,13 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     const int et = threadIdx.x - 128;
     const int by = row >> 3, bx = row & 7;
     const bool mask_on = p.mask != nullptr;
+    const bool head_on = (BN == 64) && p.head_w != nullptr;
+    const bool store_out = p.store_out != 0;
+    if (head_on) {
+      if (et < 128) shead[et] = __ldg(p.head_w + et);
+      if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
+      named_bar_sync(1, 256);
+    }
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -275,14 +290,30 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
           // two staging buffers, one barrier per chunk (see igemm.cuh)
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+          float2 hp = make_float2(0.0f, 0.0f);
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, h);
+                    mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp,
+                    store_out);
+          if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
-          if (et == 0) tma_store_wait_read<0>();
+          if (et == 0 && store_out) tma_store_wait_read<0>();
           named_bar_sync(1, 256);
-          if (et == 0) {
+          if (et == 0 && store_out) {
             tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
             tma_store_commit();
+          }
+          if (head_on && h == 0 && px_valid) {
+            // the other half's partial sums were written before the barrier; this buffer is rewritten two
+            // chunks from now, i.e. after every reader has passed the next barrier
+            const float2 o = hpart[(chunk_ctr & 1) * 128 + row];
+            const float z0 = hp.x + o.x + shead[128], z1 = hp.y + o.y + shead[129];
+            const long long pix = (long long)(y0 + by) * p.out_W + (x0 + bx);
+            const long long plane = (long long)p.out_H * p.out_W;
+            if (p.logits != nullptr) {
+              p.logits[(long long)img * 2 * plane + pix] = z0;
+              p.logits[((long long)img * 2 + 1) * plane + pix] = z1;
+            }
+            if (p.argmax != nullptr) p.argmax[(long long)img * plane + pix] = (z1 > z0) ? 1 : 0;
           }
         }
       }

@@ -70,6 +70,13 @@ int ub_unpack_all(const void* table_dev, int n_jobs, long long total, int accumu
  * y[n,oy,ox,co] = act(bias[co] + sum_{r,s,ci} x[n,oy+r,ox+s,ci] * W[co,ci,r,s]);  y is (h-2)x(w-2). */
 int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, int relu,
                    void* stream);
+/* conv12e + finalconv in one launch (network.py:187-190; tester.py:30): the last 3x3 conv (<= 256 -> 64 channels,
+ * bias + ReLU) with the 1x1 64 -> 2 head evaluated in the epilogue on the fp32 accumulators, i.e. BEFORE the bf16
+ * rounding of the activation.  y may be NULL (inference: the 64-channel activation is never written to HBM).
+ * logits: fp32 [n,2,h-2,w-2] NCHW or NULL; argmax: uint8 [n,h-2,w-2] or NULL (1 iff z1 > z0: ties -> class 0). */
+int ub_conv3x3_fwd_head(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y,
+                        const float* head_w, const float* head_b, float* logits_nchw, unsigned char* argmax,
+                        void* stream);
 /* dx = full correlation of dy with the rotated weights; if relu_src != NULL the ReLU backward of the
  * layer that produced x is fused: dx *= (relu_src > 0).  (autograd of network.py:131-188) */
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,

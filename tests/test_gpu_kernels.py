@@ -70,6 +70,39 @@ def test_conv3x3_fwd_dgrad_wgrad(ops, shape):
     assert rel_l2(dw, gw) < FP32_TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 6, 6, 64), (2, 45, 37, 64), (1, 70, 70, 128), (3, 20, 26, 64)])
+def test_conv3x3_fwd_fused_head(ops, shape):
+    """conv12e + finalconv in one launch (network.py:187-190): logits come from the fp32 accumulators, so they match
+    the fp32 reference to fp32 tolerance -- tighter than conv -> bf16 store -> head; the stored activation still is
+    the bf16-rounded conv output; y = None (inference) gives the same logits and the tester.py:30 argmax."""
+    n, h, w, cin = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(64, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(64, device=DEV)
+    hw = torch.randn(2, 64, 1, 1, device=DEV) / 8
+    hb = torch.randn(2, device=DEV)
+    act = F.relu(F.conv2d(bf(x).float(), bf(wt).float(), b))
+    ref = F.conv2d(act, hw, hb)
+    wp = ops.pack_weight(wt, ops.PACK_CONV_FWD)
+    y = torch.full((n, h - 2, w - 2, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+    logits = torch.full((n, 2, h - 2, w - 2), float("nan"), device=DEV)
+    ops.conv3x3_fwd_head(nhwc(x), wp, b, y, hw, hb, logits, None)
+    assert rel_l2(nchw(y), act) < BF16_OUT_TOL
+    assert rel_l2(logits, ref) < FP32_TOL
+    y2 = torch.empty_like(y)
+    ops.conv3x3_fwd(nhwc(x), wp, b, y2, relu=True)
+    assert torch.equal(y, y2)                                          # same activation bits as the plain conv
+    lg2 = torch.full_like(logits, float("nan"))
+    am = torch.full((n, h - 2, w - 2), 7, dtype=torch.uint8, device=DEV)
+    ops.conv3x3_fwd_head(nhwc(x), wp, b, None, hw, hb, lg2, am)        # inference: no activation store
+    assert torch.equal(lg2, logits)
+    assert torch.equal(am.long(), (logits[:, 1] > logits[:, 0]).long())
+    am2 = torch.full_like(am, 7)
+    ops.conv3x3_fwd_head(nhwc(x), wp, b, None, hw, hb, None, am2)      # argmax only
+    assert torch.equal(am2, am)
+
+
 def test_conv3x3_strided_views_write_in_place(ops):
     n, h, w, cin, cout = 2, 22, 22, 64, 128
     torch.manual_seed(1)
@@ -201,7 +234,7 @@ def test_head_fwd_bwd(ops):
     assert rel_l2(dw.view(2, 64, 1, 1), gw) < 1e-3 and rel_l2(db, gb) < FP32_TOL
 
 
-@pytest.mark.parametrize("case", [(1, 36, 36), (3, 40, 36), (2, 388, 388)])
+@pytest.mark.parametrize("case", [(1, 36, 36), (3, 40, 36), (2, 388, 388), (2, 30, 30), (5, 44, 44)])
 def test_losses_fwd_bwd(ops, case):
     b, hp, l = case
     torch.manual_seed(6)
