@@ -218,17 +218,17 @@ void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) 
   P.out_H = H;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool HEAD = false>
 int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm2_kernel<BN, MT><<<grid, 384, smem_bytes, st>>>(P);
+  igemm2_kernel<BN, MT, HEAD><<<grid, 384, smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
 }
 
@@ -308,6 +308,7 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   }
   if (P.store_out && (e = make_map4(&P.o_map, out, 8, 16))) return e;
   const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem;
+  if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
   if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
@@ -929,7 +930,7 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
       (!dlogits || aligned16(dlogits))) {
     // no crop: every image plane is one linear run -> 8 pixels per thread, all loads issued up front
     long long lb = (total / 8 + 255) / 256;
-    if (lb > kLossMaxBlocks) lb = kLossMaxBlocks;
+    if (lb > 4ll * num_sms()) lb = 4ll * num_sms();   // persistent: 4 CTAs per SM, grid-stride with prefetch
     if (label_bytes == 1)
       loss_linear_kernel<uint8_t><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(
           logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, (unsigned int)(plane / 8), kind,

@@ -527,54 +527,80 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
 // plane is one linear run, so a thread owns 8 consecutive pixels and issues all of its loads (2 x 128 bit per
 // logit channel and weight, 64 bit of uint8 labels) before the first use: ~104 B in flight per thread instead
 // of 52, no row/column index arithmetic.  Same partial-sum protocol as loss_kernel.
-__device__ __forceinline__ void load_labels8(const uint8_t* p, int (&lab)[8]) {
+// 8 labels -> one bit mask (bit i = label i is non-zero, i.e. class 1 of the one-hot target, trainer.py:63-66)
+__device__ __forceinline__ uint32_t load_labels8(const uint8_t* p) {
   const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  uint32_t m = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    lab[i] = (u.x >> (8 * i)) & 0xff;
-    lab[4 + i] = (u.y >> (8 * i)) & 0xff;
+    m |= ((u.x >> (8 * i)) & 0xffu) ? (1u << i) : 0u;
+    m |= ((u.y >> (8 * i)) & 0xffu) ? (16u << i) : 0u;
   }
+  return m;
 }
-__device__ __forceinline__ void load_labels8(const long long* p, int (&lab)[8]) {
+__device__ __forceinline__ uint32_t load_labels8(const long long* p) {
+  uint32_t m = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(p) + i);
-    lab[2 * i] = (int)v.x;
-    lab[2 * i + 1] = (int)v.y;
+    m |= (v.x != 0 ? 1u : 0u) << (2 * i);
+    m |= (v.y != 0 ? 1u : 0u) << (2 * i + 1);
   }
+  return m;
 }
 
 template <typename LabelT>
-__global__ void __launch_bounds__(256) loss_linear_kernel(const float* __restrict__ logits,
-                                                          const LabelT* __restrict__ label,
-                                                          const float* __restrict__ weight, float* __restrict__ dlogits,
-                                                          float* __restrict__ loss_out, float* __restrict__ partials,
-                                                          unsigned int* __restrict__ counter, int B,
-                                                          unsigned int plane8, int kind, float grad_scale) {
+struct LossUnit {           // the 8 pixels a thread works on: 6 x 128-bit loads + the labels
+  float4 a0, a1, b0, b1, w0, w1;
+  uint32_t lab;   // bit i = class of pixel i
+};
+
+template <typename LabelT>
+__device__ __forceinline__ void loss_unit_load(LossUnit<LabelT>& q, unsigned int u, unsigned int plane8,
+                                               long long plane, const float* __restrict__ logits,
+                                               const LabelT* __restrict__ label, const float* __restrict__ weight) {
+  const unsigned int n = u / plane8;
+  const long long loff = (long long)u * 8;
+  const long long zoff = loff + (long long)n * plane;    // = n*2*plane + (u - n*plane8)*8
+  const float4* z0p = reinterpret_cast<const float4*>(logits + zoff);
+  const float4* z1p = reinterpret_cast<const float4*>(logits + zoff + plane);
+  const float4* wp = reinterpret_cast<const float4*>(weight + loff);
+  q.a0 = __ldg(z0p); q.a1 = __ldg(z0p + 1);
+  q.b0 = __ldg(z1p); q.b1 = __ldg(z1p + 1);
+  q.w0 = __ldg(wp);  q.w1 = __ldg(wp + 1);
+  q.lab = load_labels8(label + loff);
+}
+
+// Persistent grid (4 CTAs per SM), grid-stride over 8-pixel units with a one-unit register prefetch: the loads
+// of unit i+1 are in flight while the ~50 MUFU operations of unit i run, so the SFU time (6 MUFU per pixel for
+// the BCE form, ~12 us at config 5) hides under the HBM time instead of adding to it.
+template <typename LabelT>
+__global__ void __launch_bounds__(256, 4) loss_linear_kernel(const float* __restrict__ logits,
+                                                             const LabelT* __restrict__ label,
+                                                             const float* __restrict__ weight,
+                                                             float* __restrict__ dlogits, float* __restrict__ loss_out,
+                                                             float* __restrict__ partials,
+                                                             unsigned int* __restrict__ counter, int B,
+                                                             unsigned int plane8, int kind, float grad_scale) {
   const unsigned int total_u = (unsigned int)B * plane8;
   const long long plane = (long long)plane8 * 8;
+  const unsigned int stride = gridDim.x * blockDim.x;
   float acc = 0.0f;
-  for (unsigned int u = blockIdx.x * blockDim.x + threadIdx.x; u < total_u; u += gridDim.x * blockDim.x) {
-    const unsigned int n = u / plane8;
-    const unsigned int r = u - n * plane8;
-    const long long zoff = (long long)n * 2 * plane + (long long)r * 8;
-    const long long loff = (long long)u * 8;
-    const float4* z0p = reinterpret_cast<const float4*>(logits + zoff);
-    const float4* z1p = reinterpret_cast<const float4*>(logits + zoff + plane);
-    const float4* wp = reinterpret_cast<const float4*>(weight + loff);
-    const float4 a0 = __ldg(z0p), a1 = __ldg(z0p + 1);
-    const float4 b0 = __ldg(z1p), b1 = __ldg(z1p + 1);
-    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-    int lab[8];
-    load_labels8(label + loff, lab);
-    const float z0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float z1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  unsigned int u = blockIdx.x * blockDim.x + threadIdx.x;
+  LossUnit<LabelT> nx;
+  if (u < total_u) loss_unit_load(nx, u, plane8, plane, logits, label, weight);
+  for (; u < total_u; u += stride) {
+    const LossUnit<LabelT> q = nx;
+    if (u + stride < total_u) loss_unit_load(nx, u + stride, plane8, plane, logits, label, weight);
+    const float z0[8] = {q.a0.x, q.a0.y, q.a0.z, q.a0.w, q.a1.x, q.a1.y, q.a1.z, q.a1.w};
+    const float z1[8] = {q.b0.x, q.b0.y, q.b0.z, q.b0.w, q.b1.x, q.b1.y, q.b1.z, q.b1.w};
+    const float wv[8] = {q.w0.x, q.w0.y, q.w0.z, q.w0.w, q.w1.x, q.w1.y, q.w1.z, q.w1.w};
     float g0[8], g1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      const bool lab = (q.lab >> i) & 1u;
       if (kind == 0) {
-        const float y0 = lab[i] ? 0.0f : 1.0f, y1 = lab[i] ? 1.0f : 0.0f;
+        const float y0 = lab ? 0.0f : 1.0f, y1 = lab ? 1.0f : 0.0f;
         const float e0 = __expf(-fabsf(z0[i])), e1 = __expf(-fabsf(z1[i]));
         const float l0 = fmaxf(z0[i], 0.0f) - y0 * z0[i] + __logf(1.0f + e0);
         const float l1 = fmaxf(z1[i], 0.0f) - y1 * z1[i] + __logf(1.0f + e1);
@@ -584,16 +610,19 @@ __global__ void __launch_bounds__(256) loss_linear_kernel(const float* __restric
         g0[i] = wv[i] * (s0 - y0) * grad_scale;
         g1[i] = wv[i] * (s1 - y1) * grad_scale;
       } else {
-        const float m = fmaxf(z0[i], z1[i]);
-        const float e0 = __expf(z0[i] - m), e1 = __expf(z1[i] - m);
-        const float ssum = e0 + e1;
-        acc += wv[i] * (m + __logf(ssum) - (lab[i] ? z1[i] : z0[i]));
-        const float inv = __fdividef(1.0f, ssum);
-        g0[i] = wv[i] * (e0 * inv - (lab[i] ? 0.0f : 1.0f)) * grad_scale;
-        g1[i] = wv[i] * (e1 * inv - (lab[i] ? 1.0f : 0.0f)) * grad_scale;
+        // two classes: logsumexp(z) - z_l = softplus(z_other - z_l), softmax_1 = sigmoid(z1 - z0): 3 MUFU per pixel
+        const float d = z1[i] - z0[i];
+        const float e = __expf(-fabsf(d));
+        const float r = __fdividef(1.0f, 1.0f + e);
+        const float p1 = d >= 0.0f ? r : e * r;               // softmax probability of class 1
+        const float t = lab ? -d : d;                          // z_other - z_label
+        acc += wv[i] * (fmaxf(t, 0.0f) + __logf(1.0f + e));
+        g1[i] = wv[i] * (p1 - (lab ? 1.0f : 0.0f)) * grad_scale;
+        g0[i] = -g1[i];
       }
     }
     if (dlogits != nullptr) {
+      const long long zoff = (long long)u * 8 + (long long)(u / plane8) * plane;
       float4* d0p = reinterpret_cast<float4*>(dlogits + zoff);
       float4* d1p = reinterpret_cast<float4*>(dlogits + zoff + plane);
       d0p[0] = make_float4(g0[0], g0[1], g0[2], g0[3]);

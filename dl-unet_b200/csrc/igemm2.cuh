@@ -44,7 +44,7 @@ struct alignas(64) Igemm2Params {
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
 
-template <int BN, int MT>
+template <int BN, int MT, bool HEAD = false>
 __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
   constexpr int P = 8 * MT + 2;          // patch width in pixels
   constexpr int B_BYTES = BN * 128;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
-    if (p.store_out) tma_prefetch_desc(&p.o_map);
+    if (!HEAD || p.store_out) tma_prefetch_desc(&p.o_map);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.n_a; ++i) {
@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     const int et = threadIdx.x - 128;
     const int by = row >> 3, bx = row & 7;
     const bool mask_on = p.mask != nullptr;
-    const bool head_on = (BN == 64) && p.head_w != nullptr;
-    const bool store_out = p.store_out != 0;
+    constexpr bool head_on = HEAD && BN == 64;   // separate instantiation: the plain conv epilogue stays lean
+    const bool store_out = !head_on || p.store_out != 0;
     if (head_on) {
       if (et < 128) shead[et] = __ldg(p.head_w + et);
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
