@@ -76,3 +76,18 @@ for (name, kind, cin, cout) in LAYERS:
     print(f"{name:10s} {hin:4d} {cin:5d} {cout:5d} | {t_f:8.1f} {fl / t_f / 1e6:7.1f} | {t_d:8.1f} {fl / t_d / 1e6:7.1f} | "
           f"{t_w0:8.1f} {fl / t_w0 / 1e6:7.1f} | {t_w2:8.1f} {fl / t_w2 / 1e6:7.1f} | {t_w5:8.1f} {fl / t_w5 / 1e6:7.1f} | w4 {t_w4:7.1f} auto {t_auto:7.1f}", flush=True)
 print("totals (ms):", {k: round(v / 1e3, 2) for k, v in tot.items()})
+
+# conv12e + finalconv: fused epilogue head vs conv -> bf16 store -> head kernel
+x = rnd(B, 390, 390, 64)
+y = torch.empty(B, 388, 388, 64, dtype=torch.bfloat16, device=DEV)
+wf = rnd(64, 9 * 64) / 30
+bias = torch.zeros(64, device=DEV)
+hw, hb = torch.randn(2, 64, device=DEV) / 8, torch.zeros(2, device=DEV)
+lg = torch.empty(B, 2, 388, 388, device=DEV)
+am = torch.empty(B, 388, 388, dtype=torch.uint8, device=DEV)
+t_plain = timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y))
+t_head = timeit(lambda: ops.head_fwd(y, hw, hb, lg, None))
+t_fused = timeit(lambda: ops.conv3x3_fwd_head(x, wf, bias, y, hw, hb, lg, None))
+t_inf = timeit(lambda: ops.conv3x3_fwd_head(x, wf, bias, None, hw, hb, None, am))
+print(f"conv12e+head: conv {t_plain:.1f} us + head {t_head:.1f} us = {t_plain + t_head:.1f} us; fused (train) {t_fused:.1f} us; "
+      f"fused, no activation store, argmax only (inference) {t_inf:.1f} us")
