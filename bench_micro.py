@@ -105,6 +105,41 @@ def main():
     run("sgd_momentum (31.03 M params)", nel * 20, [lambda: ops.sgd_momentum(pa, ga, ma, 1e-4, 0.99, False)],
         "working set 372 MB > L2")
 
+    # ---- loss weight maps (functions.py:7-78) for 16 label tiles of 388x388, on the device vs the reference's
+    # CPU route (OpenCV per sample, restated in dl-unet_b200/functions.py) on the host cores of this box
+    import time
+    from b200 import weightmap
+    from b200.synth import synthetic_batch
+    import functions as Fn
+    _, labels, _ = synthetic_batch(16, 572, seed=5)
+    lab_cpu = labels[:, 0].contiguous()
+    lab = lab_cpu.to(dev)
+    wout = torch.empty(16, 388, 388, device=dev)
+    px = 16 * 388 * 388
+    for check in (False,):
+        for f in (lambda: weightmap.weighted_map(lab, check=check, out=wout),):
+            f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.reps):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / args.reps * 1e3
+    t0 = time.perf_counter()
+    wref = Fn.weighted_map(lab_cpu[:4])
+    cpu_us = (time.perf_counter() - t0) / 4 * 16 * 1e6
+    same = float((wout[:4].cpu() - wref).abs().max())
+    # algorithmic bytes: label 8 B in + fp32 map out per pixel (the candidate / component planes are internal)
+    print(json.dumps({"kernel": "weighted_map 16 x 388x388 (6 launches)", "us": round(us, 2), "algorithmic_MB": round(px * 12 / 1e6, 1),
+                      "achieved_GBs": round(px * 12 / us / 1e3, 1), "peak_GBs": peak, "frac": round(px * 12 / us / 1e3 / peak, 4),
+                      "tiles_per_s": round(16 / (us * 1e-6), 1), "cpu_reference_us": round(cpu_us, 1),
+                      "cpu_tiles_per_s": round(16 / (cpu_us * 1e-6), 2), "speedup_vs_cpu": round(cpu_us / us, 1),
+                      "max_abs_diff_vs_cpu": same,
+                      "note": "latency-bound integer kernels (union-find, column scan, pruned row scan); CPU = OpenCV route on "
+                              f"{os.cpu_count()} host cores (single-threaded per sample, as the reference)"}), flush=True)
+
 
 if __name__ == "__main__":
     main()

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "elementwise.cuh"
+#include "weightmap.cuh"
 #include "igemm.cuh"
 #include "igemm2.cuh"
 #include "probe.cuh"
@@ -477,6 +478,36 @@ int set_mask(IgemmParams& P, const ub_tensor4* relu_src, const ub_tensor4* dx) {
   P.mask_sy = relu_src->sy;
   P.mask_sx = relu_src->sx;
   return make_map4(&P.m_map, relu_src, P.BW, P.BH);
+}
+
+static long long wm_align(long long v) { return (v + 255) & ~255ll; }
+
+template <typename LabelT>
+static int weight_map_t(const LabelT* gt, int b, int h, int w, double w0, double sigma2, int truncate_wc, float* out,
+                        void* workspace, int* status, int class_balance_only, cudaStream_t st) {
+  const int hw = h * w;
+  const long long total = (long long)b * hw;
+  char* ws = reinterpret_cast<char*>(workspace);
+  int* count1 = reinterpret_cast<int*>(ws);
+  int* L = reinterpret_cast<int*>(ws + wm_align(4ll * b));
+  uint32_t* cand = reinterpret_cast<uint32_t*>(ws + wm_align(4ll * b) + wm_align(4ll * total));
+  cudaError_t e = cudaMemsetAsync(count1, 0, 4ll * b, st);
+  if (e != cudaSuccess) return (int)e;
+  int cb = (hw + 255) / 256;
+  if (cb > 64) cb = 64;
+  wm_count_kernel<LabelT><<<dim3(cb, b), 256, 0, st>>>(gt, count1, hw);
+  if (class_balance_only) {
+    wm_class_balance_kernel<LabelT><<<dim3(cb, b), 256, 0, st>>>(gt, count1, out, status, hw);
+    return (int)cudaGetLastError();
+  }
+  const int g = ew_grid(total);
+  wm_init_kernel<LabelT><<<g, 256, 0, st>>>(gt, L, hw, total);
+  wm_merge_kernel<<<g, 256, 0, st>>>(L, h, w, b);
+  wm_flatten_kernel<<<g, 256, 0, st>>>(L, hw, total);
+  wm_columns_kernel<<<dim3((w + 127) / 128, b), 128, 0, st>>>(L, cand, h, w, b);
+  wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 16 * w, st>>>(gt, cand, count1, out, status, h, w, w0,
+                                                                            2.0 * sigma2, truncate_wc);
+  return (int)cudaGetLastError();
 }
 
 }  // namespace
@@ -948,6 +979,53 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
     loss_kernel<long long><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         logits, (const long long*)label, weight, dlogits, loss_out, partials, counter, b, hp, wp, l, pad, kind,
         grad_scale, vec4);
+  return (int)cudaGetLastError();
+}
+
+// ---- loss weight maps (functions.py:7-117) ----------------------------------------------------------------
+long long ub_weight_map_workspace_bytes(int b, int h, int w) {
+  if (b <= 0 || h <= 0 || w <= 0) return 0;
+  const long long hw = (long long)h * w;
+  return wm_align(4ll * b) + wm_align(4ll * b * hw) + wm_align(16ll * b * hw);
+}
+
+int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, double w0, double sigma2, int truncate_wc,
+                  float* out, void* workspace, int* status, void* stream) {
+  if (!label || !out || !workspace || !status) return UB_E_ARG;
+  if (label_bytes != 1 && label_bytes != 8) return UB_E_ARG;
+  // packed candidates: dy < 2^11, label + 1 < 2^21; shared row buffer 16 B per column; grid.y / grid.z limits
+  if (b <= 0 || b > 65535 || h <= 0 || w <= 0 || h >= 2048 || w > 2048 || (long long)h * w >= (1ll << 21) - 1) return UB_E_SHAPE;
+  if (label_bytes == 1)
+    return weight_map_t<uint8_t>((const uint8_t*)label, b, h, w, w0, sigma2, truncate_wc, out, workspace, status, 0,
+                                 (cudaStream_t)stream);
+  return weight_map_t<long long>((const long long*)label, b, h, w, w0, sigma2, truncate_wc, out, workspace, status, 0,
+                                 (cudaStream_t)stream);
+}
+
+int ub_class_balance(const void* label, int label_bytes, int b, int h, int w, float* out, void* workspace, int* status,
+                     void* stream) {
+  if (!label || !out || !workspace || !status) return UB_E_ARG;
+  if (label_bytes != 1 && label_bytes != 8) return UB_E_ARG;
+  if (b <= 0 || b > 65535 || h <= 0 || w <= 0 || (long long)h * w >= (1ll << 31)) return UB_E_SHAPE;
+  if (label_bytes == 1)
+    return weight_map_t<uint8_t>((const uint8_t*)label, b, h, w, 0, 1, 0, out, workspace, status, 1, (cudaStream_t)stream);
+  return weight_map_t<long long>((const long long*)label, b, h, w, 0, 1, 0, out, workspace, status, 1, (cudaStream_t)stream);
+}
+
+int ub_mask_metrics(const void* pred, int pred_bytes, const void* label, int label_bytes, long long n,
+                    unsigned long long* counts, void* stream) {
+  if (!pred || !label || !counts || n <= 0) return UB_E_ARG;
+  if ((pred_bytes != 1 && pred_bytes != 8) || (label_bytes != 1 && label_bytes != 8)) return UB_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = ew_grid(n);
+  if (pred_bytes == 1 && label_bytes == 1)
+    mask_metrics_kernel<uint8_t, uint8_t><<<g, 256, 0, st>>>((const uint8_t*)pred, (const uint8_t*)label, counts, n);
+  else if (pred_bytes == 1)
+    mask_metrics_kernel<uint8_t, long long><<<g, 256, 0, st>>>((const uint8_t*)pred, (const long long*)label, counts, n);
+  else if (label_bytes == 1)
+    mask_metrics_kernel<long long, uint8_t><<<g, 256, 0, st>>>((const long long*)pred, (const uint8_t*)label, counts, n);
+  else
+    mask_metrics_kernel<long long, long long><<<g, 256, 0, st>>>((const long long*)pred, (const long long*)label, counts, n);
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,253 @@
+// Loss weight maps on the device (functions.py:7-78 `weighted_map`, functions.py:82-117 `class_balance`):
+//   w = w_c + w0 * exp(-(d1 + d2)^2 / (2 sigma^2)) * (1 - gt)
+// with d1 / d2 the exact Euclidean distances to the nearest / second-nearest 4-connected foreground object.
+// The reference does this per sample on the CPU (OpenCV connectedComponents + one distanceTransform PER OBJECT +
+// a sort over objects); here it is four integer kernels and the result is bit-compatible with the reference:
+//   1. wm_init / wm_merge / wm_flatten : 4-connected component labelling, union-find with atomicMin on a
+//      label image (label = smallest linear pixel index of the component + 1; 0 = background).
+//   2. wm_columns : per column, for every row the nearest foreground pixel above (and below) and the nearest
+//      one above (below) that belongs to a DIFFERENT object: <= 4 candidates (dy, label) per pixel, packed
+//      into 32 bits.  These four are sufficient for the two nearest distinct objects: a third object further
+//      along the same column direction is beaten by the two before it.
+//   3. wm_rows : per pixel, scan the row's columns outwards (x, x-1, x+1, ...) over the 4 candidates each,
+//      keeping (d1^2, label1, d2^2) in exact integer arithmetic, and stop as soon as dx^2 >= d2^2.
+//      d = sqrtf((float)d^2) is what OpenCV's DIST_L2 / DIST_MASK_PRECISE transform returns; the rest of the
+//      formula runs in fp64 and is rounded to fp32 once, like the numpy expression it replaces.
+// All byte / integer work, HBM- and latency-bound; one launch each for the whole batch.
+#pragma once
+#include <cstdint>
+
+namespace ub {
+
+constexpr uint32_t WM_INVALID = 0xffffffffu;
+constexpr int WM_DY_BITS = 11;   // dy <= 2047, label + 1 < 2^21
+
+template <typename LabelT>
+__device__ __forceinline__ bool wm_fg(const LabelT* __restrict__ gt, long long i) {
+  return (uint8_t)gt[i] != 0;   // connectedComponents runs on gt.astype(uint8): non-zero byte = foreground
+}
+
+// ---- counts: c1[b] = number of label == 1 ... (non-zero) pixels
+template <typename LabelT>
+__global__ void __launch_bounds__(256) wm_count_kernel(const LabelT* __restrict__ gt, int* __restrict__ count1,
+                                                       int hw) {
+  const int b = blockIdx.y;
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+    c += gt[(long long)b * hw + i] != 0 ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count1 + b, c);
+}
+
+// ---- connected components (4-connectivity)
+__device__ __forceinline__ int wm_find(const int* L, int i) {
+  int p = __ldcg(L + i);   // L2 reads: other threads re-parent nodes with atomics while we walk
+  while (p != i) {
+    i = p;
+    p = __ldcg(L + i);
+  }
+  return i;
+}
+
+__device__ __forceinline__ void wm_union(int* L, int a, int b) {
+  while (true) {
+    a = wm_find(L, a);
+    b = wm_find(L, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(L + b, a);   // hang the larger root under the smaller one
+    if (old == b) return;
+    b = old;                               // somebody re-parented b meanwhile: retry from there
+  }
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(256) wm_init_kernel(const LabelT* __restrict__ gt, int* __restrict__ L, int hw,
+                                                      long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    L[i] = wm_fg(gt, i) ? (int)(i % hw) : -1;   // parent pointers are indices inside the sample's own plane
+}
+
+__global__ void __launch_bounds__(256) wm_merge_kernel(int* L, int H, int W, int B) {
+  const int hw = H * W;
+  const long long total = (long long)B * hw;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(g / hw), i = (int)(g - (long long)b * hw);
+    int* Lb = L + (long long)b * hw;
+    if (Lb[i] < 0) continue;
+    const int x = i % W;
+    if (x > 0 && Lb[i - 1] >= 0) wm_union(Lb, i, i - 1);
+    if (i >= W && Lb[i - W] >= 0) wm_union(Lb, i, i - W);
+  }
+}
+
+__global__ void __launch_bounds__(256) wm_flatten_kernel(int* L, int hw, long long total) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long base = g - g % hw;
+    const int i = (int)(g - base);
+    if (L[g] >= 0) L[g] = wm_find(L + base, i);   // roots are fixed points, so concurrent flattening is safe
+  }
+}
+
+// ---- column pass: thread = (sample, column); cand[b][y][k][x], k = up1, up2, down1, down2
+__device__ __forceinline__ uint32_t wm_pack(int dy, int label) { return ((uint32_t)(label + 1) << WM_DY_BITS) | (uint32_t)dy; }
+
+__global__ void __launch_bounds__(128) wm_columns_kernel(const int* __restrict__ L, uint32_t* __restrict__ cand, int H,
+                                                         int W, int B) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (x >= W) return;
+  const int* Lb = L + (long long)b * H * W;
+  uint32_t* cb = cand + (long long)b * H * 4 * W;
+  int y1 = -1, l1 = -1, y2 = -1, l2 = -1;   // nearest fg pixel so far / nearest one of another object
+#pragma unroll 8
+  for (int y = 0; y < H; ++y) {
+    const int l = Lb[y * W + x];
+    if (l >= 0) {
+      if (l != l1) {
+        y2 = y1;
+        l2 = l1;
+        l1 = l;
+      }
+      y1 = y;
+    }
+    cb[((long long)y * 4 + 0) * W + x] = l1 >= 0 ? wm_pack(y - y1, l1) : WM_INVALID;
+    cb[((long long)y * 4 + 1) * W + x] = l2 >= 0 ? wm_pack(y - y2, l2) : WM_INVALID;
+  }
+  y1 = l1 = y2 = l2 = -1;
+#pragma unroll 8
+  for (int y = H - 1; y >= 0; --y) {
+    const int l = Lb[y * W + x];
+    if (l >= 0) {
+      if (l != l1) {
+        y2 = y1;
+        l2 = l1;
+        l1 = l;
+      }
+      y1 = y;
+    }
+    cb[((long long)y * 4 + 2) * W + x] = l1 >= 0 ? wm_pack(y1 - y, l1) : WM_INVALID;
+    cb[((long long)y * 4 + 3) * W + x] = l2 >= 0 ? wm_pack(y2 - y, l2) : WM_INVALID;
+  }
+}
+
+// ---- row pass + formula.  grid = (ceil(W / 128), H, B); the row's candidates live in shared memory.
+struct WmState {
+  uint32_t d1, d2;   // squared distances (exact)
+  uint32_t l1;       // label + 1 of the nearest object
+};
+
+__device__ __forceinline__ void wm_offer(WmState& s, uint32_t c, uint32_t dx2) {
+  if (c == WM_INVALID) return;
+  const uint32_t dy = c & ((1u << WM_DY_BITS) - 1u);
+  const uint32_t l = c >> WM_DY_BITS;
+  const uint32_t d = dx2 + dy * dy;
+  if (l == s.l1) {
+    s.d1 = min(s.d1, d);
+  } else if (d < s.d1) {   // a new nearest object: the old nearest becomes the best of "all the others"
+    s.d2 = s.d1;
+    s.d1 = d;
+    s.l1 = l;
+  } else {
+    s.d2 = min(s.d2, d);
+  }
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__ gt, const uint32_t* __restrict__ cand,
+                                                      const int* __restrict__ count1, float* __restrict__ out,
+                                                      int* __restrict__ status, int H, int W, double w0,
+                                                      double two_sigma2, int truncate_wc) {
+  extern __shared__ uint32_t srow[];   // [4][W]
+  const int y = blockIdx.y, b = blockIdx.z;
+  const uint32_t* crow = cand + ((long long)b * H + y) * 4 * W;
+  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) srow[i] = crow[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const long long pix = ((long long)b * H + y) * W + x;
+  const bool fg = gt[pix] != 0;
+  WmState s{WM_INVALID, WM_INVALID, 0u};
+  for (int k = 0; k < W && !fg; ++k) {   // foreground pixels get w_d = 0: (1 - gt) in functions.py:70
+    const uint32_t k2 = (uint32_t)k * (uint32_t)k;
+    if (k2 >= s.d2) break;   // nothing at |dx| >= k can improve either distance
+    const int xl = x - k, xr = x + k;
+    if (xl < 0 && xr >= W) break;
+    if (xl >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wm_offer(s, srow[j * W + xl], k2);
+    }
+    if (k > 0 && xr < W) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wm_offer(s, srow[j * W + xr], k2);
+    }
+  }
+  const int hw = H * W;
+  const int c1 = count1[b], c0 = hw - c1;
+  // w_c (functions.py:34-40): counts[1] / counts[class]; held in the label's dtype, so an integer label truncates
+  float wc = fg ? 1.0f : (float)c1 / (float)c0;
+  if (truncate_wc) wc = truncf(wc);
+  double wd = 0.0;
+  if (!fg && s.d1 != WM_INVALID) {
+    const double d1 = (double)sqrtf((float)s.d1);
+    const double d2 = s.d2 != WM_INVALID ? (double)sqrtf((float)s.d2) : 0.0;   // one object: d2 = 0 (functions.py:62-64)
+    const double t = d1 + d2;
+    wd = w0 * exp(-(t * t) / two_sigma2);
+  }
+  out[pix] = (float)((double)wc + wd);
+  if (x == 0 && y == 0) {
+    int st = 0;
+    if (c1 == 0 || c0 == 0) st |= 1;   // a single class: the reference's counts[1] raises IndexError
+    if (c1 == 0) st |= 2;              // no object: maps[0] raises IndexError
+    status[b] = st;
+  }
+}
+
+// class_balance (functions.py:82-117): w = counts[1] / counts[class] in fp32
+template <typename LabelT>
+__global__ void __launch_bounds__(256) wm_class_balance_kernel(const LabelT* __restrict__ gt,
+                                                               const int* __restrict__ count1, float* __restrict__ out,
+                                                               int* __restrict__ status, int hw) {
+  const int b = blockIdx.y;
+  const int c1 = count1[b], c0 = hw - c1;
+  const float w0 = (float)c1 / (float)c0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+    out[(long long)b * hw + i] = gt[(long long)b * hw + i] != 0 ? 1.0f : w0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[b] = (c1 == 0 || c0 == 0) ? 1 : 0;
+}
+
+// ---- mask metrics (functions.py:150-213): counts for IoU = |p & l| / |p | l| and pixel error = sum|p - l| / n.
+// out[0] += |p & l|, out[1] += |p | l|, out[2] += sum |p - l| (64-bit counters, caller zeroes).
+template <typename PT, typename LT>
+__global__ void __launch_bounds__(256) mask_metrics_kernel(const PT* __restrict__ pred, const LT* __restrict__ label,
+                                                           unsigned long long* __restrict__ out, long long n) {
+  unsigned int inter = 0, uni = 0;
+  unsigned long long diff = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = (long long)pred[i], l = (long long)label[i];
+    inter += (p != 0 && l != 0) ? 1u : 0u;      // np.logical_and / np.logical_or
+    uni += (p != 0 || l != 0) ? 1u : 0u;
+    diff += (unsigned long long)(p > l ? p - l : l - p);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    uni += __shfl_xor_sync(0xffffffffu, uni, o);
+    diff += __shfl_xor_sync(0xffffffffu, diff, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (inter) atomicAdd(out, (unsigned long long)inter);
+    if (uni) atomicAdd(out + 1, (unsigned long long)uni);
+    if (diff) atomicAdd(out + 2, diff);
+  }
+}
+
+}  // namespace ub

@@ -18,7 +18,11 @@ except Exception:  # pragma: no cover
 
 def class_balance(gt_batch):
     """functions.py:82-117: per-sample class-frequency weights, w[gt == v] = count(1) / count(v)
-    with `counts[1]` the SECOND unique value (IndexError on a single-class label, as upstream)."""
+    with `counts[1]` the SECOND unique value (IndexError on a single-class label, as upstream).
+    A CUDA label batch is processed on the device (b200.weightmap)."""
+    if gt_batch.is_cuda:
+        from b200 import weightmap as _wm
+        return _wm.class_balance(gt_batch)
     w_batch = torch.empty(gt_batch.shape, dtype=torch.float32)
     for b in range(gt_batch.shape[0]):
         gt = gt_batch[b]
@@ -35,6 +39,9 @@ def weighted_map(gt_batch):
     pixels, with the file's constants (w0 = 20, sigma^2 = 25), 4-connected components and exact L2
     distance transforms.  w_c is held in the label's dtype, so an int64 label truncates the class
     ratio exactly like the reference does (functions.py:37-40)."""
+    if gt_batch.is_cuda:   # device path: csrc/weightmap.cuh, same values (and quirks) without OpenCV or the host
+        from b200 import weightmap as _wm
+        return _wm.weighted_map(gt_batch)
     if _cv is None:
         raise RuntimeError("weighted_map needs OpenCV (cv2), as the reference does")
     w0, sig2 = 20, 25
@@ -79,7 +86,10 @@ def IoU(pred, label):
 
 
 def evaluation_metrics(pred, label):
-    """functions.py:150-168: 2x1 array [IoU; pixel error]."""
+    """functions.py:150-168: 2x1 array [IoU; pixel error].  CUDA masks are reduced on the device."""
+    if pred.is_cuda and label.is_cuda:
+        from b200 import weightmap as _wm
+        return _wm.evaluation_metrics(pred, label)
     out = np.empty([2, 1])
     out[0] = IoU(pred, label)
     out[1] = Pixel_error(pred, label)

@@ -30,7 +30,7 @@ def testing(unet, test_loader, batch_size, device, output_dir):
         if test_eval is None:
             # the reference accumulates with np.concatenate but drops the result (tester.py:42):
             # its statistics are those of the first image
-            test_eval = evaluation_metrics(pred[0].detach(), label[0, 0].detach())
+            test_eval = evaluation_metrics(pred[0].detach(), label[0, 0].to(pred.device))   # reduced on the device
 
     test = np.mean(test_eval, axis=1)
     test_std = np.std(test_eval, axis=1)

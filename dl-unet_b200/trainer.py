@@ -38,7 +38,8 @@ def _goal_for(dataset):
 
 
 def _weights_for(dataset, labels):
-    """trainer.py:68-73 -- CPU weight map for the batch ([B,L,L] fp32)."""
+    """trainer.py:68-73 -- weight map for the batch ([B,L,L] fp32).  `labels` already lives on the training
+    device: on CUDA the maps are built there (b200/weightmap.py) instead of by OpenCV on the host."""
     gt = labels.squeeze(1)
     return weighted_map(gt) if dataset is HELA else class_balance(gt)
 
@@ -85,6 +86,7 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
         for images, labels in train_loader:
             optimizer.zero_grad()
             logits = unet(images.to(device, non_blocking=True))
+            labels = labels.to(device, non_blocking=True)
             weight_maps = _weights_for(DATASET, labels)
             loss = weighted_bce_with_logits(logits, labels, weight_maps)
             loss.backward()
@@ -101,6 +103,7 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
         with torch.no_grad():
             for images, labels in val_loader:
                 logits = unet(images.to(device, non_blocking=True))
+                labels = labels.to(device, non_blocking=True)
                 weight_maps = _weights_for(DATASET, labels)
                 total_loss_val += weighted_bce_with_logits(logits, labels, weight_maps)
                 if val_eval is None:

@@ -126,6 +126,29 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
                     float* dlogits, float* loss_out, void* workspace, int b, int hp, int wp, int l, float grad_scale,
                     void* stream);
 
+/* ---- loss weight maps on the device (functions.py:7-78 weighted_map, functions.py:82-117 class_balance) ----
+ * label: [b,h,w] uint8 (label_bytes 1) or int64 (8), binary {0,1}.  out: fp32 [b,h,w].
+ *   weighted_map: w = w_c + w0*exp(-(d1+d2)^2 / (2*sigma2)) * (1 - gt), d1/d2 = exact Euclidean distance to the
+ *   nearest / second-nearest 4-connected object (d2 = 0 when there is only one), w_c = count(1)/count(class);
+ *   truncate_wc != 0 reproduces the reference's integer-label truncation of w_c (functions.py:37-40).
+ *   The reference's constants are w0 = 20, sigma2 = 25 (functions.py:29-30).
+ *   class_balance: w = count(1)/count(class) in fp32.
+ * status: device int[b]; bit 0 = the sample has a single class, bit 1 = no object -- the cases in which the
+ * reference raises IndexError (functions.py:40 / :60); the host wrapper turns them into that exception.
+ * workspace: ub_weight_map_workspace_bytes(b,h,w) bytes of device memory (component labels + column candidates).
+ * Limits: h < 2048, w <= 2048, h*w < 2^21 - 1 (packed 32-bit candidates). */
+long long ub_weight_map_workspace_bytes(int b, int h, int w);
+int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, double w0, double sigma2, int truncate_wc,
+                  float* out, void* workspace, int* status, void* stream);
+int ub_class_balance(const void* label, int label_bytes, int b, int h, int w, float* out, void* workspace, int* status,
+                     void* stream);
+
+/* ---- segmentation metrics on the device (functions.py:150-213: IoU, Pixel_error) ----
+ * pred / label: n elements, uint8 (bytes 1) or int64 (8).  counts[3] (device, caller zeroes) receive
+ * |pred & label|, |pred | label| and sum |pred - label|:  IoU = counts[0]/counts[1], pixel error = counts[2]/n. */
+int ub_mask_metrics(const void* pred, int pred_bytes, const void* label, int label_bytes, long long n,
+                    unsigned long long* counts, void* stream);
+
 /* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients); out += */
 int ub_colsum(const void* g_bf16, float* out, long long n_pix, int c, long long ld, void* stream);
 

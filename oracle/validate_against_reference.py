@@ -156,6 +156,27 @@ def main():
     cb = ref_functions.class_balance(lab)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "class_balance.npz"), lab=lab.numpy(), w=cb.numpy())
 
+    # ---- weight maps (functions.py:7-117) vs oracle/weightmap_oracle.py, SURVEY.md section 8 row f1.
+    # cv.distanceTransform's float sqrt is not correctly rounded (1 ulp off on ~20 % of the pixels, measured here
+    # with OpenCV 4.13), the oracle's is (IEEE sqrtf of the exact integer d^2): so the pin is "equal within
+    # 2.5e-6 absolute" (2 float ulps at w <= 21) and bit-equal wherever OpenCV's sqrt happens to be exact.
+    import weightmap_oracle as W
+    for kind, size, b, seed in (("blobs", 96, 2, 3), ("noise", 48, 1, 4), ("single", 64, 1, 5), ("blobs", 388, 1, 6)):
+        lab = W.synthetic_labels(b, size, seed, kind)
+        gold = dict(kind=kind, size=size, batch=b, seed=seed)
+        for tag, tdt, ndt in (("i64", torch.int64, np.int64), ("f32", torch.float32, np.float32)):
+            rw = ref_functions.weighted_map(torch.from_numpy(lab).to(tdt)).numpy()
+            ow = W.weighted_map(lab.astype(ndt))
+            check(f"weighted_map {kind} {size} {tag}: oracle within 2.5e-6 of the reference "
+                  f"(bit-equal on {100.0 * (rw == ow).mean():.1f} % of pixels)", float(np.abs(rw - ow).max()) <= 2.5e-6)
+            gold["w_" + tag] = rw
+        rc = ref_functions.class_balance(torch.from_numpy(lab)).numpy()
+        check(f"class_balance {kind} {size}: bit-equal", np.array_equal(rc, W.class_balance(lab)))
+        gold["cb"] = rc
+        path = os.path.join(ROOT, "tests", "golden", f"weightmap_{kind}_{size}.npz")
+        np.savez_compressed(path, **gold)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
     print("ALL PASS" if ok else "SOME CHECKS FAILED")
     return 0 if ok else 1
 

@@ -66,3 +66,29 @@ def test_oracle_bit_equal_to_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "validate_against_reference.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["weightmap_blobs_96", "weightmap_noise_48", "weightmap_single_64", "weightmap_blobs_388"])
+def test_weightmap_oracle_reproduces_reference_golden(golden_dir, name):
+    """oracle/weightmap_oracle.py (scipy, no OpenCV) against the outputs of the reference's own weighted_map /
+    class_balance (functions.py:7-117) stored by validate_against_reference.py.  Tolerance 2.5e-6 absolute: OpenCV's
+    float sqrt is 1 ulp off on part of the pixels, everything else is bit-equal (see the oracle's header)."""
+    import weightmap_oracle as W
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    lab = W.synthetic_labels(int(g["batch"]), int(g["size"]), int(g["seed"]), str(g["kind"]))
+    for tag, dt in (("i64", np.int64), ("f32", np.float32)):
+        w = W.weighted_map(lab.astype(dt))
+        assert w.dtype == np.float32 and float(np.abs(w - g["w_" + tag]).max()) <= 2.5e-6
+        assert (w == g["w_" + tag]).mean() > 0.5
+    assert np.array_equal(W.class_balance(lab), g["cb"])
+    # the integer-label quirk (functions.py:37-40): w_c is truncated, so background weights lose the class ratio
+    bg = lab == 0
+    assert np.all(g["w_i64"][bg] <= g["w_f32"][bg] + 1e-6)
+
+
+def test_weightmap_oracle_raises_like_reference():
+    import weightmap_oracle as W
+    with pytest.raises(IndexError):
+        W.weighted_map(np.zeros((1, 8, 8), dtype=np.int64))      # single class: counts[1] (functions.py:40)
+    with pytest.raises(IndexError):
+        W.class_balance(np.ones((1, 8, 8), dtype=np.int64))
