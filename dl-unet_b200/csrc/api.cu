@@ -489,9 +489,10 @@ static int weight_map_t(const LabelT* gt, int b, int h, int w, double w0, double
   const long long total = (long long)b * hw;
   char* ws = reinterpret_cast<char*>(workspace);
   int* count1 = reinterpret_cast<int*>(ws);
-  int* L = reinterpret_cast<int*>(ws + wm_align(4ll * b));
-  uint32_t* cand = reinterpret_cast<uint32_t*>(ws + wm_align(4ll * b) + wm_align(4ll * total));
-  cudaError_t e = cudaMemsetAsync(count1, 0, 4ll * b, st);
+  int* n_obj = count1 + b;
+  int* L = reinterpret_cast<int*>(ws + wm_align(8ll * b));
+  uint32_t* cand = reinterpret_cast<uint32_t*>(ws + wm_align(8ll * b) + wm_align(4ll * total));
+  cudaError_t e = cudaMemsetAsync(count1, 0, 8ll * b, st);
   if (e != cudaSuccess) return (int)e;
   int cb = (hw + 255) / 256;
   if (cb > 64) cb = 64;
@@ -501,12 +502,19 @@ static int weight_map_t(const LabelT* gt, int b, int h, int w, double w0, double
     return (int)cudaGetLastError();
   }
   const int g = ew_grid(total);
-  wm_init_kernel<LabelT><<<g, 256, 0, st>>>(gt, L, hw, total);
+  wm_init_kernel<LabelT><<<(int)(((long long)b * h + 7) / 8), 256, 0, st>>>(gt, L, h, w, b);
   wm_merge_kernel<<<g, 256, 0, st>>>(L, h, w, b);
-  wm_flatten_kernel<<<g, 256, 0, st>>>(L, hw, total);
+  wm_flatten_kernel<<<g, 256, 0, st>>>(L, n_obj, hw, total);
   wm_columns_kernel<<<dim3((w + 127) / 128, b), 128, 0, st>>>(L, cand, h, w, b);
-  wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 16 * w, st>>>(gt, cand, count1, out, status, h, w, w0,
-                                                                            2.0 * sigma2, truncate_wc);
+  // search radius: w0 * exp(-t^2 / (2 sigma^2)) < 2^-150 (rounds to +0 in fp32) for t >= cap
+  int cap = w > h ? w : h;
+  if (w0 > 0.0 && sigma2 > 0.0) {
+    const double t2 = 2.0 * sigma2 * (log(w0) + 150.0 * 0.6931471805599453);
+    const double t = t2 > 0.0 ? sqrt(t2) : 0.0;
+    if (t + 2.0 < (double)cap) cap = (int)t + 2;
+  }
+  wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 16 * w, st>>>(gt, cand, count1, n_obj, out, status, h, w,
+                                                                            w0, 2.0 * sigma2, truncate_wc, cap);
   return (int)cudaGetLastError();
 }
 
@@ -986,7 +994,7 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
 long long ub_weight_map_workspace_bytes(int b, int h, int w) {
   if (b <= 0 || h <= 0 || w <= 0) return 0;
   const long long hw = (long long)h * w;
-  return wm_align(4ll * b) + wm_align(4ll * b * hw) + wm_align(16ll * b * hw);
+  return wm_align(8ll * b) + wm_align(4ll * b * hw) + wm_align(16ll * b * hw);
 }
 
 int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, double w0, double sigma2, int truncate_wc,

@@ -66,14 +66,36 @@ __device__ __forceinline__ void wm_union(int* L, int a, int b) {
   }
 }
 
+// One warp per image row: every foreground pixel starts out pointing at the first pixel of its horizontal run
+// (ballot + count-leading-zeros per 32-pixel chunk, run start carried across chunks), so the horizontal unions
+// are done before the union-find starts.
 template <typename LabelT>
-__global__ void __launch_bounds__(256) wm_init_kernel(const LabelT* __restrict__ gt, int* __restrict__ L, int hw,
-                                                      long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x)
-    L[i] = wm_fg(gt, i) ? (int)(i % hw) : -1;   // parent pointers are indices inside the sample's own plane
+__global__ void __launch_bounds__(256) wm_init_kernel(const LabelT* __restrict__ gt, int* __restrict__ L, int H,
+                                                      int W, int B) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * H) return;
+  const int y = (int)(row % H);
+  const LabelT* g = gt + row * W;
+  int* Lr = L + row * W;
+  int carry = -1;   // run start (x) if the pixel just left of this chunk is foreground
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    const bool fg = x < W && (uint8_t)g[x] != 0;   // connectedComponents runs on gt.astype(uint8)
+    const uint32_t m = __ballot_sync(0xffffffffu, fg);
+    const uint32_t zeros_below = ~m & ((1u << lane) - 1u);
+    int start;
+    if (zeros_below) start = x0 + (32 - __clz(zeros_below));   // just right of the nearest background pixel
+    else start = carry >= 0 ? carry : x0;
+    if (x < W) Lr[x] = fg ? y * W + start : -1;
+    // carry for the next chunk: run start of lane 31 if it is foreground
+    const int s31 = __shfl_sync(0xffffffffu, start, 31);
+    carry = (m >> 31) ? s31 : -1;
+  }
 }
 
+// Vertical unions, only where a new overlap between two runs begins: pixel and its upper neighbour are foreground
+// and (left, upper-left) are not both foreground (otherwise the pixel to the left already joined the two runs).
 __global__ void __launch_bounds__(256) wm_merge_kernel(int* L, int H, int W, int B) {
   const int hw = H * W;
   const long long total = (long long)B * hw;
@@ -81,19 +103,22 @@ __global__ void __launch_bounds__(256) wm_merge_kernel(int* L, int H, int W, int
        g += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(g / hw), i = (int)(g - (long long)b * hw);
     int* Lb = L + (long long)b * hw;
-    if (Lb[i] < 0) continue;
+    if (i < W || Lb[i] < 0 || Lb[i - W] < 0) continue;
     const int x = i % W;
-    if (x > 0 && Lb[i - 1] >= 0) wm_union(Lb, i, i - 1);
-    if (i >= W && Lb[i - W] >= 0) wm_union(Lb, i, i - W);
+    if (x > 0 && Lb[i - 1] >= 0 && Lb[i - W - 1] >= 0) continue;
+    wm_union(Lb, i, i - W);
   }
 }
 
-__global__ void __launch_bounds__(256) wm_flatten_kernel(int* L, int hw, long long total) {
+__global__ void __launch_bounds__(256) wm_flatten_kernel(int* L, int* __restrict__ n_obj, int hw, long long total) {
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
        g += (long long)gridDim.x * blockDim.x) {
     const long long base = g - g % hw;
     const int i = (int)(g - base);
-    if (L[g] >= 0) L[g] = wm_find(L + base, i);   // roots are fixed points, so concurrent flattening is safe
+    if (L[g] < 0) continue;
+    const int r = wm_find(L + base, i);   // roots are fixed points, so concurrent flattening is safe
+    L[g] = r;
+    if (r == i) atomicAdd(n_obj + g / hw, 1);   // one root per object
   }
 }
 
@@ -163,9 +188,9 @@ __device__ __forceinline__ void wm_offer(WmState& s, uint32_t c, uint32_t dx2) {
 
 template <typename LabelT>
 __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__ gt, const uint32_t* __restrict__ cand,
-                                                      const int* __restrict__ count1, float* __restrict__ out,
-                                                      int* __restrict__ status, int H, int W, double w0,
-                                                      double two_sigma2, int truncate_wc) {
+                                                      const int* __restrict__ count1, const int* __restrict__ n_obj,
+                                                      float* __restrict__ out, int* __restrict__ status, int H, int W,
+                                                      double w0, double two_sigma2, int truncate_wc, int cap) {
   extern __shared__ uint32_t srow[];   // [4][W]
   const int y = blockIdx.y, b = blockIdx.z;
   const uint32_t* crow = cand + ((long long)b * H + y) * 4 * W;
@@ -176,7 +201,10 @@ __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__
   const long long pix = ((long long)b * H + y) * W + x;
   const bool fg = gt[pix] != 0;
   WmState s{WM_INVALID, WM_INVALID, 0u};
-  for (int k = 0; k < W && !fg; ++k) {   // foreground pixels get w_d = 0: (1 - gt) in functions.py:70
+  // `cap`: beyond d1 + d2 >= cap the term w0 * exp(-(d1+d2)^2 / 2 sigma^2) is below 2^-150 and rounds to +0 in
+  // fp32 whatever w_c is, so neither distance needs to be known beyond it (set by the host from w0 and sigma).
+  const int kmax = min(W, cap);
+  for (int k = 0; k < kmax && !fg; ++k) {   // foreground pixels get w_d = 0: (1 - gt) in functions.py:70
     const uint32_t k2 = (uint32_t)k * (uint32_t)k;
     if (k2 >= s.d2) break;   // nothing at |dx| >= k can improve either distance
     const int xl = x - k, xr = x + k;
@@ -196,11 +224,12 @@ __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__
   float wc = fg ? 1.0f : (float)c1 / (float)c0;
   if (truncate_wc) wc = truncf(wc);
   double wd = 0.0;
-  if (!fg && s.d1 != WM_INVALID) {
+  const bool one_object = n_obj[b] == 1;   // then d2 = 0 (functions.py:62-64)
+  if (!fg && s.d1 != WM_INVALID && (one_object || s.d2 != WM_INVALID)) {
     const double d1 = (double)sqrtf((float)s.d1);
-    const double d2 = s.d2 != WM_INVALID ? (double)sqrtf((float)s.d2) : 0.0;   // one object: d2 = 0 (functions.py:62-64)
+    const double d2 = one_object ? 0.0 : (double)sqrtf((float)s.d2);
     const double t = d1 + d2;
-    wd = w0 * exp(-(t * t) / two_sigma2);
+    wd = w0 * exp(-(t * t) / two_sigma2);   // a distance that was cut off at `cap` only ever lands here as exp -> 0
   }
   out[pix] = (float)((double)wc + wd);
   if (x == 0 && y == 0) {
