@@ -505,15 +505,17 @@ static int weight_map_t(const LabelT* gt, int b, int h, int w, double w0, double
   wm_init_kernel<LabelT><<<(int)(((long long)b * h + 7) / 8), 256, 0, st>>>(gt, L, h, w, b);
   wm_merge_kernel<<<g, 256, 0, st>>>(L, h, w, b);
   wm_flatten_kernel<<<g, 256, 0, st>>>(L, n_obj, hw, total);
-  wm_columns_kernel<<<dim3((w + 127) / 128, b), 128, 0, st>>>(L, cand, h, w, b);
-  // search radius: w0 * exp(-t^2 / (2 sigma^2)) < 2^-150 (rounds to +0 in fp32) for t >= cap
-  int cap = w > h ? w : h;
+  // cut-off distance: w0 * exp(-t^2 / (2 sigma^2)) < 2^-150 (rounds to +0 in fp32) for t >= cap.  It is a property
+  // of (w0, sigma) alone -- the kernels clamp their loops to the image themselves.
+  int cap = 1 << 20;
   if (w0 > 0.0 && sigma2 > 0.0) {
     const double t2 = 2.0 * sigma2 * (log(w0) + 150.0 * 0.6931471805599453);
     const double t = t2 > 0.0 ? sqrt(t2) : 0.0;
     if (t + 2.0 < (double)cap) cap = (int)t + 2;
   }
-  wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 16 * w, st>>>(gt, cand, count1, n_obj, out, status, h, w,
+  if (cap > 32767) cap = 32767;   // keeps cap * cap inside 32 bits; images are < 2048 pixels high anyway
+  wm_columns_kernel<<<dim3((w + 127) / 128, (h + WM_SEG - 1) / WM_SEG, b), 128, 0, st>>>(L, cand, h, w, cap);
+  wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 8 * w, st>>>(gt, cand, count1, n_obj, out, status, h, w,
                                                                             w0, 2.0 * sigma2, truncate_wc, cap);
   return (int)cudaGetLastError();
 }
@@ -994,7 +996,7 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
 long long ub_weight_map_workspace_bytes(int b, int h, int w) {
   if (b <= 0 || h <= 0 || w <= 0) return 0;
   const long long hw = (long long)h * w;
-  return wm_align(8ll * b) + wm_align(4ll * b * hw) + wm_align(16ll * b * hw);
+  return wm_align(8ll * b) + wm_align(4ll * b * hw) + wm_align(8ll * b * hw);
 }
 
 int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, double w0, double sigma2, int truncate_wc,

@@ -3,16 +3,19 @@
 // with d1 / d2 the exact Euclidean distances to the nearest / second-nearest 4-connected foreground object.
 // The reference does this per sample on the CPU (OpenCV connectedComponents + one distanceTransform PER OBJECT +
 // a sort over objects); here it is four integer kernels and the result is bit-compatible with the reference:
-//   1. wm_init / wm_merge / wm_flatten : 4-connected component labelling, union-find with atomicMin on a
-//      label image (label = smallest linear pixel index of the component + 1; 0 = background).
-//   2. wm_columns : per column, for every row the nearest foreground pixel above (and below) and the nearest
-//      one above (below) that belongs to a DIFFERENT object: <= 4 candidates (dy, label) per pixel, packed
-//      into 32 bits.  These four are sufficient for the two nearest distinct objects: a third object further
-//      along the same column direction is beaten by the two before it.
-//   3. wm_rows : per pixel, scan the row's columns outwards (x, x-1, x+1, ...) over the 4 candidates each,
-//      keeping (d1^2, label1, d2^2) in exact integer arithmetic, and stop as soon as dx^2 >= d2^2.
-//      d = sqrtf((float)d^2) is what OpenCV's DIST_L2 / DIST_MASK_PRECISE transform returns; the rest of the
-//      formula runs in fp64 and is rounded to fp32 once, like the numpy expression it replaces.
+//   1. wm_init / wm_merge / wm_flatten : 4-connected component labelling.  One warp per row points every
+//      foreground pixel at the start of its horizontal run (ballot + clz), vertical unions are issued only where a
+//      new overlap between two runs begins (union-find with atomicMin), then every pixel is pointed at its root
+//      (label = smallest linear pixel index of the component) and the roots are counted.
+//   2. wm_columns : per column and row, the two nearest foreground pixels of DIFFERENT objects in that column
+//      (dy, label), packed into 32 bits each.  Two per column are sufficient for the two nearest distinct objects
+//      of any pixel: all candidates of a column share dx.
+//   3. wm_rows : per pixel, scan the row's columns outwards (x, x-1, x+1, ...) keeping (d1^2, label1, d2^2) in
+//      exact integer arithmetic, and stop as soon as dx^2 >= d2^2, or once both distances are known to be so
+//      large that the exponential term is exactly +0 in fp32.
+//      d = sqrtf((float)d^2) is what OpenCV's DIST_L2 / DIST_MASK_PRECISE transform returns (up to OpenCV's own
+//      1-ulp sqrt error); the rest of the formula runs in fp64 and is rounded to fp32 once, like the numpy
+//      expression it replaces.
 // All byte / integer work, HBM- and latency-bound; one launch each for the whole batch.
 #pragma once
 #include <cstdint>
@@ -122,45 +125,92 @@ __global__ void __launch_bounds__(256) wm_flatten_kernel(int* L, int* __restrict
   }
 }
 
-// ---- column pass: thread = (sample, column); cand[b][y][k][x], k = up1, up2, down1, down2
+// ---- column pass: thread = (sample, 32-row segment, column) -> cand[b][y][2][x]: the two nearest foreground pixels
+// OF DIFFERENT OBJECTS in column x as seen from row y, packed (label + 1) << 11 | dy, nearest first.
+// Two per column are sufficient for the two nearest distinct objects of any pixel of the row: all candidates of one
+// column share dx, so a third object of that column is beaten by the two before it, and a farther pixel of the same
+// object by the nearer one.  They are the best two of four: the nearest pixel above / below and the nearest pixel
+// above / below that belongs to another object than that one (found by walking the column down, then up).
+// Distances of `cap` rows or more are dropped: beyond d1 + d2 >= cap the weight term is exactly +0 in fp32 (see
+// wm_rows_kernel), so the state a segment inherits from the rows before it is found by looking back < cap rows.
+constexpr int WM_SEG = 32;
 __device__ __forceinline__ uint32_t wm_pack(int dy, int label) { return ((uint32_t)(label + 1) << WM_DY_BITS) | (uint32_t)dy; }
+__device__ __forceinline__ uint32_t wm_dy(uint32_t c) { return c & ((1u << WM_DY_BITS) - 1u); }
+__device__ __forceinline__ uint32_t wm_label(uint32_t c) { return c >> WM_DY_BITS; }
+
+struct WmScan {
+  int y1, l1, y2, l2;   // row / label of the nearest foreground pixel, and of the nearest one of another object
+  __device__ __forceinline__ void see(int y, int l) {      // rows arrive in scan order (monotone y)
+    if (l < 0) return;
+    if (l != l1) {
+      y2 = y1;
+      l2 = l1;
+      l1 = l;
+    }
+    y1 = y;
+  }
+  // state before a segment: walk away from it (step = -1 above, +1 below) until two objects are known
+  __device__ __forceinline__ void inherit(const int* __restrict__ col, int W, int y_from, int y_stop, int step) {
+    y1 = l1 = y2 = l2 = -1;
+    for (int y = y_from; y != y_stop; y += step) {
+      const int l = col[(long long)y * W];
+      if (l < 0) continue;
+      if (l1 < 0) {
+        y1 = y;
+        l1 = l;
+      } else if (l != l1) {
+        y2 = y;
+        l2 = l;
+        return;
+      }
+    }
+  }
+};
+
+// best two of (a1, a2, b1, b2) with different labels; a1 / b1 are the nearest of their direction
+__device__ __forceinline__ void wm_best2(uint32_t a1, uint32_t a2, uint32_t b1, uint32_t b2, uint32_t& c1, uint32_t& c2) {
+  // WM_INVALID has dy = 2047 = the largest, so plain comparisons of dy sort it last
+  c1 = (wm_dy(b1) < wm_dy(a1)) ? b1 : a1;
+  c2 = WM_INVALID;
+  if (c1 == WM_INVALID) return;
+  const uint32_t l = wm_label(c1);
+  uint32_t best = 1u << WM_DY_BITS;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t c = i == 0 ? a1 : i == 1 ? a2 : i == 2 ? b1 : b2;
+    if (c != WM_INVALID && wm_label(c) != l && wm_dy(c) < best) {
+      best = wm_dy(c);
+      c2 = c;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(128) wm_columns_kernel(const int* __restrict__ L, uint32_t* __restrict__ cand, int H,
-                                                         int W, int B) {
+                                                         int W, int cap) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
+  const int y0 = blockIdx.y * WM_SEG, b = blockIdx.z;
   if (x >= W) return;
-  const int* Lb = L + (long long)b * H * W;
-  uint32_t* cb = cand + (long long)b * H * 4 * W;
-  int y1 = -1, l1 = -1, y2 = -1, l2 = -1;   // nearest fg pixel so far / nearest one of another object
-#pragma unroll 8
-  for (int y = 0; y < H; ++y) {
-    const int l = Lb[y * W + x];
-    if (l >= 0) {
-      if (l != l1) {
-        y2 = y1;
-        l2 = l1;
-        l1 = l;
-      }
-      y1 = y;
-    }
-    cb[((long long)y * 4 + 0) * W + x] = l1 >= 0 ? wm_pack(y - y1, l1) : WM_INVALID;
-    cb[((long long)y * 4 + 1) * W + x] = l2 >= 0 ? wm_pack(y - y2, l2) : WM_INVALID;
+  const int y_end = min(H, y0 + WM_SEG);
+  const int* Lb = L + (long long)b * H * W + x;
+  uint32_t* cb = cand + (long long)b * H * 2 * W + x;
+  WmScan s;
+  s.inherit(Lb, W, y0 - 1, max(-1, y0 - cap), -1);
+  for (int y = y0; y < y_end; ++y) {          // candidates above: parked in the output planes until the walk back
+    s.see(y, Lb[(long long)y * W]);
+    const int d1 = y - s.y1, d2 = y - s.y2;
+    cb[((long long)y * 2 + 0) * W] = (s.l1 >= 0 && d1 < cap) ? wm_pack(d1, s.l1) : WM_INVALID;
+    cb[((long long)y * 2 + 1) * W] = (s.l2 >= 0 && d2 < cap) ? wm_pack(d2, s.l2) : WM_INVALID;
   }
-  y1 = l1 = y2 = l2 = -1;
-#pragma unroll 8
-  for (int y = H - 1; y >= 0; --y) {
-    const int l = Lb[y * W + x];
-    if (l >= 0) {
-      if (l != l1) {
-        y2 = y1;
-        l2 = l1;
-        l1 = l;
-      }
-      y1 = y;
-    }
-    cb[((long long)y * 4 + 2) * W + x] = l1 >= 0 ? wm_pack(y1 - y, l1) : WM_INVALID;
-    cb[((long long)y * 4 + 3) * W + x] = l2 >= 0 ? wm_pack(y2 - y, l2) : WM_INVALID;
+  s.inherit(Lb, W, y_end, min(H, y_end - 1 + cap), 1);
+  for (int y = y_end - 1; y >= y0; --y) {     // candidates below, merged with the ones above
+    s.see(y, Lb[(long long)y * W]);
+    const int d1 = s.y1 - y, d2 = s.y2 - y;
+    const uint32_t b1 = (s.l1 >= 0 && d1 < cap) ? wm_pack(d1, s.l1) : WM_INVALID;
+    const uint32_t b2 = (s.l2 >= 0 && d2 < cap) ? wm_pack(d2, s.l2) : WM_INVALID;
+    uint32_t c1, c2;
+    wm_best2(cb[((long long)y * 2 + 0) * W], cb[((long long)y * 2 + 1) * W], b1, b2, c1, c2);
+    cb[((long long)y * 2 + 0) * W] = c1;
+    cb[((long long)y * 2 + 1) * W] = c2;
   }
 }
 
@@ -170,11 +220,7 @@ struct WmState {
   uint32_t l1;       // label + 1 of the nearest object
 };
 
-__device__ __forceinline__ void wm_offer(WmState& s, uint32_t c, uint32_t dx2) {
-  if (c == WM_INVALID) return;
-  const uint32_t dy = c & ((1u << WM_DY_BITS) - 1u);
-  const uint32_t l = c >> WM_DY_BITS;
-  const uint32_t d = dx2 + dy * dy;
+__device__ __forceinline__ void wm_offer(WmState& s, uint32_t l, uint32_t d) {
   if (l == s.l1) {
     s.d1 = min(s.d1, d);
   } else if (d < s.d1) {   // a new nearest object: the old nearest becomes the best of "all the others"
@@ -191,10 +237,10 @@ __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__
                                                       const int* __restrict__ count1, const int* __restrict__ n_obj,
                                                       float* __restrict__ out, int* __restrict__ status, int H, int W,
                                                       double w0, double two_sigma2, int truncate_wc, int cap) {
-  extern __shared__ uint32_t srow[];   // [4][W]
+  extern __shared__ uint32_t srow[];   // [2][W]: the two candidates of every column of this row
   const int y = blockIdx.y, b = blockIdx.z;
-  const uint32_t* crow = cand + ((long long)b * H + y) * 4 * W;
-  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) srow[i] = crow[i];
+  const uint32_t* crow = cand + ((long long)b * H + y) * 2 * W;
+  for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) srow[i] = crow[i];
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
@@ -203,19 +249,30 @@ __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__
   WmState s{WM_INVALID, WM_INVALID, 0u};
   // `cap`: beyond d1 + d2 >= cap the term w0 * exp(-(d1+d2)^2 / 2 sigma^2) is below 2^-150 and rounds to +0 in
   // fp32 whatever w_c is, so neither distance needs to be known beyond it (set by the host from w0 and sigma).
+  const bool one_object = n_obj[b] == 1;   // then d2 = 0 (functions.py:62-64)
   const int kmax = min(W, cap);
+  const uint32_t cap2 = (uint32_t)cap * (uint32_t)cap;
   for (int k = 0; k < kmax && !fg; ++k) {   // foreground pixels get w_d = 0: (1 - gt) in functions.py:70
     const uint32_t k2 = (uint32_t)k * (uint32_t)k;
     if (k2 >= s.d2) break;   // nothing at |dx| >= k can improve either distance
+    // every unseen candidate is >= k away, so d1_final >= min(d1, k) and d2_final >= min(d2, k): once both are
+    // >= k >= cap / 2 the sum is >= cap and the weight term is +0 whatever is still out there
+    if (!one_object && 4u * k2 >= cap2 && s.d1 >= k2) break;
     const int xl = x - k, xr = x + k;
     if (xl < 0 && xr >= W) break;
-    if (xl >= 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wm_offer(s, srow[j * W + xl], k2);
-    }
-    if (k > 0 && xr < W) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wm_offer(s, srow[j * W + xr], k2);
+    for (int side = 0; side < 2; ++side) {
+      const int xc = side == 0 ? xl : xr;
+      if (xc < 0 || xc >= W || (side == 1 && k == 0)) continue;
+      const uint32_t c1 = srow[xc];
+      if (c1 == WM_INVALID) continue;
+      const uint32_t dy1 = wm_dy(c1), e1 = k2 + dy1 * dy1;
+      if (e1 >= s.d2) continue;                 // the column's nearest cannot improve anything, nor can its second
+      wm_offer(s, wm_label(c1), e1);
+      const uint32_t c2 = srow[W + xc];
+      if (c2 == WM_INVALID) continue;
+      const uint32_t dy2 = wm_dy(c2);
+      wm_offer(s, wm_label(c2), k2 + dy2 * dy2);
     }
   }
   const int hw = H * W;
@@ -224,7 +281,6 @@ __global__ void __launch_bounds__(128) wm_rows_kernel(const LabelT* __restrict__
   float wc = fg ? 1.0f : (float)c1 / (float)c0;
   if (truncate_wc) wc = truncf(wc);
   double wd = 0.0;
-  const bool one_object = n_obj[b] == 1;   // then d2 = 0 (functions.py:62-64)
   if (!fg && s.d1 != WM_INVALID && (one_object || s.d2 != WM_INVALID)) {
     const double d1 = (double)sqrtf((float)s.d1);
     const double d2 = one_object ? 0.0 : (double)sqrtf((float)s.d2);
