@@ -255,14 +255,16 @@ class Engine:
             e = st.g_off[lname + ".bias"] + _align(st.numel[lname + ".bias"])
             self.grad_ready_hook(s, e)
 
-    def _conv_bwd(self, lname, x, dy, dx, relu_src):
-        """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer."""
+    def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False):
+        """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer.  bias_done: the kernel that
+        produced dy (pool / head backward) already accumulated its column sums into the bias gradient."""
         st = self.store
         dwp = st.dwp(lname)
         ops.conv3x3_wgrad(x, dy, dwp)
         if self.grad_ready_hook is not None:  # data parallel: the layer's gradient must be final now
             ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
-        ops.colsum(dy, st.g(lname + ".bias"))
+        if not bias_done:
+            ops.colsum(dy, st.g(lname + ".bias"))
         self._ready(lname)
         if dx is not None:
             ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src)
@@ -282,12 +284,12 @@ class Engine:
         dlogits = dlogits.contiguous().float()
 
         ops.head_bwd(a["d12"], P("finalconv.weight"), dlogits, gr["d12"], st.g("finalconv.weight"),
-                     st.g("finalconv.bias"))
+                     st.g("finalconv.bias"), st.g("conv12e.bias"))
         self._ready("finalconv")
         dy = gr["d12"]
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
-            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"])
+            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=(l == 1))
             self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None)
             # up-convolution: its output is the upper channel half of the concat buffer
             up_name = f"upconv{l}"
@@ -310,8 +312,9 @@ class Engine:
             H = g.enc2[l]
             if H & 1:
                 gr[f"e{l}2"].zero_()  # floor-mode pool: the last row / column gets no gradient
-            ops.pool2x2_bwd(gr[f"p{l}"], gr[f"cat{l}"][..., :C], g.coff[l], a[f"i{l}"], a[f"p{l}"], gr[f"e{l}2"])
-            self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"])
+            ops.pool2x2_bwd(gr[f"p{l}"], gr[f"cat{l}"][..., :C], g.coff[l], a[f"i{l}"], a[f"p{l}"], gr[f"e{l}2"],
+                            st.g(f"conv{l}2c.bias"))
+            self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"], bias_done=True)
             if l > 1:
                 self._conv_bwd(f"conv{l}1c", a[f"p{l - 1}"], gr[f"e{l}1"], gr[f"p{l - 1}"], None)
             else:

@@ -49,9 +49,9 @@ SIGNATURES = {
     "ub_conv1_fwd": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
     "ub_conv1_wgrad": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
     "ub_pool2x2_fwd": (_i, [_P, _P, _P, _T4, _i, _i, _i, _i, _i, _P]),
-    "ub_pool2x2_bwd": (_i, [_P, _T4, _i, _P, _P, _P, _i, _i, _i, _i, _P]),
+    "ub_pool2x2_bwd": (_i, [_P, _T4, _i, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "ub_head_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _P]),
-    "ub_head_bwd": (_i, [_P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_head_bwd": (_i, [_P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
     "ub_loss_workspace_bytes": (_ll, []),
     "ub_loss_fwd_bwd": (_i, [_i, _P, _P, _i, _P, _P, _P, _P, _i, _i, _i, _i, _f, _P]),
     "ub_weight_map_workspace_bytes": (_ll, [_i, _i, _i]),

@@ -240,10 +240,12 @@ def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
     return y, idx
 
 
-def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx):
+def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx, dbias=None):
+    """dbias (fp32 [C], zeroed by the caller): also receives the column sums of dx (bias gradient of the conv
+    that fed the pool)."""
     n, h, w, c = dx.shape
-    _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), n, h, w, c,
-                                     _stream()), "pool2x2_bwd")
+    _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), _ptr(dbias),
+                                     n, h, w, c, _stream()), "pool2x2_bwd")
     return dx
 
 
@@ -252,10 +254,11 @@ def head_fwd(x, w, bias, logits=None, argmax=None):
     _chk(_lib.load().ub_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(logits), _ptr(argmax), n, h, wd, _stream()), "head_fwd")
 
 
-def head_bwd(x, w, dlogits, dx, dw, db):
+def head_bwd(x, w, dlogits, dx, dw, db, dbias_x=None):
+    """dbias_x (fp32 [64], zeroed by the caller): also receives the column sums of dx (bias gradient of conv12e)."""
     n, h, wd, _ = x.shape
-    _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), n, h, wd, _stream()),
-          "head_bwd")
+    _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dbias_x), n, h, wd,
+                                  _stream()), "head_bwd")
 
 
 LOSS_BCE, LOSS_SOFTMAX_CE = 0, 1

@@ -897,9 +897,10 @@ int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4*
 }
 
 int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsigned char* idx, const void* pooled,
-                   void* dx, int n, int h, int w, int c, void* stream) {
+                   void* dx, float* dbias, int n, int h, int w, int c, void* stream) {
   if (!idx || !pooled || !dx) return UB_E_ARG;
   if ((c % 8) || n <= 0 || h < 2 || w < 2) return UB_E_SHAPE;
+  if (dbias && (c > 2048 || 256 % (c / 8))) return UB_E_SHAPE;   // a thread must keep its channel octet
   if (!aligned16(dx) || !aligned16(pooled) || (dy && !aligned16(dy))) return UB_E_ALIGN;
   const __nv_bfloat16* catp = nullptr;
   int ch = 0, cw = 0, cc = 0;
@@ -915,7 +916,7 @@ int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsi
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
   pool_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, catp, idx,
                                                                    (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n,
-                                                                   h, w, c, ch, cw, cc, c_off);
+                                                                   h, w, c, ch, cw, cc, c_off, dbias);
   return (int)cudaGetLastError();
 }
 
@@ -930,8 +931,8 @@ int ub_head_fwd(const void* x, const float* w, const float* bias, float* logits,
   return (int)cudaGetLastError();
 }
 
-int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db, int n, int h,
-                int w_, void* stream) {
+int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db, float* dbias_x,
+                int n, int h, int w_, void* stream) {
   if (!x || !w || !dlogits || !dx || !dw || !db) return UB_E_ARG;
   if (!aligned16(x) || !aligned16(dx)) return UB_E_ALIGN;
   const long long npix = (long long)h * w_;
@@ -940,7 +941,7 @@ int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, f
   if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
   if (blocks < 1) blocks = 1;
   head_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, dlogits,
-                                                                (__nv_bfloat16*)dx, dw, db, npix, n);
+                                                                (__nv_bfloat16*)dx, dw, db, dbias_x, npix, n);
   return (int)cudaGetLastError();
 }
 

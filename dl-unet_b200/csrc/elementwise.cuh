@@ -231,9 +231,16 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
                                                        const uint8_t* __restrict__ idx,
                                                        const __nv_bfloat16* __restrict__ pooled,
                                                        __nv_bfloat16* __restrict__ dx, int n_img, int H, int W, int C,
-                                                       int cat_H, int cat_W, int cat_C, int c_off) {
+                                                       int cat_H, int cat_W, int cat_C, int c_off,
+                                                       float* __restrict__ dbias) {
+  // dbias != nullptr: also accumulate the column sums of dx (= the bias gradient of the conv that fed the pool,
+  // network.py:132-151) -- every pooled element contributes its one scattered value.  256 % C8 == 0 (checked by
+  // the host), so a thread keeps its channel octet over the whole grid-stride loop and sums in registers.
   const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
   const long long total = (long long)n_img * Ho * Wo * C8;
+  float bsum[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bsum[c] = 0.0f;
   for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
        gid += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(gid % C8);
@@ -268,12 +275,26 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
       const float gv = pv[c] > 0.0f ? g[c] : 0.0f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k][c] = (code == (uint32_t)k) ? gv : 0.0f;
+      bsum[c] += __bfloat162float(__float2bfloat16_rn(gv));   // the value as stored (what the wgrad kernel reads)
     }
     __nv_bfloat16* xp = dx + (((long long)n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
     *reinterpret_cast<uint4*>(xp) = pack8(o[0]);
     *reinterpret_cast<uint4*>(xp + C) = pack8(o[1]);
     *reinterpret_cast<uint4*>(xp + (long long)W * C) = pack8(o[2]);
     *reinterpret_cast<uint4*>(xp + (long long)W * C + C) = pack8(o[3]);
+  }
+  if (dbias != nullptr) {
+    __shared__ float sred[256][9];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sred[threadIdx.x][c] = bsum[c];
+    __syncthreads();
+    const int slots = 256 / C8;   // threads tid, tid + C8, ... share the octet tid % C8
+    for (int i = threadIdx.x; i < C; i += 256) {
+      const int cc8 = i >> 3, c = i & 7;
+      float v = 0.0f;
+      for (int sl = 0; sl < slots; ++sl) v += sred[sl * C8 + cc8][c];
+      atomicAdd(dbias + i, v);
+    }
   }
 }
 
@@ -332,7 +353,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ w,
                                                        const float* __restrict__ dlogits,
                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
-                                                       float* __restrict__ db, long long n_pix_per_img, int n_img) {
+                                                       float* __restrict__ db, float* __restrict__ dbias_x,
+                                                       long long n_pix_per_img, int n_img) {
+  // dbias_x != nullptr: also the column sums of dX = the bias gradient of conv12e (network.py:188)
   const int oct = threadIdx.x & 7;
   float w0[8], w1[8];
 #pragma unroll
@@ -340,9 +363,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
     w0[c] = __ldg(w + oct * 8 + c);
     w1[c] = __ldg(w + 64 + oct * 8 + c);
   }
-  float a0[8], a1[8], sb0 = 0.0f, sb1 = 0.0f;
+  float a0[8], a1[8], bs[8], sb0 = 0.0f, sb1 = 0.0f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a0[c] = a1[c] = 0.0f;
+  for (int c = 0; c < 8; ++c) a0[c] = a1[c] = bs[c] = 0.0f;
   const unsigned int total = (unsigned int)(n_pix_per_img * n_img * 8);
   const unsigned int npp = (unsigned int)n_pix_per_img;
   for (unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
@@ -355,6 +378,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       o[c] = v[c] > 0.0f ? fmaf(d0, w0[c], d1 * w1[c]) : 0.0f;
+      bs[c] += __bfloat162float(__float2bfloat16_rn(o[c]));
       a0[c] = fmaf(d0, v[c], a0[c]);
       a1[c] = fmaf(d1, v[c], a1[c]);
     }
@@ -371,16 +395,19 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
     a0[c] += __shfl_xor_sync(0xffffffffu, a0[c], 16);
     a1[c] += __shfl_xor_sync(0xffffffffu, a1[c], 8);
     a1[c] += __shfl_xor_sync(0xffffffffu, a1[c], 16);
+    bs[c] += __shfl_xor_sync(0xffffffffu, bs[c], 8);
+    bs[c] += __shfl_xor_sync(0xffffffffu, bs[c], 16);
   }
   sb0 = warp_sum(sb0);
   sb1 = warp_sum(sb1);
-  __shared__ float sred[8][130];
+  __shared__ float sred[8][194];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane < 8) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       sred[warp][lane * 8 + c] = a0[c];
       sred[warp][64 + lane * 8 + c] = a1[c];
+      sred[warp][130 + lane * 8 + c] = bs[c];
     }
   }
   if (lane == 0) {
@@ -388,13 +415,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
     sred[warp][129] = sb1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 130; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (dbias_x != nullptr ? 194 : 130); i += blockDim.x) {
     float v = 0.0f;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sred[wv][i];
     if (i < 128)
       atomicAdd(dw + i, v);
-    else
+    else if (i < 130)
       atomicAdd(db + (i - 128), v);
+    else
+      atomicAdd(dbias_x + (i - 130), v);
   }
 }
 

@@ -105,15 +105,18 @@ int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* dw, float* db
  * is crop_and_concat's offset (negative = zero padding, the border is never written).                */
 int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4* cat, int c_off, int n, int h, int w,
                    int c, void* stream);
-/* dx[n,h,w,c] = scatter((dy + window(dcat)) * (pooled > 0)) by idx; dy / dcat may be NULL */
+/* dx[n,h,w,c] = scatter((dy + window(dcat)) * (pooled > 0)) by idx; dy / dcat may be NULL.
+ * dbias (fp32 [c], may be NULL, caller zeroes): += column sums of dx = the bias gradient of the conv that fed the
+ * pool (saves the separate ub_colsum pass over dx); needs 256 % (c/8) == 0. */
 int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsigned char* idx, const void* pooled,
-                   void* dx, int n, int h, int w, int c, void* stream);
+                   void* dx, float* dbias, int n, int h, int w, int c, void* stream);
 
 /* ---- 1x1 head, 64 -> 2 (network.py:190) and argmax (tester.py:30; trainer.py:82) ---- */
 int ub_head_fwd(const void* x_bf16, const float* w, const float* bias, float* logits_nchw, unsigned char* argmax,
                 int n, int h, int w_, void* stream);
+/* dbias_x (fp32 [64], may be NULL, caller zeroes): += column sums of dx = the bias gradient of conv12e */
 int ub_head_bwd(const void* x_bf16, const float* w, const float* dlogits_nchw, void* dx_bf16, float* dw, float* db,
-                int n, int h, int w_, void* stream);
+                float* dbias_x, int n, int h, int w_, void* stream);
 
 /* ---- pixel-wise weighted loss, forward + dlogits fused (trainer.py:60-75) ----
  * kind 0: BCE-with-logits vs the one-hot target, mean over B*2*L*L (nn.BCEWithLogitsLoss(weight));

@@ -194,7 +194,9 @@ def test_pool_indices_and_skip_write_bit_exact(ops, case):
     dyp = bf(torch.randn(n, hp, hp, c, device=DEV))
     dcat = bf(torch.randn(n, hu, hu, 2 * c, device=DEV))
     dx = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=DEV)
-    ops.pool2x2_bwd(dyp, dcat[..., :c], coff, idx, y, dx)
+    dbias = torch.zeros(c, device=DEV)
+    ops.pool2x2_bwd(dyp, dcat[..., :c], coff, idx, y, dx, dbias)
+    assert rel_l2(dbias, dx.float().sum((0, 1, 2))) < FP32_TOL      # fused bias gradient = column sums of dx
     xr = nchw(x).requires_grad_(True)
     g = bf(nchw(dyp) + F.pad(nchw(dcat[..., :c]), (coff,) * 4)).float()
     F.max_pool2d(F.relu(xr), 2, 2).backward(g)
@@ -230,7 +232,9 @@ def test_head_fwd_bwd(ops):
     gx, gw, gb = torch.autograd.grad(ref, (xr, wf, bfin), dl)
     dx = torch.empty_like(x)
     dw, db = torch.zeros(2, 64, device=DEV), torch.zeros(2, device=DEV)
-    ops.head_bwd(x, wf.detach(), dl, dx, dw, db)
+    dbx = torch.zeros(64, device=DEV)
+    ops.head_bwd(x, wf.detach(), dl, dx, dw, db, dbx)
+    assert rel_l2(dbx, dx.float().sum((0, 1, 2))) < FP32_TOL        # fused bias gradient of conv12e
     assert rel_l2(nchw(dx), gx) < BF16_OUT_TOL
     assert rel_l2(dw.view(2, 64, 1, 1), gw) < 1e-3 and rel_l2(db, gb) < FP32_TOL
 
