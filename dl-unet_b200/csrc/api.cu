@@ -855,8 +855,8 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(y)) return UB_E_ALIGN;
   if (n > 65535 || h - 2 > 65535) return UB_E_SHAPE;
-  const int rpb = 96;  // amortises the 80 weight/bias register loads of every thread
-  const dim3 grid(((w_ - 2) * 8 + 255) / 256, (h - 2 + rpb - 1) / rpb, n);
+  const int rpb = 96;  // amortises the 40 weight/bias register loads of every thread
+  const dim3 grid(((w_ - 2) * 16 + 255) / 256, (h - 2 + rpb - 1) / rpb, n);
   conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_, rpb);
   return (int)cudaGetLastError();
 }

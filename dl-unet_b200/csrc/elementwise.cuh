@@ -30,25 +30,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------
 // conv11c: 1 -> 64 channels, 3x3 valid, fp32 image in, bf16 NHWC out, fused
 // bias + ReLU (network.py:131).  K = 9 cannot feed the tensor pipe; the kernel
-// is bound by its 2 B x 64 x pixels output write.
-// grid.x covers pixels*8 threads; thread = (pixel, channel octet).
+// is bound by its 2 B x 64 x pixels output write and by 9 fp32 FMAs per output.
+// Thread = (pixel column, channel QUAD): 36 weights + 4 biases in registers (an octet per thread needs 80 and caps
+// the SM at 8 warps, which left the FMA pipe idle two thirds of the time), 8-byte stores, a warp writes the 256
+// contiguous bytes of two pixels.
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                         int n_img, int H, int W, int rows_per_block) {
-  // grid = (ceil(Wo*8/256), ceil(Ho/rows_per_block), n): no index divisions; a thread keeps its channel
-  // octet and its x position and walks down rows_per_block rows, so its 8 x 9 weights and 8 biases are
-  // loaded once into registers and the three input rows slide (6 of 9 taps are reused per step).
+  // grid = (ceil(Wo*16/256), ceil(Ho/rows_per_block), n): no index divisions; a thread keeps its channel quad and
+  // its x position and walks down rows_per_block rows; the three input rows slide (6 of 9 taps reused per step).
   const int Ho = H - 2, Wo = W - 2;
   const int gx = blockIdx.x * 256 + threadIdx.x;
-  const int ox = gx >> 3, oct = gx & 7;
+  const int ox = gx >> 4, q = gx & 15;
   const int n = blockIdx.z;
   if (ox >= Wo) return;
-  float wr[8][9], br[8];
+  float wr[4][9], br[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    br[c] = __ldg(b + oct * 8 + c);
+  for (int c = 0; c < 4; ++c) {
+    br[c] = __ldg(b + q * 4 + c);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (oct * 8 + c) * 9 + t);
+    for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (q * 4 + c) * 9 + t);
   }
   const int y_begin = blockIdx.y * rows_per_block;
   const int y_end = min(Ho, y_begin + rows_per_block);
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     in[6 + s] = __ldg(xp + W + s);
     nxt[s] = __ldg(xp + 2 * W + s);
   }
+  __nv_bfloat16* yp = y + (((long long)n * Ho + y_begin) * Wo + ox) * 64 + q * 4;
   for (int oy = y_begin; oy < y_end; ++oy) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
@@ -68,92 +70,80 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       in[6 + s] = nxt[s];
     }
     xp += W;
-    if (oy + 1 < y_end) {  // input row of the NEXT output row: in flight while this row's 72 FMAs run
+    if (oy + 1 < y_end) {  // input row of the NEXT output row: in flight while this row's FMAs run
 #pragma unroll
       for (int s = 0; s < 3; ++s) nxt[s] = __ldg(xp + 2 * W + s);
     }
-    float o[8];
+    float o[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       float a = br[c];
 #pragma unroll
       for (int t = 0; t < 9; ++t) a = fmaf(in[t], wr[c][t], a);
       o[c] = fmaxf(a, 0.0f);
     }
-    *reinterpret_cast<uint4*>(y + (((long long)n * Ho + oy) * Wo + ox) * 64 + oct * 8) = pack8(o);
+    uint2 pk;
+    pk.x = pack_bf16x2(o[0], o[1]);
+    pk.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(yp) = pk;
+    yp += (long long)Wo * 64;
   }
 }
 
 // conv11c weight + bias gradient: dW[co, tap] = sum_p dY[p, co] * x[p + tap], db[co] = sum_p dY[p, co].
-// dY is bf16 NHWC (already ReLU-masked).  One thread = (pixel, channel octet); block-level
-// reduction in shared memory, then one atomicAdd per (co, tap) per block.
-__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x,
+// dY is bf16 NHWC (already ReLU-masked).  Thread = (pixel slot, channel octet, tap half): half 0 accumulates taps
+// 0..4, half 1 taps 5..8 and the bias (x = 1): 40 accumulators per thread instead of 80, so twice the warps fit.
+// Block-level reduction in shared memory, then one atomicAdd per (co, tap) per block.
+__global__ void __launch_bounds__(256, 3) conv1_wgrad_kernel(const float* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ dy,
                                                           float* __restrict__ dw, float* __restrict__ db, int n_img,
                                                           int H, int W, int rows_per_block) {
-  // grid = (ceil(Ho / rows_per_block), n): a block sweeps its rows with 32 pixels x 8 channel octets per
-  // pass -- no index divisions; every thread keeps its octet.
+  // grid = (ceil(Ho / rows_per_block), n): a block sweeps its rows with 16 pixels x 8 octets x 2 halves per pass
   const int Ho = H - 2, Wo = W - 2;
   const int n = blockIdx.y;
-  const int oct = threadIdx.x & 7, px = threadIdx.x >> 3;
-  float acc[8][10];
+  const int oct = threadIdx.x & 7, half = (threadIdx.x >> 3) & 1, px = threadIdx.x >> 4;
+  int off[5];   // image offsets of this half's taps; the 5th of half 1 is the bias pseudo-tap
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int t = min(half * 5 + j, 8);
+    off[j] = (t / 3) * W + (t % 3);
+  }
+  float acc[8][5];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
-    for (int t = 0; t < 10; ++t) acc[c][t] = 0.0f;
+    for (int j = 0; j < 5; ++j) acc[c][j] = 0.0f;
   const int y_begin = blockIdx.x * rows_per_block;
   const int y_end = min(Ho, y_begin + rows_per_block);
   for (int oy = y_begin; oy < y_end; ++oy) {
     const float* xrow = x + ((long long)n * H + oy) * W;
     const __nv_bfloat16* grow = dy + (((long long)n * Ho + oy) * Wo) * 64 + oct * 8;
-    // software pipeline: the loads of pixel ox+32 are in flight while the 80 FMAs of pixel ox run
-    uint4 g4n = make_uint4(0u, 0u, 0u, 0u);
-    float inn[9];
-    if (px < Wo) {
-      g4n = __ldg(reinterpret_cast<const uint4*>(grow + (long long)px * 64));
+    // no register prefetch: 12 warps per SM-quarter hide the load latency, and the 9 registers keep that occupancy
+#pragma unroll 1
+    for (int ox = px; ox < Wo; ox += 16) {
+      float g[8], in[5];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(grow + (long long)ox * 64)), g);
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int j = 0; j < 5; ++j) in[j] = __ldg(xrow + ox + off[j]);
+      if (half) in[4] = 1.0f;
 #pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) inn[r * 3 + s2] = __ldg(xrow + r * W + px + s2);
-    }
-    for (int ox = px; ox < Wo; ox += 32) {
-      float g[8], in[9];
-      unpack8(g4n, g);
+      for (int c = 0; c < 8; ++c)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) in[t] = inn[t];
-      const int oxn = ox + 32;
-      if (oxn < Wo) {
-        g4n = __ldg(reinterpret_cast<const uint4*>(grow + (long long)oxn * 64));
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int s2 = 0; s2 < 3; ++s2) inn[r * 3 + s2] = __ldg(xrow + r * W + oxn + s2);
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], in[t], acc[c][t]);
-        acc[c][9] += g[c];
-      }
+        for (int j = 0; j < 5; ++j) acc[c][j] = fmaf(g[c], in[j], acc[c][j]);
     }
   }
-  // lanes with equal (lane & 7) share the octet: reduce over xor 8, 16; then across warps through smem
+  // lanes with equal (lane & 15) share (octet, half): reduce over xor 16; then across warps through smem
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
-    for (int t = 0; t < 10; ++t) {
-      float v = acc[c][t];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      acc[c][t] = v;
-    }
+    for (int j = 0; j < 5; ++j) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float sred[8][64][10];  // [warp][channel][tap]
-  if (lane < 8) {
+  __shared__ float sred[8][64][10];  // [warp][channel][tap, 9 = bias]
+  if (lane < 16) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
-      for (int t = 0; t < 10; ++t) sred[warp][lane * 8 + c][t] = acc[c][t];
+      for (int j = 0; j < 5; ++j) sred[warp][oct * 8 + c][half * 5 + j] = acc[c][j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 10; i += blockDim.x) {
