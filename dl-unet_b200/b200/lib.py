@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libunet_b200.so")
+LIB_PATH = os.environ.get("UB_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "csrc", "libunet_b200.so")
 
 
 class Tensor4(C.Structure):

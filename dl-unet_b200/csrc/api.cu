@@ -855,9 +855,8 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(y)) return UB_E_ALIGN;
   if (n > 65535 || h - 2 > 65535) return UB_E_SHAPE;
-  const int rpb = 96;  // amortises the 40 weight/bias register loads of every thread
-  const dim3 grid(((w_ - 2) * 16 + 255) / 256, (h - 2 + rpb - 1) / rpb, n);
-  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_, rpb);
+  const dim3 grid((w_ - 2 + 15) / 16, (h - 2 + C1_ROWS - 1) / C1_ROWS, n);
+  conv1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, w, bias, (__nv_bfloat16*)y, n, h, w_);
   return (int)cudaGetLastError();
 }
 
@@ -866,8 +865,8 @@ int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
   if (n > 65535) return UB_E_SHAPE;
-  // ~8 blocks per SM
-  int rpb = (int)(((long long)(h - 2) * n + 8ll * num_sms() - 1) / (8ll * num_sms()));
+  // ~10 blocks per SM (5 resident, two waves)
+  int rpb = (int)(((long long)(h - 2) * n + 10ll * num_sms() - 1) / (10ll * num_sms()));
   if (rpb < 1) rpb = 1;
   const dim3 grid((h - 2 + rpb - 1) / rpb, n);
   conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, dw, db, n, h, w_, rpb);
@@ -914,9 +913,12 @@ int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsi
     cc = (int)dcat->sx;
   }
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  pool_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, catp, idx,
-                                                                   (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n,
-                                                                   h, w, c, ch, cw, cc, c_off, dbias);
+  if (dbias)
+    pool_bwd_kernel<true><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, catp, idx, (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n, h, w, c, ch, cw, cc, c_off, dbias);
+  else
+    pool_bwd_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, catp, idx, (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n, h, w, c, ch, cw, cc, c_off, nullptr);
   return (int)cudaGetLastError();
 }
 

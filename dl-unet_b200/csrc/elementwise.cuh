@@ -28,22 +28,50 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------
+// Ampere-style asynchronous copies (global -> shared without a register round trip): the staging mechanism of the
+// two conv11c kernels, whose operands are too narrow / misaligned for TMA boxes (a 4-byte-aligned fp32 image).
+__device__ __forceinline__ void cp_async_4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // conv11c: 1 -> 64 channels, 3x3 valid, fp32 image in, bf16 NHWC out, fused
 // bias + ReLU (network.py:131).  K = 9 cannot feed the tensor pipe; the kernel
 // is bound by its 2 B x 64 x pixels output write and by 9 fp32 FMAs per output.
-// Thread = (pixel column, channel QUAD): 36 weights + 4 biases in registers (an octet per thread needs 80 and caps
-// the SM at 8 warps, which left the FMA pipe idle two thirds of the time), 8-byte stores, a warp writes the 256
-// contiguous bytes of two pixels.
+// Thread = (pixel column, channel QUAD): 36 weights + 4 biases in registers, 8-byte stores, a warp writes the 256
+// contiguous bytes of two pixels.  The block's image window ((rows + 2) x 18 floats) is staged in shared memory
+// once: with global loads in the row loop the kernel sat in long-scoreboard stalls (ncu: 9.4 of 13.9 cycles per
+// issued instruction) however many warps were resident.
+constexpr int C1_ROWS = 96;   // output rows per block
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
-                                                        int n_img, int H, int W, int rows_per_block) {
-  // grid = (ceil(Wo*16/256), ceil(Ho/rows_per_block), n): no index divisions; a thread keeps its channel quad and
-  // its x position and walks down rows_per_block rows; the three input rows slide (6 of 9 taps reused per step).
+                                                        int n_img, int H, int W) {
+  // grid = (ceil(Wo/16), ceil(Ho/C1_ROWS), n): no index divisions; a thread keeps its channel quad and its x
+  // position and walks down the rows; the three input rows slide (6 of 9 taps reused per step).
+  __shared__ float sx[(C1_ROWS + 2) * 18];
   const int Ho = H - 2, Wo = W - 2;
-  const int gx = blockIdx.x * 256 + threadIdx.x;
-  const int ox = gx >> 4, q = gx & 15;
+  const int x0 = blockIdx.x * 16;
+  const int px = threadIdx.x >> 4, q = threadIdx.x & 15;
+  const int ox = x0 + px;
   const int n = blockIdx.z;
-  if (ox >= Wo) return;
+  const int y_begin = blockIdx.y * C1_ROWS;
+  const int y_end = min(Ho, y_begin + C1_ROWS);
+  const int rows_in = y_end - y_begin + 2;
+  const float* xb = x + ((long long)n * H + y_begin) * W + x0;
+  const int cols_in = min(18, W - x0);
+  for (int i = threadIdx.x; i < rows_in * 18; i += 256) {
+    const int r = i / 18, c = i - r * 18;
+    if (c < cols_in) cp_async_4(&sx[i], xb + (long long)r * W + c);
+  }
+  cp_async_commit();
   float wr[4][9], br[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -51,28 +79,23 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (q * 4 + c) * 9 + t);
   }
-  const int y_begin = blockIdx.y * rows_per_block;
-  const int y_end = min(Ho, y_begin + rows_per_block);
-  const float* xp = x + ((long long)n * H + y_begin) * W + ox;
-  float in[9], nxt[3];
+  cp_async_wait<0>();
+  __syncthreads();
+  if (ox >= Wo) return;
+  const float* sp = sx + px;
+  float in[9];
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
-    in[3 + s] = __ldg(xp + s);
-    in[6 + s] = __ldg(xp + W + s);
-    nxt[s] = __ldg(xp + 2 * W + s);
+    in[3 + s] = sp[s];
+    in[6 + s] = sp[18 + s];
   }
   __nv_bfloat16* yp = y + (((long long)n * Ho + y_begin) * Wo + ox) * 64 + q * 4;
-  for (int oy = y_begin; oy < y_end; ++oy) {
+  for (int r = 0; r < y_end - y_begin; ++r) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       in[s] = in[3 + s];
       in[3 + s] = in[6 + s];
-      in[6 + s] = nxt[s];
-    }
-    xp += W;
-    if (oy + 1 < y_end) {  // input row of the NEXT output row: in flight while this row's FMAs run
-#pragma unroll
-      for (int s = 0; s < 3; ++s) nxt[s] = __ldg(xp + 2 * W + s);
+      in[6 + s] = sp[(r + 2) * 18 + s];
     }
     float o[4];
 #pragma unroll
@@ -91,65 +114,94 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 }
 
 // conv11c weight + bias gradient: dW[co, tap] = sum_p dY[p, co] * x[p + tap], db[co] = sum_p dY[p, co].
-// dY is bf16 NHWC (already ReLU-masked).  Thread = (pixel slot, channel octet, tap half): half 0 accumulates taps
-// 0..4, half 1 taps 5..8 and the bias (x = 1): 40 accumulators per thread instead of 80, so twice the warps fit.
-// Block-level reduction in shared memory, then one atomicAdd per (co, tap) per block.
-__global__ void __launch_bounds__(256, 3) conv1_wgrad_kernel(const float* __restrict__ x,
+// dY is bf16 NHWC (already ReLU-masked), 8 KB per 64-pixel tile, streamed through a 3-stage cp.async ring together
+// with the tile's 3 x 66 image window, so ~16 KB per block (5 blocks per SM) are in flight whatever the compute
+// does.  Thread = (pixel slot, channel octet, tap half): half 0 accumulates taps 0..4, half 1 taps 5..8 and the
+// bias (x = 1): 40 accumulators.  Block-level reduction in shared memory, one atomicAdd per (co, tap) per block.
+constexpr int C1W_TILE = 64, C1W_STAGES = 3;
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ dy,
                                                           float* __restrict__ dw, float* __restrict__ db, int n_img,
                                                           int H, int W, int rows_per_block) {
-  // grid = (ceil(Ho / rows_per_block), n): a block sweeps its rows with 16 pixels x 8 octets x 2 halves per pass
+  __shared__ __align__(16) uint8_t sdy[C1W_STAGES][C1W_TILE * 128];
+  __shared__ float sxw[C1W_STAGES][3][C1W_TILE + 2];
+  __shared__ float sred[8][16][41];   // [warp][(half, octet)][channel-in-octet x 5 taps], padded
   const int Ho = H - 2, Wo = W - 2;
   const int n = blockIdx.y;
   const int oct = threadIdx.x & 7, half = (threadIdx.x >> 3) & 1, px = threadIdx.x >> 4;
-  int off[5];   // image offsets of this half's taps; the 5th of half 1 is the bias pseudo-tap
+  const int y_begin = blockIdx.x * rows_per_block;
+  const int y_end = min(Ho, y_begin + rows_per_block);
+  const int xtiles = (Wo + C1W_TILE - 1) / C1W_TILE;
+  const int n_tiles = (y_end - y_begin) * xtiles;
+  int soff[5];   // offsets of this half's taps inside the staged window; the 5th of half 1 is the bias pseudo-tap
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     const int t = min(half * 5 + j, 8);
-    off[j] = (t / 3) * W + (t % 3);
+    soff[j] = (t / 3) * (C1W_TILE + 2) + (t % 3);
   }
   float acc[8][5];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int j = 0; j < 5; ++j) acc[c][j] = 0.0f;
-  const int y_begin = blockIdx.x * rows_per_block;
-  const int y_end = min(Ho, y_begin + rows_per_block);
-  for (int oy = y_begin; oy < y_end; ++oy) {
-    const float* xrow = x + ((long long)n * H + oy) * W;
-    const __nv_bfloat16* grow = dy + (((long long)n * Ho + oy) * Wo) * 64 + oct * 8;
-    // no register prefetch: 12 warps per SM-quarter hide the load latency, and the 9 registers keep that occupancy
-#pragma unroll 1
-    for (int ox = px; ox < Wo; ox += 16) {
-      float g[8], in[5];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(grow + (long long)ox * 64)), g);
+
+  auto issue = [&](int t) {
+    if (t < n_tiles) {
+      const int st = t % C1W_STAGES;
+      const int oy = y_begin + t / xtiles, x0 = (t % xtiles) * C1W_TILE;
+      const int npx = min(C1W_TILE, Wo - x0);
+      const __nv_bfloat16* g = dy + (((long long)n * Ho + oy) * Wo + x0) * 64;
+      for (int i = threadIdx.x; i < npx * 8; i += 256) cp_async_16(&sdy[st][i * 16], g + i * 8);
+      const float* xr = x + ((long long)n * H + oy) * W + x0;
+      for (int i = threadIdx.x; i < 3 * (C1W_TILE + 2); i += 256) {
+        const int r = i / (C1W_TILE + 2), c = i - r * (C1W_TILE + 2);
+        if (c < npx + 2) cp_async_4(&sxw[st][r][c], xr + (long long)r * W + c);
+      }
+    }
+    cp_async_commit();   // an (empty) group per call keeps the wait_group arithmetic uniform
+  };
+  for (int t = 0; t < C1W_STAGES - 1; ++t) issue(t);
+  for (int t = 0; t < n_tiles; ++t) {
+    cp_async_wait<C1W_STAGES - 2>();
+    __syncthreads();                 // tile t has landed for everyone; everyone is done with tile t-1's stage
+    issue(t + C1W_STAGES - 1);
+    const int st = t % C1W_STAGES;
+    const int npx = min(C1W_TILE, Wo - (t % xtiles) * C1W_TILE);
+    const float* sw = &sxw[st][0][0];
 #pragma unroll
-      for (int j = 0; j < 5; ++j) in[j] = __ldg(xrow + ox + off[j]);
-      if (half) in[4] = 1.0f;
+    for (int i = 0; i < C1W_TILE / 16; ++i) {
+      const int p = px + 16 * i;
+      if (p < npx) {
+        float g[8], in[5];
+        unpack8(*reinterpret_cast<const uint4*>(&sdy[st][p * 128 + oct * 16]), g);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+        for (int j = 0; j < 5; ++j) in[j] = sw[p + soff[j]];
+        if (half) in[4] = 1.0f;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) acc[c][j] = fmaf(g[c], in[j], acc[c][j]);
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) acc[c][j] = fmaf(g[c], in[j], acc[c][j]);
+      }
     }
   }
+  cp_async_wait<0>();
   // lanes with equal (lane & 15) share (octet, half): reduce over xor 16; then across warps through smem
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int j = 0; j < 5; ++j) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float sred[8][64][10];  // [warp][channel][tap, 9 = bias]
   if (lane < 16) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
-      for (int j = 0; j < 5; ++j) sred[warp][oct * 8 + c][half * 5 + j] = acc[c][j];
+      for (int j = 0; j < 5; ++j) sred[warp][half * 8 + oct][c * 5 + j] = acc[c][j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 10; i += blockDim.x) {
     const int ch = i / 10, t = i % 10;
     float v = 0.0f;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sred[wv][ch][t];
+    for (int wv = 0; wv < 8; ++wv) v += sred[wv][(t / 5) * 8 + (ch >> 3)][(ch & 7) * 5 + (t % 5)];
     if (t < 9)
       atomicAdd(dw + ch * 9 + t, v);
     else
@@ -216,6 +268,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const __nv_bfloat16* __re
 // tensor -- the next encoder conv's dgrad (dense) and the skip half of the concat
 // gradient (window of dcat at the crop_and_concat offset) -- and (b) the ReLU backward of
 // the conv that fed the pool (gradient passes only where the pooled value > 0).
+template <bool BIAS>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ dcat,
                                                        const uint8_t* __restrict__ idx,
@@ -223,7 +276,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
                                                        __nv_bfloat16* __restrict__ dx, int n_img, int H, int W, int C,
                                                        int cat_H, int cat_W, int cat_C, int c_off,
                                                        float* __restrict__ dbias) {
-  // dbias != nullptr: also accumulate the column sums of dx (= the bias gradient of the conv that fed the pool,
+  // BIAS: also accumulate the column sums of dx (= the bias gradient of the conv that fed the pool,
   // network.py:132-151) -- every pooled element contributes its one scattered value.  256 % C8 == 0 (checked by
   // the host), so a thread keeps its channel octet over the whole grid-stride loop and sums in registers.
   const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
@@ -265,7 +318,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
       const float gv = pv[c] > 0.0f ? g[c] : 0.0f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k][c] = (code == (uint32_t)k) ? gv : 0.0f;
-      bsum[c] += __bfloat162float(__float2bfloat16_rn(gv));   // the value as stored (what the wgrad kernel reads)
+      if (BIAS) bsum[c] += gv;
     }
     __nv_bfloat16* xp = dx + (((long long)n * H + 2 * oy) * W + 2 * ox) * C + c8 * 8;
     *reinterpret_cast<uint4*>(xp) = pack8(o[0]);
@@ -273,7 +326,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
     *reinterpret_cast<uint4*>(xp + (long long)W * C) = pack8(o[2]);
     *reinterpret_cast<uint4*>(xp + (long long)W * C + C) = pack8(o[3]);
   }
-  if (dbias != nullptr) {
+  if (BIAS) {
     __shared__ float sred[256][9];
 #pragma unroll
     for (int c = 0; c < 8; ++c) sred[threadIdx.x][c] = bsum[c];
