@@ -10,17 +10,20 @@ namespace ub {
 // weight rows in smem ([2][64] floats, row pitch 64); the partial dot products of the fp32, post-ReLU, NOT yet
 // bf16-rounded activations are returned in *head_part.  `stage` = false skips the bf16 staging write (inference:
 // the activation itself is never stored).
-__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on,
-                                          const __nv_bfloat16* mcols, uint8_t* ebuf, int row, int h,
+// The ReLU-backward mask row (64 B: this thread's pixel, its 32 columns of the source activation).
+__device__ __forceinline__ void load_mask(const __nv_bfloat16* mcols, uint4 (&m4)[4]) {
+  const uint4* mp = reinterpret_cast<const uint4*>(mcols);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
+}
+
+// mask_on: apply the ReLU-backward mask; mask_valid = false zeroes the row (pixel outside the image), else m4 holds
+// the mask row, loaded by the caller (igemm2 requests it one chunk ahead so that its L2 latency is off the
+// tfull -> TMA-store critical path).
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
+                                          const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                           const float* shead = nullptr, float2* head_part = nullptr,
                                           bool stage = true) {
-  // the mask row (64 B of this thread's pixel) is requested first: its latency overlaps the TMEM load
-  uint4 m4[4];
-  if (mask_on && mcols != nullptr) {
-    const uint4* mp = reinterpret_cast<const uint4*>(mcols);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
-  }
   uint32_t v[32];
   tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
@@ -62,7 +65,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, in
     o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
     if (mask_on) {
       // ReLU backward on packed bf16 pairs: a bf16 is > 0 exactly when its bits, read as int16, are > 0
-      if (mcols != nullptr) {
+      if (mask_valid) {
         o.x &= __vcmpgts2(m4[c].x, 0u);
         o.y &= __vcmpgts2(m4[c].y, 0u);
         o.z &= __vcmpgts2(m4[c].z, 0u);

@@ -230,8 +230,11 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
         // Two staging buffers, ONE barrier per chunk: before the barrier thread 0 waits until every earlier
         // TMA store has finished reading smem, so after it the other buffer is free for the next chunk.
         uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+        uint4 m4[4];
+        // the mask row is requested first: its latency overlaps the TMEM load
+        if (mrow != nullptr) load_mask(mrow + j * 64, m4);
         epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
-                  mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, hw);
+                  mrow != nullptr, m4, ebuf, row, hw);
         fence_proxy_async_smem();
         if (et == 0) tma_store_wait_read<0>();
         named_bar_sync(1, 256);

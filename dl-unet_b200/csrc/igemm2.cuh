@@ -259,6 +259,27 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
       named_bar_sync(1, 256);
     }
+    // ReLU-backward mask rows are requested ONE CHUNK AHEAD (the next sub-tile / column chunk, or the first chunk of
+    // this CTA's next tile): an L2 hit costs ~1000 cycles under load, about the whole tensor time of a K = 64 tile.
+    auto mask_row = [&](int tt, int sub, int j) -> const __nv_bfloat16* {
+      const int nt = tt % p.n_tiles_n;
+      int mt = tt / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int xx = (tx * MT + sub) * 8 + bx, yy = ty * 16 + by;
+      if (xx >= p.out_W || yy >= p.out_H) return nullptr;
+      return p.mask + (long long)img * p.mask_sn + (long long)yy * p.mask_sy + (long long)xx * p.mask_sx + nt * BN + j * 64 +
+             h * 32;
+    };
+    uint4 mcur[4];
+    bool mcur_valid = false;
+    if (mask_on && (int)blockIdx.x < total_tiles) {
+      const __nv_bfloat16* mp = mask_row(blockIdx.x, 0, 0);
+      mcur_valid = mp != nullptr;
+      if (mcur_valid) load_mask(mp, mcur);
+    }
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -282,18 +303,35 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         const int x0 = (tx * MT + sub) * 8;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + sub) * BN;
         const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
-        const __nv_bfloat16* mrow = nullptr;
-        if (mask_on && px_valid)
-          mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx +
-                 n0 + h * 32;
 #pragma unroll 1
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
           // two staging buffers, one barrier per chunk (see igemm.cuh)
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+          uint4 mnext[4];
+          bool mnext_valid = false;
+          if (mask_on) {
+            int nt_t = t, nsub = sub, nj = j + 1;
+            if (nj == BN / 64) {
+              nj = 0;
+              if (++nsub == MT) {
+                nsub = 0;
+                nt_t = t + gridDim.x;
+              }
+            }
+            if (nt_t < total_tiles) {
+              const __nv_bfloat16* mp = mask_row(nt_t, nsub, nj);
+              mnext_valid = mp != nullptr;
+              if (mnext_valid) load_mask(mp, mnext);
+            }
+          }
           float2 hp = make_float2(0.0f, 0.0f);
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    mrow != nullptr ? mrow + j * 64 : nullptr, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp,
-                    store_out);
+                    mcur_valid, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out);
+          if (mask_on) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mcur[i] = mnext[i];
+            mcur_valid = mnext_valid;
+          }
           if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
           if (et == 0 && store_out) tma_store_wait_read<0>();
