@@ -119,11 +119,13 @@ class TrainStep:
         self.global_batch = global_batch
         self.graphs = {}
         self._loss_ws = None
+        self.logits = None       # the step's uncropped logits [B,2,Hp,Wp] (a static buffer when replaying a graph)
 
     def _eager(self, images, labels, weight, out_loss, dlogits_cache):
         eng = self.unet.engine
         st = eng.store
         logits, ws = eng.forward(images, train=True)
+        self.logits = logits
         b, _, hp, wp = logits.shape
         l = labels.shape[-1]
         nb = self.global_batch or b
@@ -164,6 +166,7 @@ class TrainStep:
         g["lab"].copy_(labels, non_blocking=True)
         g["w"].copy_(weight, non_blocking=True)
         g["graph"].replay()
+        self.logits = g["logits"]
         return g["loss"][0]
 
     def _capture(self, images, labels, weight):
@@ -187,4 +190,7 @@ class TrainStep:
         with torch.cuda.graph(graph):
             self._eager(img, lab, w, loss, dl)
         # the capture itself executed nothing; parameters are still p0
-        return {"graph": graph, "img": img, "lab": lab, "w": w, "loss": loss}
+        # everything the captured kernels address by raw pointer must outlive the graph: the dlogits buffer in `dl`
+        # was allocated by the warm-up (ordinary pool) -- dropping it here would let torch.cuda.empty_cache()
+        # (trainer.py calls it every epoch) unmap memory the replays still write to
+        return {"graph": graph, "img": img, "lab": lab, "w": w, "loss": loss, "logits": self.logits, "dlogits": dl}

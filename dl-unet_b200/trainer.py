@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.optim as optim
 
-from b200.train import FusedSGD, weighted_bce_with_logits
+from b200.train import FusedSGD, TrainStep, weighted_bce_with_logits
 from functions import class_balance, evaluation_metrics, weighted_map
 
 # The reference selects its stop criterion and weight-map generator with `DATASET is '<literal>'`
@@ -68,6 +68,8 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
     prog_dir, model_dir = os.path.join(fold_dir, 'progress'), os.path.join(fold_dir, 'models')
     os.makedirs(prog_dir, exist_ok=True)
     os.makedirs(model_dir, exist_ok=True)
+    # the whole hot-loop body (trainer.py:54-78) as one replayed CUDA graph per batch shape / learning rate
+    train_step = TrainStep(unet, optimizer, kind="bce", graph=True)
     loss_best_epoch = 100000.0
     history = {k: [] for k in ('train_eval_iou', 'train_eval_pe', 'val_eval_iou', 'val_eval_pe', 'loss', 'loss_val')}
     epoch = 0
@@ -84,16 +86,13 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
 
         # ---- hot loop (trainer.py:52-89)
         for images, labels in train_loader:
-            optimizer.zero_grad()
-            logits = unet(images.to(device, non_blocking=True))
+            images = images.to(device, non_blocking=True)
             labels = labels.to(device, non_blocking=True)
-            weight_maps = _weights_for(DATASET, labels)
-            loss = weighted_bce_with_logits(logits, labels, weight_maps)
-            loss.backward()
-            optimizer.step()
-            total_loss += loss.detach()
+            weight_maps = _weights_for(DATASET, labels)          # built on the device (b200/weightmap.py)
+            # zero_grad + forward + crop + one-hot + weighted BCE + backward + SGD step: one call
+            total_loss += train_step(images, labels, weight_maps)
             if train_eval is None:
-                train_eval = _first_sample_metrics(logits.detach(), labels)
+                train_eval = _first_sample_metrics(train_step.logits, labels)
         train_eval_epoch = np.mean(train_eval, axis=1)
 
         if torch.cuda.is_available():

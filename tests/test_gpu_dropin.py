@@ -1,0 +1,100 @@
+"""GPU: the reference's call surface end to end -- `training(unet, train_loader, val_loader, epochs, batch_size,
+device, fold_dir, DATASET)` (trainer.py:15) and `testing(unet, test_loader, batch_size, device, output_dir)`
+(tester.py:13) -- running on the B200 kernels with device-side weight maps and metrics, against the CPU oracle
+stepping through the same batches (trainer.py:54-78 restated in oracle/unet_oracle.py, weight maps from
+oracle/weightmap_oracle.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+S, L = 220, 36
+
+
+def loaders(n_train, n_val, seed):
+    """Lists of (images f32 [1,1,S,S] CPU, labels i64 [1,1,L,L] CPU): what the reference's DataLoader yields
+    at batch size 1 (the size at which its weight broadcast is well defined)."""
+    import weightmap_oracle as W
+    g = torch.Generator().manual_seed(seed)
+    out, k = [], seed * 100
+    while len(out) < n_train + n_val:
+        full = torch.from_numpy(W.synthetic_labels(1, S, k, "blobs"))[:, None]               # blobs over the whole tile
+        k += 1
+        h = (S - L) // 2
+        lab = full[:, :, h:h + L, h:h + L].contiguous()                                        # label = its centre
+        if not 0.1 * L * L < int(lab.sum()) < 0.9 * L * L:                                     # both classes present
+            continue
+        img = 0.2 + 0.5 * full.float() + 0.3 * torch.rand(1, 1, S, S, generator=g)
+        out.append((img, lab))
+    return out[:n_train], out[n_train:]
+
+
+@pytest.mark.parametrize("hela", [True, False])
+def test_training_drop_in_matches_oracle_epochs(tmp_path, hela, capsys):
+    import unet_oracle as O
+    import weightmap_oracle as W
+    import trainer
+    from network import Unet
+    torch.set_num_threads(os.cpu_count() or 1)
+    train, val = loaders(3, 2, 5)
+    dataset = trainer.HELA if hela else "ISBI2012-from-argparse"        # identity test, as upstream (trainer.py:68)
+    torch.manual_seed(4)
+    net = Unet().to(DEV)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    trainer.training(net, train, val, 1, 1, DEV, str(tmp_path), dataset)   # epochs 0 and 1 (range(epochs + 1))
+    out = capsys.readouterr().out
+    assert "Training is finished" in out and "Model has been saved" in out
+    # ---- the same two epochs on the oracle
+    wm = (lambda l: W.weighted_map(l)) if hela else (lambda l: W.class_balance(l))
+    mom, losses, vlosses = {}, [], []
+    for epoch in range(2):
+        tot = 0.0
+        for img, lab in train:
+            w = torch.from_numpy(wm(lab[:, 0].numpy()))
+            loss, _, _ = O.train_step(sd, mom, img, lab, w)
+            tot += loss.item()
+        losses.append(tot / len(train))
+        vt = 0.0
+        for img, lab in val:
+            w = torch.from_numpy(wm(lab[:, 0].numpy()))
+            vt += O.loss_bce(O.center_crop_preds(O.forward(sd, img), L), lab, w).item()
+        vlosses.append(vt / len(val))
+    got = np.loadtxt(tmp_path / "progress" / "loss.out")
+    gotv = np.loadtxt(tmp_path / "progress" / "loss_val.out")
+    # epoch 0 is the same computation up to bf16 (north star: loss within 1e-2 relative); epoch 1 follows weights that
+    # already took three bf16-gradient SGD steps from a chaotic start (loss 100+ -> 10), hence the looser bound
+    assert abs(got[0] - losses[0]) <= 2e-2 * abs(losses[0]), (got, losses)
+    assert abs(got[1] - losses[1]) <= 0.15 * abs(losses[1]), (got, losses)
+    assert abs(gotv[0] - vlosses[0]) <= 5e-2 * abs(vlosses[0]), (gotv, vlosses)
+    for f in ("train_eval_iou", "train_eval_pe", "val_eval_iou", "val_eval_pe"):
+        assert np.loadtxt(tmp_path / "progress" / (f + ".out")).shape == (2,)
+    ck = torch.load(tmp_path / "models" / "unet_weight_save_best.pth", map_location="cpu")
+    assert list(ck.keys()) == O.PARAM_NAMES and all(v.dtype == torch.float32 for v in ck.values())
+    fresh = Unet()
+    fresh.load_state_dict(ck)                                             # the 46-key checkpoint round-trips
+
+
+def test_testing_drop_in_writes_reference_outputs(tmp_path, capsys):
+    import unet_oracle as O
+    import tester
+    import functions as Fn
+    from network import Unet
+    torch.manual_seed(6)
+    net = Unet().to(DEV)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    _, test = loaders(0, 2, 9)
+    tester.testing(net, test, 1, DEV, str(tmp_path))
+    assert "Testing is finished" in capsys.readouterr().out
+    for sub, stem in (("images", "image"), ("preds", "pred"), ("labels", "label")):
+        assert sorted(os.listdir(tmp_path / sub)) == [f"{stem}0.tif", f"{stem}1.tif"]
+    iou = np.loadtxt(tmp_path / "test_iou.out")
+    pe = np.loadtxt(tmp_path / "test_pe.out")
+    img, lab = test[0]
+    omask = O.predict_mask(sd, img, L)
+    ref = Fn.evaluation_metrics(omask[0], lab[0, 0])                      # CPU route of the reference formulas
+    # statistics of the FIRST image only (tester.py:42 drops the concatenation), std over a single value = 0
+    assert iou[1] == 0 and pe[1] == 0
+    assert abs(pe[0] - ref[1, 0]) <= 0.02 and (np.isnan(iou[0]) == np.isnan(ref[0, 0])) and (np.isnan(iou[0]) or abs(iou[0] - ref[0, 0]) <= 0.05)
