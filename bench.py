@@ -109,6 +109,15 @@ def cpu_reference_steps(steps, warmup, threads=None):
     return 1.0 / dt, cores, dt
 
 
+def workload_config(per_gpu, global_batch, world):
+    """The `config` object both arms report (BASELINE config 2 at N = 1, config 3 at N > 1)."""
+    return {"workload": f"original U-Net (64-1024 ch, valid convs) 572x572->388x388 training step "
+                        f"(fwd + weighted BCE + bwd + SGD-momentum), {per_gpu} tiles per GPU, global batch "
+                        f"{global_batch}, random-init weights (reference init, seed 0), weight map w0=10 sigma=5",
+            "baseline_config": 2 if world == 1 else 3, "tiles_per_gpu": per_gpu, "global_batch": global_batch,
+            "parallelism": f"dp{world}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -121,9 +130,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "U-Net 572x572->388x388 training step, CPU, batch 1 (BASELINE config 1); "
-                               "the reference is pure PyTorch: its path is restated in oracle/unet_oracle.py and pinned "
-                               "bit-exactly against /root/reference by oracle/validate_against_reference.py"},
+        "config": dict(workload_config(16 if args.gpus == 1 else 128 // args.gpus, 16 if args.gpus == 1 else 128, args.gpus),
+                       sample="each step = ONE tile of that workload (batch 1, fp32: BASELINE config 1) on the host cores; the "
+                              "reference is pure PyTorch (no build, cannot travel): its path is restated in "
+                              "oracle/unet_oracle.py and pinned bit-exactly against /root/reference by "
+                              "oracle/validate_against_reference.py"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -247,12 +258,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"original U-Net (64-1024 ch, valid convs) 572x572->388x388 training step "
-                                   f"(fwd + weighted BCE + bwd + SGD-momentum), {per_gpu} tiles per GPU, global batch "
-                                   f"{global_batch}, random-init weights (reference init, seed 0), weight map w0=10 sigma=5",
-                       "baseline_config": 2 if world == 1 else 3, "tiles_per_gpu": per_gpu, "global_batch": global_batch,
-                       "parallelism": f"dp{world}", "l2": "working set per step (>5 GB of activations) is far larger than the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks"},
+            "config": dict(workload_config(per_gpu, global_batch, world),
+                           l2="working set per step (>5 GB of activations) is far larger than the 126 MB L2; no flush needed",
+                           timing="CUDA events on the launch stream, barrier+synchronize both sides, max over ranks"),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": ke},
             "gpu_launches": launches,
             "clocks": clocks,

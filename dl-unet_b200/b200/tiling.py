@@ -35,3 +35,43 @@ def stitch(masks, height, width, tile_in=572):
     tile_out, halo, ny, nx, _, _ = plan(height, width, tile_in)
     m = masks.reshape(ny, nx, tile_out, tile_out).permute(0, 2, 1, 3).reshape(ny * tile_out, nx * tile_out)
     return m[:height, :width]
+
+
+def mirror_transform(image, dtype=torch.float32):
+    """data.py:249-312 (`mirror_transform` / `mirror_transform_tensor`) on the device: a CUDA image [..., n, n] is
+    mirrored outwards up to the network input size of `input_size_compute` -> [B, 1, input_size, input_size].
+    Same index rule as the reference's slice assignments (edge not repeated on the low side, repeated on the high
+    side); like them it needs an even size difference.  The reference returns float64; the network input is fp32."""
+    from . import lib as _lib
+    from .geometry import input_size_compute
+    from .ops import _chk, _need_cuda, _ptr, _stream
+    _need_cuda(image)
+    n = image.shape[-1]
+    if image.shape[-2] != n:
+        raise RuntimeError(f"expected square images, got {tuple(image.shape)}")
+    _, size, _ = input_size_compute(n)
+    if (size - n) % 2:
+        raise ValueError(f"could not broadcast: input size {size} minus image size {n} is odd (data.py:270-277)")
+    src = image.reshape(-1, n, n).contiguous().float()
+    out = torch.empty(src.shape[0], 1, size, size, dtype=torch.float32, device=image.device)
+    _chk(_lib.load().ub_mirror_pad(_ptr(src), _ptr(out), src.shape[0], n, size, _stream()), "mirror_pad")
+    return out.to(dtype)
+
+
+def segment_image(unet, image, tile_in=572, batch=16, ranks=(0, 1)):
+    """Overlap-tile inference of one whole image [H, W] (CUDA, fp32): reflect-pad, cut into tiles, run forward +
+    centre-crop + argmax (tester.py:27-30) on this rank's share of the tiles (rank r of n takes tiles r, r+n, ...;
+    independent units, no collective) and return (tile_indices, uint8 masks [k, tile_out, tile_out]).  With
+    ranks=(0, 1) the masks are stitched and the [H, W] uint8 mask is returned instead."""
+    rank, world = ranks
+    h, w = image.shape
+    tile_out, _, ny, nx, _, _ = plan(h, w, tile_in)
+    mine = list(range(rank, ny * nx, world))
+    tiles = cut_tiles(image, tile_in)[mine]
+    out = torch.empty(len(mine), tile_out, tile_out, dtype=torch.uint8, device=image.device)
+    for b0 in range(0, len(mine), batch):
+        t = tiles[b0:b0 + batch]
+        unet.engine.forward(t, train=False, argmax_out=out[b0:b0 + t.shape[0]], want_logits=False)
+    if world == 1:
+        return stitch(out, h, w, tile_in)
+    return mine, out

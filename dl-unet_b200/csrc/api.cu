@@ -1042,6 +1042,15 @@ int ub_mask_metrics(const void* pred, int pred_bytes, const void* label, int lab
   return (int)cudaGetLastError();
 }
 
+int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* stream) {
+  if (!image || !out) return UB_E_ARG;
+  // the reference's slice assignments need the same border on both sides and a border narrower than the image
+  if (b <= 0 || n <= 0 || size < n || ((size - n) & 1) || (size - n) / 2 >= n) return UB_E_SHAPE;
+  const long long total = (long long)b * size * size;
+  mirror_pad_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, out, n, size, (size - n) / 2, total);
+  return (int)cudaGetLastError();
+}
+
 int ub_colsum(const void* g, float* out, long long n_pix, int c, long long ld, void* stream) {
   if (!g || !out) return UB_E_ARG;
   if (c % 8 || c > 2048 || (256 % (c / 8)) || (ld % 8)) return UB_E_SHAPE;

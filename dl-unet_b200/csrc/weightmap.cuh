@@ -335,4 +335,24 @@ __global__ void __launch_bounds__(256) mask_metrics_kernel(const PT* __restrict_
   }
 }
 
+// ---- mirror padding of a test image up to the network's input size (data.py:249-312 `mirror_transform`):
+// out[b, y, x] = in[b, m(y), m(x)],  m(i) = pad - i below the image (reflect, edge not repeated) and
+// 2n - 1 - (i - pad) above it (the reference's slices repeat the edge row / column on that side).
+__device__ __forceinline__ int mirror_index(int i, int pad, int n) {
+  const int j = i - pad;
+  return j < 0 ? -j : (j >= n ? 2 * n - 1 - j : j);
+}
+
+__global__ void __launch_bounds__(256) mirror_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int n,
+                                                         int size, int pad, long long total) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(g % size);
+    const long long r = g / size;
+    const int y = (int)(r % size);
+    const long long b = r / size;
+    out[g] = __ldg(in + (b * n + mirror_index(y, pad, n)) * n + mirror_index(x, pad, n));
+  }
+}
+
 }  // namespace ub

@@ -146,6 +146,11 @@ int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, doubl
 int ub_class_balance(const void* label, int label_bytes, int b, int h, int w, float* out, void* workspace, int* status,
                      void* stream);
 
+/* ---- mirror padding of test images (data.py:249-312 mirror_transform / mirror_transform_tensor) ----
+ * image: fp32 [b,n,n]; out: fp32 [b,size,size], border (size-n)/2 on every side (size-n even, border < n):
+ * reflected without the edge below the image, with the edge repeated above it -- the reference's slices. */
+int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* stream);
+
 /* ---- segmentation metrics on the device (functions.py:150-213: IoU, Pixel_error) ----
  * pred / label: n elements, uint8 (bytes 1) or int64 (8).  counts[3] (device, caller zeroes) receive
  * |pred & label|, |pred | label| and sum |pred - label|:  IoU = counts[0]/counts[1], pixel error = counts[2]/n. */

@@ -117,3 +117,49 @@ def test_mask_metrics_match_reference_formulas():
     assert m[1, 0] == np.sum(abs(p - l)) / p.size
     m8 = Fn.evaluation_metrics(pred.to(torch.uint8), lab)
     assert np.array_equal(m, m8)
+
+
+@pytest.mark.parametrize("n", [388, 512, 250])
+def test_mirror_transform_matches_reference_slices(n):
+    """data.py:249-312: the reference's nine slice assignments, restated here literally (numpy) as the oracle."""
+    from b200 import tiling
+    from b200.geometry import input_size_compute
+    torch.manual_seed(n)
+    image = torch.rand(n, n)
+    _, size, _ = input_size_compute(n)
+    pad = (size - n) // 2
+    img = image.numpy().astype(np.float64)
+    ref = np.zeros((size, size))
+    ref[pad:pad + n, pad:pad + n] = img
+    ref[:pad, pad:pad + n] = img[pad:0:-1, 0:n]
+    ref[:pad, :pad] = ref[0:pad, pad + pad:pad:-1]
+    ref[:pad, pad + n:] = ref[0:pad, n + pad - 1:n - 1:-1]
+    ref[n + pad:, pad:pad + n] = img[n:n - pad - 1:-1, 0:n]
+    ref[n + pad:, :pad] = ref[n + pad:, pad + pad:pad:-1]
+    ref[n + pad:, n + pad:] = ref[n + pad:, n + pad - 1:n - 1:-1]
+    ref[pad:n + pad, :pad] = img[:, pad:0:-1]
+    ref[pad:n + pad, n + pad:] = img[:, n - 1:n - 1 - pad:-1]
+    out = tiling.mirror_transform(image.to(DEV))
+    assert out.shape == (1, 1, size, size)
+    assert np.array_equal(out[0, 0].cpu().numpy(), ref.astype(np.float32))       # a pure gather: bit-exact
+
+
+def test_segment_image_equals_per_tile_forward():
+    """Whole-image overlap-tile inference = the per-tile predict() masks put side by side, and sharding the tiles
+    over two ranks gives the same masks (independent units, no collective)."""
+    from network import Unet
+    from b200 import tiling
+    torch.manual_seed(1)
+    net = Unet().to(DEV)
+    image = torch.rand(300, 420, device=DEV)
+    mask = tiling.segment_image(net, image, tile_in=252, batch=3)
+    tile_out, halo, ny, nx, _, _ = tiling.plan(300, 420, 252)
+    assert mask.shape == (300, 420) and mask.dtype == torch.uint8 and (ny, nx) == (5, 7)
+    tiles = tiling.cut_tiles(image, 252)
+    ref = torch.cat([net.predict(tiles[i:i + 1]) for i in range(ny * nx)]).to(torch.uint8)
+    assert torch.equal(mask, tiling.stitch(ref, 300, 420, 252))
+    parts = [tiling.segment_image(net, image, tile_in=252, batch=4, ranks=(r, 2)) for r in range(2)]
+    full = torch.empty_like(ref)
+    for idx, m in parts:
+        full[idx] = m
+    assert torch.equal(full, ref)
