@@ -57,6 +57,8 @@ SIGNATURES = {
     "ub_weight_map_workspace_bytes": (_ll, [_i, _i, _i]),
     "ub_weight_map": (_i, [_P, _i, _i, _i, _i, C.c_double, C.c_double, _i, _P, _P, _P, _P]),
     "ub_class_balance": (_i, [_P, _i, _i, _i, _i, _P, _P, _P, _P]),
+    "ub_augment_workspace_bytes": (_ll, [_i, _i, _i, C.c_double]),
+    "ub_augment_batch": (_i, [_P, _P, _i, _i, _i, _P, _P, _i, _i, _i, C.c_double, C.c_double, _P, _P, _P, _P]),
     "ub_mirror_pad": (_i, [_P, _P, _i, _i, _i, _P]),
     "ub_mask_metrics": (_i, [_P, _i, _P, _i, _ll, _P, _P]),
     "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),

@@ -14,6 +14,7 @@
 
 #include "elementwise.cuh"
 #include "weightmap.cuh"
+#include "augment.cuh"
 #include "igemm.cuh"
 #include "igemm2.cuh"
 #include "probe.cuh"
@@ -518,6 +519,40 @@ static int weight_map_t(const LabelT* gt, int b, int h, int w, double w0, double
   wm_rows_kernel<LabelT><<<dim3((w + 127) / 128, h, b), 128, 8 * w, st>>>(gt, cand, count1, n_obj, out, status, h, w,
                                                                             w0, 2.0 * sigma2, truncate_wc, cap);
   return (int)cudaGetLastError();
+}
+
+// ---- augmentation (data.py:93-137, 225-245): window of the padded image the rotated crop can touch
+struct AugPlan {
+  int pad, padded, wn, win0, radius;
+  long long off_T, off_rot, off_blur, off_E, off_minmax, off_kern, total;
+};
+
+AugPlan aug_plan(int b, int crop, int size, double sigma) {
+  AugPlan p;
+  p.pad = size;                              // np.pad(image, pad_width=input_size) (data.py:111)
+  p.padded = crop + 2 * size;
+  // rotated crop: |coordinate - centre| <= size / sqrt(2) + 1; + 2 for the cubic support; + 45 so that the prefilter
+  // (pole -0.268: 45 pixels = 1e-26) cannot tell the window edge from the real edge of the padded image
+  int need = (int)(size * 0.70710678118654752 + 1.0) + 2 + 45;
+  int wn = ((2 * need + 31) / 32) * 32;
+  if (wn > p.padded) wn = p.padded;
+  if ((p.padded - wn) & 1) ++wn;
+  if (wn > p.padded) wn = p.padded;
+  p.wn = wn;
+  p.win0 = (p.padded - wn) / 2;
+  p.radius = (int)(4.0 * sigma + 0.5);       // scipy gaussian_filter: truncate = 4
+  const long long plane = (long long)wn * wn * 8, s2 = (long long)size * size;
+  long long o = 0;
+  auto take = [&](long long bytes) { const long long at = o; o += (bytes + 255) & ~255ll; return at; };
+  take(2ll * b * plane);                     // A at offset 0
+  p.off_T = take(2ll * b * plane);
+  p.off_rot = take(2ll * b * s2);
+  p.off_blur = take(2ll * 2 * b * s2 * 8);   // two fp64 buffers of [b][2][S][S]
+  p.off_E = take((long long)b * s2);
+  p.off_minmax = take(8ll * b);
+  p.off_kern = take(8ll * (2 * p.radius + 1));
+  p.total = o;
+  return p;
 }
 
 }  // namespace
@@ -1048,6 +1083,85 @@ int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* 
   if (b <= 0 || n <= 0 || size < n || ((size - n) & 1) || (size - n) / 2 >= n) return UB_E_SHAPE;
   const long long total = (long long)b * size * size;
   mirror_pad_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, out, n, size, (size - n) / 2, total);
+  return (int)cudaGetLastError();
+}
+
+long long ub_augment_workspace_bytes(int b, int crop, int input_size, double sigma) {
+  if (b <= 0 || crop < 2 || input_size < crop || sigma <= 0.0 || sigma > 64.0) return 0;
+  return aug_plan(b, crop, input_size, sigma).total;
+}
+
+int ub_augment_batch(const unsigned char* images, const unsigned char* targets, int n_img, int img_h, int img_w,
+                     const int* sample, const double* noise, int b, int crop, int input_size, double alpha,
+                     double sigma, float* out_image, long long* out_label, void* workspace, void* stream) {
+  if (!images || !targets || !sample || !noise || !out_image || !out_label || !workspace) return UB_E_ARG;
+  if (b <= 0 || b > 32767 || n_img <= 0 || crop < 2 || crop > img_h || crop > img_w || input_size < crop ||
+      ((input_size - crop) & 1) || input_size > 4096 || sigma <= 0.0 || sigma > 64.0)
+    return UB_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AugPlan P = aug_plan(b, crop, input_size, sigma);
+  char* ws = reinterpret_cast<char*>(workspace);
+  double* A = reinterpret_cast<double*>(ws);
+  double* T = reinterpret_cast<double*>(ws + P.off_T);
+  uint8_t* Rm = reinterpret_cast<uint8_t*>(ws + P.off_rot);
+  double* blur0 = reinterpret_cast<double*>(ws + P.off_blur);
+  double* blur1 = blur0 + 2ll * b * input_size * input_size;
+  uint8_t* E = reinterpret_cast<uint8_t*>(ws + P.off_E);
+  int* minmax = reinterpret_cast<int*>(ws + P.off_minmax);
+  double* kern = reinterpret_cast<double*>(ws + P.off_kern);
+  // Gaussian taps (scipy _gaussian_kernel1d) and the rotation geometry of scipy.ndimage.rotate(reshape=True) for the
+  // twelve angles data.py:115 draws, computed on the host
+  {
+    std::vector<double> k(2 * P.radius + 1);
+    double sum = 0.0;
+    for (int j = -P.radius; j <= P.radius; ++j) sum += (k[j + P.radius] = exp(-0.5 / (sigma * sigma) * (double)(j * j)));
+    for (auto& v : k) v /= sum;
+    cudaError_t e = cudaMemcpyAsync(kern, k.data(), k.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  AugAngles ang;
+  {
+    const double h3 = 0.86602540378443864676;   // cos 30
+    const double c30[4] = {1.0, h3, 0.5, 0.0}, s30[4] = {0.0, 0.5, h3, 1.0};
+    const double n = (double)P.padded;
+    for (int a = 0; a < 12; ++a) {
+      double c = c30[a % 3], s = s30[a % 3];
+      for (int q = 0; q < a / 3; ++q) {          // + 90 degrees: (c, s) -> (-s, c)
+        const double t = c;
+        c = -s;
+        s = t;
+      }
+      // rot = [[c, s], [-s, c]]; bounds of the rotated input plane
+      const double by[4] = {0.0, s * n, c * n, c * n + s * n}, bx[4] = {0.0, c * n, -s * n, -s * n + c * n};
+      double ymin = by[0], ymax = by[0], xmin = bx[0], xmax = bx[0];
+      for (int i = 1; i < 4; ++i) {
+        ymin = fmin(ymin, by[i]); ymax = fmax(ymax, by[i]);
+        xmin = fmin(xmin, bx[i]); xmax = fmax(xmax, bx[i]);
+      }
+      const int oh = (int)(ymax - ymin + 0.5), ow = (int)(xmax - xmin + 0.5);
+      const double cy = (oh - 1) / 2.0, cx = (ow - 1) / 2.0, ic = (n - 1.0) / 2.0;
+      AugGeom& g = ang.g[a];
+      g.r00 = c; g.r01 = s; g.r10 = -s; g.r11 = c;
+      g.off0 = ic - (c * cy + s * cx);
+      g.off1 = ic - (-s * cy + c * cx);
+      g.t = oh / 2 - input_size / 2;              // data.py:118-124
+      g.l = ow / 2 - input_size / 2;
+    }
+  }
+  const int wn = P.wn, S = input_size;
+  aug_init_minmax_kernel<<<(b + 127) / 128, 128, 0, st>>>(minmax, b);
+  aug_window_kernel<<<dim3((wn + 255) / 256, wn, 2 * b), 256, 0, st>>>(images, targets, sample, A, img_h, img_w, crop,
+                                                                        P.pad, P.win0, wn);
+  aug_prefilter_kernel<<<dim3((wn + 127) / 128, 2 * b), 128, 0, st>>>(A, wn, 2 * b);
+  aug_transpose_kernel<<<dim3((wn + 31) / 32, (wn + 31) / 32, 2 * b), 256, 0, st>>>(A, T, wn);
+  aug_prefilter_kernel<<<dim3((wn + 127) / 128, 2 * b), 128, 0, st>>>(T, wn, 2 * b);
+  aug_rotate_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(T, sample, Rm, ang, S, P.win0, wn);
+  aug_blur_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(noise, blur0, kern, P.radius, S, 0, 1, 1.0);
+  aug_blur_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(blur0, blur1, kern, P.radius, S, 1, 0, alpha);
+  aug_elastic_kernel<<<dim3((S + 255) / 256, S, b), 256, 0, st>>>(Rm, blur1, E, out_label, minmax, S, crop,
+                                                                  (input_size - crop) / 2);
+  const long long total = (long long)b * S * S;
+  aug_normalise_kernel<<<ew_grid(total), 256, 0, st>>>(E, minmax, out_image, (long long)S * S, total);
   return (int)cudaGetLastError();
 }
 

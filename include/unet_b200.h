@@ -146,6 +146,21 @@ int ub_weight_map(const void* label, int label_bytes, int b, int h, int w, doubl
 int ub_class_balance(const void* label, int label_bytes, int b, int h, int w, float* out, void* workspace, int* status,
                      void* stream);
 
+/* ---- training-sample augmentation on the device (data.py:93-137 ImageDataset.__getitem__, data.py:225-245
+ * elastic_transform) for a batch of b samples ----
+ * images / targets: uint8 [n_img, img_h, img_w] (targets 0 / 255).  sample: device int[b][4] = {image index, crop row
+ * x, crop column y, rotation in degrees (a multiple of 30)} -- the draws of data.py:97-104,115.  noise: device fp64
+ * [b][2][S][S] uniform [0,1) fields (random_state.rand(*shape) twice, data.py:236-237), S = input_size.
+ * Steps: crop window, np.pad(reflect, pad_width = input_size), scipy.ndimage.rotate (cubic spline + prefilter, reshape)
+ * + centre crop to S, elastic deformation (Gaussian sigma, amplitude alpha, bilinear), label crop + threshold(127),
+ * min-max normalisation.  out_image: fp32 [b,1,S,S]; out_label: int64 [b,1,crop,crop] in {0,1}.
+ * workspace: ub_augment_workspace_bytes(b, crop, S, sigma) bytes.  Host work: 81 Gaussian taps + 12 rotation
+ * geometries, one small H2D copy; otherwise asynchronous on `stream`. */
+long long ub_augment_workspace_bytes(int b, int crop, int input_size, double sigma);
+int ub_augment_batch(const unsigned char* images, const unsigned char* targets, int n_img, int img_h, int img_w,
+                     const int* sample, const double* noise, int b, int crop, int input_size, double alpha,
+                     double sigma, float* out_image, long long* out_label, void* workspace, void* stream);
+
 /* ---- mirror padding of test images (data.py:249-312 mirror_transform / mirror_transform_tensor) ----
  * image: fp32 [b,n,n]; out: fp32 [b,size,size], border (size-n)/2 on every side (size-n even, border < n):
  * reflected without the edge below the image, with the edge repeated above it -- the reference's slices. */

@@ -177,6 +177,48 @@ def main():
         np.savez_compressed(path, **gold)
         print("wrote", path, os.path.getsize(path), "bytes")
 
+    # ---- training-sample augmentation (data.py:93-137, 225-245) vs oracle/augment_oracle.py, SURVEY.md 8 row f2.
+    # The UNMODIFIED ImageDataset.__getitem__ runs on a stand-in `self` (its __init__ only reads files); numpy's
+    # global RNG is seeded, and the np.random.RandomState(None) inside elastic_transform is seeded for the call.
+    sys.modules.setdefault("wget", types.ModuleType("wget"))                 # data.py:2 imports it for downloads only
+    sys.path.insert(0, REF)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import data as ref_data                                              # its `from functions import ...` is the reference's
+    sys.path.remove(REF)
+    import augment_oracle as A
+    for name, size, crop, seed in (("augment_crop100", 160, 100, 3), ("augment_crop388", 512, 388, 4)):
+        img, gt = A.synthetic_dataset_image(size, seed)
+        fake = types.SimpleNamespace(image=[img], target=[gt], crop=crop, skip=10, alpha=3, sigma=10)
+        fake.pairs = [(i, j) for i in range(0, size - crop, 10) for j in range(0, size - crop, 10)]
+        fake.target_weighted_crop_distribution = [np.ones(len(fake.pairs)) / len(fake.pairs)]
+        np.random.seed(seed)
+        state = np.random.get_state()
+        real_rs = np.random.RandomState
+        np.random.RandomState = lambda s=None: real_rs(1000 + seed)
+        try:
+            inp_t, gt_t = ref_data.ImageDataset.__getitem__(fake, 0)
+        finally:
+            np.random.RandomState = real_rs
+        np.random.set_state(state)                                            # replay the draws (data.py:97-104, 115)
+        crop_id = np.random.choice(range(len(fake.pairs)), 1, p=fake.target_weighted_crop_distribution[0])[0]
+        x, y = fake.pairs[crop_id]
+        x += np.random.randint(-fake.skip / 2, (fake.skip / 2) + 1)
+        y += np.random.randint(-fake.skip / 2, (fake.skip / 2) + 1)
+        x, y = min(max(0, x), size - crop), min(max(0, y), size - crop)
+        rot = int(np.random.choice(np.arange(0, 360, 30)))
+        S = A.input_size_compute(crop)[1]
+        noise = A.noise_fields(1000 + seed, S)
+        o_img, o_gt = A.augment_sample(img, gt, x, y, rot, noise[0], noise[1], crop=crop)
+        check(f"{name}: image bit-equal to ImageDataset.__getitem__ (rot {rot}, window {x},{y})",
+              np.array_equal(inp_t[0].numpy(), o_img))
+        check(f"{name}: label bit-equal", np.array_equal(gt_t[0].numpy(), o_gt))
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, size=size, crop=crop, seed=seed, draws=np.array([0, x, y, rot]), noise_seed=1000 + seed,
+                            image=inp_t[0].numpy(), label=gt_t[0].numpy().astype(np.uint8))
+        print("wrote", path, os.path.getsize(path), "bytes")
+
     print("ALL PASS" if ok else "SOME CHECKS FAILED")
     return 0 if ok else 1
 

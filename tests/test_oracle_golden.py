@@ -92,3 +92,36 @@ def test_weightmap_oracle_raises_like_reference():
         W.weighted_map(np.zeros((1, 8, 8), dtype=np.int64))      # single class: counts[1] (functions.py:40)
     with pytest.raises(IndexError):
         W.class_balance(np.ones((1, 8, 8), dtype=np.int64))
+
+
+@pytest.mark.parametrize("name", ["augment_crop100", "augment_crop388"])
+def test_augment_oracle_reproduces_reference_golden(golden_dir, name):
+    """oracle/augment_oracle.py (own spline rotation / Gaussian / bilinear code, no scipy.ndimage transforms) against
+    the output of the reference's unmodified ImageDataset.__getitem__ (data.py:93-137) for the recorded draws."""
+    import augment_oracle as A
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    size, crop, seed = int(g["size"]), int(g["crop"]), int(g["seed"])
+    img, gt = A.synthetic_dataset_image(size, seed)
+    _, x, y, rot = (int(v) for v in g["draws"])
+    S = A.input_size_compute(crop)[1]
+    noise = A.noise_fields(int(g["noise_seed"]), S)
+    o_img, o_gt = A.augment_sample(img, gt, x, y, rot, noise[0], noise[1], crop=crop)
+    assert o_img.dtype == np.float32 and o_img.shape == (S, S) and o_gt.shape == (crop, crop)
+    assert np.array_equal(o_img, g["image"]) and np.array_equal(o_gt, g["label"])
+
+
+def test_augment_oracle_pieces_match_scipy():
+    import augment_oracle as A
+    from scipy import ndimage
+    rng = np.random.RandomState(0)
+    img = (ndimage.gaussian_filter(rng.rand(60, 60), 2) * 255).astype(np.uint8)
+    pad = np.pad(img, 90, mode="reflect")                                   # pad > n - 1: repeated reflection
+    idx = A.reflect_index(np.arange(60 + 180), 90, 60)
+    assert np.array_equal(pad, img[idx][:, idx])
+    for deg in (0, 30, 150, 270):
+        ref = ndimage.rotate(pad, deg)
+        h, w = ref.shape
+        crop = ref[h // 2 - 45:h // 2 + 45, w // 2 - 45:w // 2 + 45]
+        assert np.array_equal(A.rotate_center_crop(pad, deg, 90), crop), deg
+    field = rng.rand(90, 90)
+    assert np.abs(A.gaussian_filter_zero(field, 10) - ndimage.gaussian_filter(field, 10, mode="constant", cval=0)).max() < 1e-14
