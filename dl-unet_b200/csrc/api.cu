@@ -1087,7 +1087,7 @@ int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* 
 }
 
 long long ub_augment_workspace_bytes(int b, int crop, int input_size, double sigma) {
-  if (b <= 0 || crop < 2 || input_size < crop || sigma <= 0.0 || sigma > 64.0) return 0;
+  if (b <= 0 || crop < 2 || input_size < crop || sigma <= 0.0 || sigma > 11.8) return 0;   // radius = int(4 sigma + 0.5) <= AUG_MAX_RADIUS
   return aug_plan(b, crop, input_size, sigma).total;
 }
 
@@ -1096,7 +1096,7 @@ int ub_augment_batch(const unsigned char* images, const unsigned char* targets, 
                      double sigma, float* out_image, long long* out_label, void* workspace, void* stream) {
   if (!images || !targets || !sample || !noise || !out_image || !out_label || !workspace) return UB_E_ARG;
   if (b <= 0 || b > 32767 || n_img <= 0 || crop < 2 || crop > img_h || crop > img_w || input_size < crop ||
-      ((input_size - crop) & 1) || input_size > 4096 || sigma <= 0.0 || sigma > 64.0)
+      ((input_size - crop) & 1) || input_size > 4096 || sigma <= 0.0 || sigma > 11.8)
     return UB_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const AugPlan P = aug_plan(b, crop, input_size, sigma);
@@ -1156,8 +1156,9 @@ int ub_augment_batch(const unsigned char* images, const unsigned char* targets, 
   aug_transpose_kernel<<<dim3((wn + 31) / 32, (wn + 31) / 32, 2 * b), 256, 0, st>>>(A, T, wn);
   aug_prefilter_kernel<<<dim3((wn + 127) / 128, 2 * b), 128, 0, st>>>(T, wn, 2 * b);
   aug_rotate_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(T, sample, Rm, ang, S, P.win0, wn);
-  aug_blur_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(noise, blur0, kern, P.radius, S, 0, 1, 1.0);
-  aug_blur_kernel<<<dim3((S + 255) / 256, S, 2 * b), 256, 0, st>>>(blur0, blur1, kern, P.radius, S, 1, 0, alpha);
+  const dim3 bgrid((S + AUG_BLUR_LINES - 1) / AUG_BLUR_LINES, (S + AUG_BLUR_LEN - 1) / AUG_BLUR_LEN, 2 * b);
+  aug_blur_kernel<<<bgrid, 256, 0, st>>>(noise, blur0, kern, P.radius, S, 0, 1, 1.0);
+  aug_blur_kernel<<<bgrid, 256, 0, st>>>(blur0, blur1, kern, P.radius, S, 1, 0, alpha);
   aug_elastic_kernel<<<dim3((S + 255) / 256, S, b), 256, 0, st>>>(Rm, blur1, E, out_label, minmax, S, crop,
                                                                   (input_size - crop) / 2);
   const long long total = (long long)b * S * S;

@@ -60,15 +60,42 @@ __global__ void __launch_bounds__(128) aug_prefilter_kernel(double* __restrict__
     c0 += zk * (a[(long long)k * n] * gain);
     zk *= z;
   }
+  // the recursions are sequential but their loads are not: fetch 8 rows ahead of the dependent chain
   double prev = c0;
   a[0] = c0;
-  for (int k = 1; k < n; ++k) {
+  int k = 1;
+  for (; k + 8 <= n; k += 8) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = a[(long long)(k + i) * n];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      prev = v[i] * gain + z * prev;
+      v[i] = prev;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[(long long)(k + i) * n] = v[i];
+  }
+  for (; k < n; ++k) {
     prev = a[(long long)k * n] * gain + z * prev;
     a[(long long)k * n] = prev;
   }
   double next = (z / (z * z - 1.0)) * (prev + z * a[(long long)(n - 2) * n]);
   a[(long long)(n - 1) * n] = next;
-  for (int k = n - 2; k >= 0; --k) {
+  k = n - 2;
+  for (; k - 7 >= 0; k -= 8) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = a[(long long)(k - i) * n];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      next = z * (next - v[i]);
+      v[i] = next;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[(long long)(k - i) * n] = v[i];
+  }
+  for (; k >= 0; --k) {
     next = z * (next - a[(long long)k * n]);
     a[(long long)k * n] = next;
   }
@@ -132,21 +159,59 @@ __global__ void __launch_bounds__(256) aug_rotate_kernel(const double* __restric
 
 // ---- Gaussian filter with zero boundary along one axis of [planes][S][S] (scipy gaussian_filter1d, mode
 // 'constant'); `affine` applies in = 2 * in - 1 on the fly (first pass), `scale` multiplies the result (alpha).
+// Block = 32 lines x 64 positions along the filtered axis, staged with its halo in shared memory (fp64); a thread
+// produces 8 consecutive outputs from one sliding read of the taps (radius <= AUG_MAX_RADIUS).
+constexpr int AUG_MAX_RADIUS = 48, AUG_BLUR_LEN = 64, AUG_BLUR_LINES = 32;
 __global__ void __launch_bounds__(256) aug_blur_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                        const double* __restrict__ kern, int radius, int S, int axis,
                                                        int affine, double scale) {
-  const int pl = blockIdx.z, y = blockIdx.y;
+  __shared__ double tile[AUG_BLUR_LEN + 2 * AUG_MAX_RADIUS][AUG_BLUR_LINES + 1];
+  __shared__ double sk[2 * AUG_MAX_RADIUS + 1];
+  const int pl = blockIdx.z;
+  const int p0 = blockIdx.y * AUG_BLUR_LEN;     // first position along the filtered axis
+  const int l0 = blockIdx.x * AUG_BLUR_LINES;   // first line (the other axis)
   const double* src = in + (long long)pl * S * S;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < S; x += gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int j = -radius; j <= radius; ++j) {
-      const int yy = axis == 0 ? y + j : y, xx = axis == 0 ? x : x + j;
-      if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
-      double v = src[(long long)yy * S + xx];
-      if (affine) v = 2.0 * v - 1.0;
-      acc += kern[j + radius] * v;
+  const int span = AUG_BLUR_LEN + 2 * radius;
+  for (int i = threadIdx.x; i < 2 * radius + 1; i += 256) sk[i] = kern[i];
+  // stage: tile[pos][line]; consecutive threads read consecutive addresses of whichever axis is contiguous
+  for (int i = threadIdx.x; i < span * AUG_BLUR_LINES; i += 256) {
+    int pos, line;
+    if (axis == 0) {   // filtered axis = rows: lines are columns (contiguous)
+      line = i % AUG_BLUR_LINES;
+      pos = i / AUG_BLUR_LINES;
+    } else {           // filtered axis = columns (contiguous)
+      pos = i % span;
+      line = i / span;
     }
-    out[((long long)pl * S + y) * S + x] = acc * scale;
+    const int p = p0 - radius + pos, l = l0 + line;
+    double v = 0.0;
+    if (p >= 0 && p < S && l < S) {
+      v = axis == 0 ? src[(long long)p * S + l] : src[(long long)l * S + p];
+      if (affine) v = 2.0 * v - 1.0;
+    }
+    tile[pos][line] = v;
+  }
+  __syncthreads();
+  const int line = threadIdx.x & 31, seg = threadIdx.x >> 5;   // 8 segments of 8 outputs
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+  const int base = seg * 8;
+  for (int j = 0; j < 2 * radius + 8; ++j) {
+    const double v = tile[base + j][line];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = j - i;                       // tap index for output i
+      if (t >= 0 && t <= 2 * radius) acc[i] += sk[t] * v;
+    }
+  }
+  const int l = l0 + line;
+  if (l < S) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + base + i;
+      if (p < S) out[(long long)pl * S * S + (axis == 0 ? (long long)p * S + l : (long long)l * S + p)] = acc[i] * scale;
+    }
   }
 }
 

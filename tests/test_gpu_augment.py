@@ -65,7 +65,7 @@ def test_augment_draws_follow_reference_order_and_feed_training():
     from network import Unet
     from b200 import train as T
     img, gt = A.synthetic_dataset_image(300, 21)
-    aug = DeviceAugmenter(img[None], gt[None], crop=36)          # input_size 220 -> 36 x 36 labels
+    aug = DeviceAugmenter(img[None], gt[None], crop=36)          # input_size_compute(36): 380 in, 196 out >= 36
     np.random.seed(9)
     d = aug.draw([0, 0, 0])
     np.random.seed(9)
@@ -77,7 +77,7 @@ def test_augment_draws_follow_reference_order_and_feed_training():
         rot = np.random.choice(np.arange(0, 360, 30))
         assert tuple(d[k]) == (0, min(max(0, x), 300 - 36), min(max(0, y), 300 - 36), rot)
     images, labels = aug([0, 0])
-    assert images.shape == (2, 1, 220, 220) and labels.shape == (2, 1, 36, 36)
+    assert aug.input_size == 380 and images.shape == (2, 1, 380, 380) and labels.shape == (2, 1, 36, 36)
     assert float(images.min()) == 0.0 and float(images.max()) == 1.0 and set(labels.unique().tolist()) <= {0, 1}
     torch.manual_seed(0)
     net = Unet().to(DEV)
