@@ -2,7 +2,8 @@
 
 Runs ONLY in the build container, where /root/reference exists (it cannot travel to the GPU box):
 
-    python oracle/validate_against_reference.py            # check + write golden fixtures
+    python oracle/validate_against_reference.py                  # check only
+    python oracle/validate_against_reference.py --write-golden   # check + (re)write tests/golden/*.npz
 
 What is checked, on the CPU in fp32, bit-exactly (torch.equal):
   * init_state_dict(seed) == torch.manual_seed(seed); network.Unet().state_dict()
@@ -52,6 +53,17 @@ def grad_digest(g):
     g = g.detach().double().flatten()
     head = (g[:5].tolist() + [0.0] * 5)[:5]
     return np.array([g.norm().item(), g.sum().item(), g.abs().max().item()] + head, dtype=np.float64)
+
+
+WRITE_GOLDEN = "--write-golden" in sys.argv
+
+
+def save_golden(path, **arrays):
+    """Golden fixtures are only (re)written on request: a plain run is a pure check.  (The reference's weighted_map is
+    not even deterministic run to run -- OpenCV's distanceTransform flips the last bit of ~5 % of its float sqrts --
+    so rewriting the files on every test run would churn the repository.)"""
+    if WRITE_GOLDEN:
+        np.savez_compressed(path, **arrays)
 
 
 def main():
@@ -143,18 +155,19 @@ def main():
         gold["ce_loss0"] = np.float64(closs.item())
         gold["ce_grad_digest0"] = np.stack([grad_digest(cgrads[k]) for k in O.PARAM_NAMES])
         path = os.path.join(ROOT, "tests", "golden", f"unet_S{S}_B{B}_seed{seed}.npz")
-        np.savez_compressed(path, **gold)
-        print("wrote", path, os.path.getsize(path), "bytes")
+        save_golden(path, **gold)
+        if WRITE_GOLDEN:
+            print("wrote", path, os.path.getsize(path), "bytes")
 
     # ---- pool indices / tie rule
     x = torch.relu(torch.randn(2, 3, 8, 8)).round()  # many ties and all-zero windows
     v, i = O.pool_with_indices(x)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pool_ties.npz"), x=x.numpy(), v=v.numpy(), i=i.numpy())
+    save_golden(os.path.join(ROOT, "tests", "golden", "pool_ties.npz"), x=x.numpy(), v=v.numpy(), i=i.numpy())
 
     # ---- reference weight-map helpers, for the f1 row (kept for later rounds)
     lab = (torch.rand(1, 36, 36) > 0.5).long()
     cb = ref_functions.class_balance(lab)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "class_balance.npz"), lab=lab.numpy(), w=cb.numpy())
+    save_golden(os.path.join(ROOT, "tests", "golden", "class_balance.npz"), lab=lab.numpy(), w=cb.numpy())
 
     # ---- weight maps (functions.py:7-117) vs oracle/weightmap_oracle.py, SURVEY.md section 8 row f1.
     # cv.distanceTransform's float sqrt is not correctly rounded (1 ulp off on ~20 % of the pixels, measured here
@@ -174,8 +187,9 @@ def main():
         check(f"class_balance {kind} {size}: bit-equal", np.array_equal(rc, W.class_balance(lab)))
         gold["cb"] = rc
         path = os.path.join(ROOT, "tests", "golden", f"weightmap_{kind}_{size}.npz")
-        np.savez_compressed(path, **gold)
-        print("wrote", path, os.path.getsize(path), "bytes")
+        save_golden(path, **gold)
+        if WRITE_GOLDEN:
+            print("wrote", path, os.path.getsize(path), "bytes")
 
     # ---- training-sample augmentation (data.py:93-137, 225-245) vs oracle/augment_oracle.py, SURVEY.md 8 row f2.
     # The UNMODIFIED ImageDataset.__getitem__ runs on a stand-in `self` (its __init__ only reads files); numpy's
@@ -215,9 +229,10 @@ def main():
               np.array_equal(inp_t[0].numpy(), o_img))
         check(f"{name}: label bit-equal", np.array_equal(gt_t[0].numpy(), o_gt))
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
-        np.savez_compressed(path, size=size, crop=crop, seed=seed, draws=np.array([0, x, y, rot]), noise_seed=1000 + seed,
+        save_golden(path, size=size, crop=crop, seed=seed, draws=np.array([0, x, y, rot]), noise_seed=1000 + seed,
                             image=inp_t[0].numpy(), label=gt_t[0].numpy().astype(np.uint8))
-        print("wrote", path, os.path.getsize(path), "bytes")
+        if WRITE_GOLDEN:
+            print("wrote", path, os.path.getsize(path), "bytes")
 
     print("ALL PASS" if ok else "SOME CHECKS FAILED")
     return 0 if ok else 1
