@@ -17,19 +17,12 @@ __device__ __forceinline__ void load_mask(const __nv_bfloat16* mcols, uint4 (&m4
   for (int i = 0; i < 4; ++i) m4[i] = __ldg(mp + i);
 }
 
-// mask_on: apply the ReLU-backward mask; mask_valid = false zeroes the row (pixel outside the image), else m4 holds
-// the mask row, loaded by the caller (igemm2 requests it one chunk ahead so that its L2 latency is off the
-// tfull -> TMA-store critical path).
-__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
-                                          const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
-                                          const float* shead = nullptr, float2* head_part = nullptr,
-                                          bool stage = true) {
-  uint32_t v[32];
-  tmem_ld_32x32b_x32(taddr, v);
-  tmem_ld_wait();
-  float f[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+// f[32]: this thread's pixel, 32 fp32 columns fresh from the accumulator -> bias, ReLU, optional head partials,
+// bf16, optional ReLU-backward mask, swizzled staging row `row` (128 B rows, SWIZZLE_128B as the TMA store expects).
+__device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, int relu, bool mask_on, bool mask_valid,
+                                           const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
+                                           const float* shead = nullptr, float2* head_part = nullptr,
+                                           bool stage = true) {
   if (sbias != nullptr) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -77,6 +70,23 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, in
     const int chunk = (h * 4 + c) ^ (row & 7);
     *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
   }
+}
+
+
+// mask_on: apply the ReLU-backward mask; mask_valid = false zeroes the row (pixel outside the image), else m4 holds
+// the mask row, loaded by the caller (igemm2 requests it one chunk ahead so that its L2 latency is off the
+// tfull -> TMA-store critical path).
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
+                                          const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
+                                          const float* shead = nullptr, float2* head_part = nullptr,
+                                          bool stage = true) {
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(taddr, v);
+  tmem_ld_wait();
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage);
 }
 
 }  // namespace ub

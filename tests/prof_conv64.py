@@ -1,0 +1,40 @@
+"""The 64 -> 64 channel level-1 convolution alone (for ncu): python tests/prof_conv64.py [igemm3: 0|1] [batch]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
+import torch  # noqa: E402
+from b200 import ops  # noqa: E402
+
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+dev = "cuda:0"
+ops.set_option(3, 2 if mode else 0)
+hout = 568
+x = torch.randn(B, hout + 2, hout + 2, 64, device=dev).to(torch.bfloat16)
+y = torch.empty(B, hout, hout, 64, dtype=torch.bfloat16, device=dev)
+dy = torch.randn(B, hout, hout, 64, device=dev).to(torch.bfloat16)
+dx = torch.empty(B, hout + 2, hout + 2, 64, dtype=torch.bfloat16, device=dev)
+wf = torch.randn(64, 9 * 64, device=dev).to(torch.bfloat16) / 30
+bias = torch.zeros(64, device=dev)
+for _ in range(2):
+    ops.conv3x3_fwd(x, wf, bias, y)
+    ops.conv3x3_dgrad(dy, wf, dx, x)
+torch.cuda.synchronize()
+print("ok")
+if "--sweep" in sys.argv:
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+    for dbg in (0, 4, 4 + 8, 4 + 16, 4 + 8 + 16):
+        ops.set_option(4, dbg)
+        print(f"dbg={dbg}: fwd {timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y)):.1f} us  dgrad {timeit(lambda: ops.conv3x3_dgrad(dy, wf, dx, x)):.1f} us", flush=True)
+    ops.set_option(4, 0)

@@ -91,3 +91,18 @@ t_fused = timeit(lambda: ops.conv3x3_fwd_head(x, wf, bias, y, hw, hb, lg, None))
 t_inf = timeit(lambda: ops.conv3x3_fwd_head(x, wf, bias, None, hw, hb, None, am))
 print(f"conv12e+head: conv {t_plain:.1f} us + head {t_head:.1f} us = {t_plain + t_head:.1f} us; fused (train) {t_fused:.1f} us; "
       f"fused, no activation store, argmax only (inference) {t_inf:.1f} us")
+
+# 64 -> 64 layers: three-taps-per-instruction kernel (igemm3, option 3 = 1) vs the haloed-patch kernel (igemm2, option 3 = 0)
+for name, hout in (("conv12c", 568), ("conv12e", 388)):
+    x, y = rnd(B, hout + 2, hout + 2, 64), torch.empty(B, hout, hout, 64, dtype=torch.bfloat16, device=DEV)
+    dy, dx = rnd(B, hout, hout, 64), torch.empty(B, hout + 2, hout + 2, 64, dtype=torch.bfloat16, device=DEV)
+    wf, wd = rnd(64, 9 * 64) / 30, rnd(64, 9 * 64) / 30
+    bias = torch.zeros(64, device=DEV)
+    fl = 2.0 * B * hout * hout * 64 * 64 * 9
+    res = {}
+    for mode in (0, 2):
+        ops.set_option(3, mode)
+        res[mode] = (timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y)), timeit(lambda: ops.conv3x3_dgrad(dy, wd, dx, x)))
+    ops.set_option(3, 1)
+    print(f"{name}: fwd igemm2 {res[0][0]:.1f} us ({fl / res[0][0] / 1e6:.0f} TF/s) -> igemm3 {res[2][0]:.1f} us ({fl / res[2][0] / 1e6:.0f} TF/s); "
+          f"dgrad igemm2 {res[0][1]:.1f} us -> igemm3 {res[2][1]:.1f} us ({fl / res[2][1] / 1e6:.0f} TF/s)")

@@ -104,6 +104,39 @@ def test_conv3x3_fwd_fused_head(ops, shape):
     assert torch.equal(am2, am)
 
 
+@pytest.mark.parametrize("shape", [(1, 20, 20), (2, 70, 70), (1, 5, 3), (2, 33, 64), (1, 131, 47)])
+def test_igemm3_three_taps_per_instruction(ops, shape):
+    """igemm3.cuh (N = 192: the three taps of a kernel row in one tcgen05.mma, shift-and-add across pixels in the
+    epilogue) on every path it supports -- forward, dgrad with fused ReLU backward, fused head -- against the same
+    torch references as the default kernels; option 3 = 2 routes all 64 -> 64 convs through it."""
+    n, h, w = shape
+    ops.set_option(3, 2)
+    try:
+        torch.manual_seed(sum(shape))
+        x = torch.randn(n, 64, h, w, device=DEV).clamp_min(0)
+        wt = torch.randn(64, 64, 3, 3, device=DEV) / 24
+        b = torch.randn(64, device=DEV)
+        xq, wq = bf(x).float(), bf(wt).float()
+        act = F.relu(F.conv2d(xq, wq, b))
+        y = torch.full((n, h - 2, w - 2, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+        wp = ops.pack_weight(wt, ops.PACK_CONV_FWD)
+        ops.conv3x3_fwd(nhwc(x), wp, b, y, relu=True)
+        assert rel_l2(nchw(y), act) < BF16_OUT_TOL
+        dy = torch.randn(n, 64, h - 2, w - 2, device=DEV)
+        gx = F.conv_transpose2d(bf(dy).float(), wq)
+        dx = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))
+        assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+        hw, hb = torch.randn(2, 64, 1, 1, device=DEV) / 8, torch.randn(2, device=DEV)
+        logits = torch.full((n, 2, h - 2, w - 2), float("nan"), device=DEV)
+        am = torch.full((n, h - 2, w - 2), 7, dtype=torch.uint8, device=DEV)
+        ops.conv3x3_fwd_head(nhwc(x), wp, b, None, hw, hb, logits, am)
+        assert rel_l2(logits, F.conv2d(act, hw, hb)) < FP32_TOL
+        assert torch.equal(am.long(), (logits[:, 1] > logits[:, 0]).long())
+    finally:
+        ops.set_option(3, 1)
+
+
 def test_conv3x3_strided_views_write_in_place(ops):
     n, h, w, cin, cout = 2, 22, 22, 64, 128
     torch.manual_seed(1)
