@@ -19,6 +19,10 @@ import torch
 from . import ops
 from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
 
+# encoder levels whose 2x2 max pool runs inside the epilogue of conv{l}2c (the haloed-patch kernel: <= 256 channels);
+# UB_FUSED_POOL_LEVELS=0 restores the separate pool kernel everywhere (experiments)
+FUSED_POOL_LEVELS = int(__import__("os").environ.get("UB_FUSED_POOL_LEVELS", "2"))
+
 PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
 # order in which backward finishes each layer's gradients
 BACKWARD_LAYER_ORDER = [n for (n, _, _, _) in reversed(LAYERS)]
@@ -165,7 +169,9 @@ class Workspace:
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
             a[f"e{l}1"] = torch.empty(B, g.enc1[l], g.enc1[l], C, **bf)
-            a[f"e{l}2"] = torch.empty(B, g.enc2[l], g.enc2[l], C, **bf)
+            # levels 1-2 pool inside the conv epilogue: the full-resolution conv{l}2c output never exists in HBM
+            # (backward needs only the pooled values, the argmax codes and the layer's INPUT)
+            a[f"e{l}2"] = torch.empty(B, g.enc2[l], g.enc2[l], C, **bf) if l > FUSED_POOL_LEVELS else None
             a[f"p{l}"] = torch.empty(B, g.pool[l], g.pool[l], C, **bf)
             a[f"i{l}"] = torch.empty(B, g.pool[l], g.pool[l], C, dtype=torch.uint8, device=device)
             # zero once: the padded border of the skip half is never written afterwards
@@ -178,8 +184,10 @@ class Workspace:
         self.grad = {}
         if train:
             for k, t in a.items():
-                if k[0] != "i":
+                if k[0] != "i" and t is not None:
                     self.grad[k] = torch.empty_like(t)
+            for l in range(1, FUSED_POOL_LEVELS + 1):
+                self.grad[f"e{l}2"] = torch.empty(B, g.enc2[l], g.enc2[l], LEVEL_C[l], **bf)
         self.image = None
 
 
@@ -219,14 +227,18 @@ class Engine:
         P, pk = st.p, st.packs
 
         ops.conv1_fwd(image, P("conv11c.weight"), P("conv11c.bias"), a["e11"])
-        ops.conv3x3_fwd(a["e11"], pk["conv12c"][0], P("conv12c.bias"), a["e12"])
-        x = a["e12"]
+        x = None
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
             if l > 1:
                 ops.conv3x3_fwd(x, pk[f"conv{l}1c"][0], P(f"conv{l}1c.bias"), a[f"e{l}1"])
+            if l <= FUSED_POOL_LEVELS:
+                # conv{l}2c + max pool + argmax codes + skip copy in one launch (network.py:132-133, 138-139)
+                ops.conv3x3_fwd_pool(a[f"e{l}1"], pk[f"conv{l}2c"][0], P(f"conv{l}2c.bias"), C, None, a[f"p{l}"], a[f"i{l}"],
+                                     a[f"cat{l}"][..., :C], g.coff[l])
+            else:
                 ops.conv3x3_fwd(a[f"e{l}1"], pk[f"conv{l}2c"][0], P(f"conv{l}2c.bias"), a[f"e{l}2"])
-            ops.pool2x2_fwd(a[f"e{l}2"], a[f"p{l}"], a[f"i{l}"], a[f"cat{l}"][..., :C], g.coff[l])
+                ops.pool2x2_fwd(a[f"e{l}2"], a[f"p{l}"], a[f"i{l}"], a[f"cat{l}"][..., :C], g.coff[l])
             x = a[f"p{l}"]
         ops.conv3x3_fwd(x, pk["conv51c"][0], P("conv51c.bias"), a["e51"])
         ops.conv3x3_fwd(a["e51"], pk["conv52c"][0], P("conv52c.bias"), a["e52"])

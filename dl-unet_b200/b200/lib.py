@@ -41,6 +41,7 @@ SIGNATURES = {
     "ub_unpack_all": (_i, [_P, _i, _ll, _i, _P]),
     "ub_conv3x3_fwd": (_i, [_T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_fwd_head": (_i, [_T4, _P, _P, _T4, _P, _P, _P, _P, _P]),
+    "ub_conv3x3_fwd_pool": (_i, [_T4, _P, _P, _i, _T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
     "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_upconv2x2_fwd": (_i, [_T4, _P, _P, _T4, _P]),

@@ -179,6 +179,16 @@ def conv3x3_fwd_head(x, w_fwd, bias, y, head_w, head_b, logits=None, argmax=None
                                              _ptr(logits), _ptr(argmax), _stream()), "conv3x3_fwd_head")
 
 
+def conv3x3_fwd_pool(x, w_fwd, bias, cout, y, pooled, idx, cat=None, c_off=0):
+    """3x3 conv (bias + ReLU) with the 2x2 max pool, its argmax codes and the skip copy produced by the same launch
+    (network.py:132-133).  y = None: the full-resolution activation is never stored."""
+    _need_cuda(x, w_fwd, pooled, idx, y, cat)
+    n, h, w, ci = x.shape
+    with _timed("igemm", 2.0 * n * (h - 2) * (w - 2) * cout * 9 * ci):
+        _chk(_lib.load().ub_conv3x3_fwd_pool(_t4p(x), _ptr(w_fwd), _ptr(bias), int(cout), _t4p(y), _ptr(pooled), _ptr(idx),
+                                             _t4p(cat), int(c_off), _stream()), "conv3x3_fwd_pool")
+
+
 def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None):
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, co = dy.shape

@@ -224,17 +224,17 @@ void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) 
   P.out_H = H;
 }
 
-template <int BN, int MT, bool HEAD = false>
+template <int BN, int MT, bool HEAD = false, bool POOL = false>
 int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT, HEAD, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm2_kernel<BN, MT, HEAD><<<grid, 384, smem_bytes, st>>>(P);
+  igemm2_kernel<BN, MT, HEAD, POOL><<<grid, 384, smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
 }
 
@@ -272,9 +272,16 @@ struct HeadArgs {
   unsigned char* argmax;
   int store_out;
 };
+struct PoolArgs {
+  void* y;
+  unsigned char* idx;
+  void* cat;
+  int cat_H, cat_W, cat_C, c_off, store_out;
+};
 
 int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const ub_tensor4* out, int relu,
-                  const ub_tensor4* relu_src, int base_off, cudaStream_t st, const HeadArgs* head = nullptr) {
+                  const ub_tensor4* relu_src, int base_off, cudaStream_t st, const HeadArgs* head = nullptr,
+                  const PoolArgs* pool = nullptr) {
   Igemm2Params P;
   memset(&P, 0, sizeof(P));
   P.store_out = 1;
@@ -331,9 +338,26 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
     P.argmax = head->argmax;
     P.store_out = head->store_out;
   }
+  if (pool) {
+    P.pool_y = (__nv_bfloat16*)pool->y;
+    P.pool_idx = pool->idx;
+    P.pool_cat = (__nv_bfloat16*)pool->cat;
+    P.pool_C = N;
+    P.cat_H = pool->cat_H;
+    P.cat_W = pool->cat_W;
+    P.cat_C = pool->cat_C;
+    P.c_off = pool->c_off;
+    P.store_out = pool->store_out;
+  }
   if (P.store_out && (e = make_map4(&P.o_map, out, 8, 16))) return e;
   const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem;
   if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
+  if (pool) {
+    if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1, false, true>(P, smem_bytes, st);
+    if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1, false, true>(P, smem_bytes, st);
+    if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2, false, true>(P, smem_bytes, st);
+    return UB_E_SHAPE;
+  }
   if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
   if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
@@ -770,6 +794,37 @@ int ub_conv3x3_fwd_head(const ub_tensor4* x, const void* w_fwd, const float* bia
   HeadArgs h{head_w, head_b, logits, argmax, y ? 1 : 0};
   if (igemm3_eligible(x, &out, false)) return launch_igemm3(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, &h);
   return launch_igemm2(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, &h);
+}
+
+int ub_conv3x3_fwd_pool(const ub_tensor4* x, const void* w_fwd, const float* bias, int cout, const ub_tensor4* y,
+                        void* pooled, unsigned char* idx, const ub_tensor4* cat, int c_off, void* stream) {
+  int e;
+  if ((e = check_view(x))) return e;
+  if (!w_fwd || !pooled || !idx) return UB_E_ARG;
+  if (!aligned16(w_fwd) || (bias && !aligned16(bias)) || !aligned16(pooled) || (reinterpret_cast<uintptr_t>(idx) & 7)) return UB_E_ALIGN;
+  if (x->h < 4 || x->w < 4 || x->c > 256 || cout > 256 || cout <= 0 || (cout % 64)) return UB_E_SHAPE;
+  ub_tensor4 out;
+  if (y) {
+    if ((e = check_view(y))) return e;
+    if (y->n != x->n || y->h != x->h - 2 || y->w != x->w - 2 || y->c != cout) return UB_E_SHAPE;
+    out = *y;
+  } else {   // the full-resolution activation is not wanted: only its geometry is needed
+    out = *x;
+    out.ptr = nullptr;
+    out.h = x->h - 2;
+    out.w = x->w - 2;
+    out.c = cout;
+  }
+  PoolArgs pa{pooled, idx, nullptr, 0, 0, 0, c_off, y ? 1 : 0};
+  if (cat) {
+    if (!cat->ptr || !aligned16(cat->ptr) || (cat->sx % 8)) return UB_E_ALIGN;
+    if (cat->sy != (long long)cat->w * cat->sx || cat->sn != (long long)cat->h * cat->sy || cat->n != x->n) return UB_E_SHAPE;
+    pa.cat = cat->ptr;
+    pa.cat_H = cat->h;
+    pa.cat_W = cat->w;
+    pa.cat_C = (int)cat->sx;
+  }
+  return launch_igemm2(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, nullptr, &pa);
 }
 
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,

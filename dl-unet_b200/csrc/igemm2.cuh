@@ -15,6 +15,7 @@
 //   dgrad: taps read dy[y0 + r - 2, x0 + s - 2]  (base offset -2, TMA zero fill = the padding), weights
 //          pre-rotated by ub_pack_weight mode 1; optional fused ReLU-backward mask in the epilogue.
 #pragma once
+#include "elementwise.cuh"
 #include "epilogue.cuh"
 #include "ptx.cuh"
 
@@ -39,12 +40,18 @@ struct alignas(64) Igemm2Params {
   const float* head_b;     // [2]
   float* logits;           // [n][2][out_H][out_W] fp32 or nullptr
   uint8_t* argmax;         // [n][out_H][out_W] or nullptr (class 1 iff z1 > z0: ties -> 0, tester.py:30)
-  int store_out;           // 0 = do not store the bf16 activation (inference)
+  int store_out;           // 0 = do not store the bf16 activation (inference; or: only its pooled form is wanted)
+  // fused 2x2 max pool (POOL instantiation; network.py:133,139): the pooled tensor, the argmax codes and the skip
+  // copy into the decoder's concat buffer are produced from the staged tile, see pool_fwd_kernel for the rules
+  __nv_bfloat16* pool_y;   // dense [n][out_H/2][out_W/2][C]
+  uint8_t* pool_idx;       // same shape, 1 byte per element
+  __nv_bfloat16* pool_cat; // concat buffer view (dense in n, y, x) or nullptr
+  int pool_C, cat_H, cat_W, cat_C, c_off;
 };
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
 
-template <int BN, int MT, bool HEAD = false>
+template <int BN, int MT, bool HEAD = false, bool POOL = false>
 __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
   constexpr int P = 8 * MT + 2;          // patch width in pixels
   constexpr int B_BYTES = BN * 128;
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
-    if (!HEAD || p.store_out) tma_prefetch_desc(&p.o_map);
+    if ((!HEAD && !POOL) || p.store_out) tma_prefetch_desc(&p.o_map);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.n_a; ++i) {
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     const int by = row >> 3, bx = row & 7;
     const bool mask_on = p.mask != nullptr;
     constexpr bool head_on = HEAD && BN == 64;   // separate instantiation: the plain conv epilogue stays lean
-    const bool store_out = !head_on || p.store_out != 0;
+    const bool store_out = (!head_on && !POOL) || p.store_out != 0;
     if (head_on) {
       if (et < 128) shead[et] = __ldg(p.head_w + et);
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
           }
           float2 hp = make_float2(0.0f, 0.0f);
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    mcur_valid, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out);
+                    mcur_valid, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL);
           if (mask_on) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) mcur[i] = mnext[i];
@@ -339,6 +346,51 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
           if (et == 0 && store_out) {
             tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
             tma_store_commit();
+          }
+          if (POOL) {
+            // 2x2 max pool of the staged 8 x 16 pixel tile: thread = (pooled pixel, channel octet); the staging
+            // buffer is rewritten two chunks from now, i.e. after every reader has passed the next barrier
+            const int pp = et >> 3, c8 = et & 7;
+            const int py = pp >> 2, pxl = pp & 3;
+            const int oy = (y0 >> 1) + py, ox = (x0 >> 1) + pxl;
+            const int Ho = p.out_H >> 1, Wo = p.out_W >> 1;
+            if (oy < Ho && ox < Wo) {
+              const int r00 = (2 * py) * 8 + 2 * pxl;
+              float v[4][8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int r = r00 + (k >> 1) * 8 + (k & 1);
+                unpack8(*reinterpret_cast<const uint4*>(ebuf + r * 128 + ((c8 ^ (r & 7)) << 4)), v[k]);
+              }
+              float m[8];
+              uint32_t code[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                m[c] = v[0][c];
+                code[c] = 0;
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                  const float t = v[k][c];
+                  if (t > m[c] || t != t) {   // first maximum in window order, NaN wins (ATen)
+                    m[c] = t;
+                    code[c] = k;
+                  }
+                }
+              }
+              const uint4 o = pack8(m);
+              const int ch = n0 + j * 64 + c8 * 8;
+              const long long pix = ((long long)img * Ho + oy) * Wo + ox;
+              *reinterpret_cast<uint4*>(p.pool_y + pix * p.pool_C + ch) = o;
+              uint2 cc;
+              cc.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+              cc.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+              *reinterpret_cast<uint2*>(p.pool_idx + pix * p.pool_C + ch) = cc;
+              if (p.pool_cat != nullptr) {
+                const int cy = oy - p.c_off, cx = ox - p.c_off;
+                if (cy >= 0 && cy < p.cat_H && cx >= 0 && cx < p.cat_W)
+                  *reinterpret_cast<uint4*>(p.pool_cat + (((long long)img * p.cat_H + cy) * p.cat_W + cx) * p.cat_C + ch) = o;
+              }
+            }
           }
           if (head_on && h == 0 && px_valid) {
             // the other half's partial sums were written before the barrier; this buffer is rewritten two

@@ -77,6 +77,13 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
 int ub_conv3x3_fwd_head(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y,
                         const float* head_w, const float* head_b, float* logits_nchw, unsigned char* argmax,
                         void* stream);
+/* conv{1,2}2c + max_pool2d in one launch (network.py:132-133, 138-139): a 3x3 conv (<= 256 -> cout in {64, 128, 192,
+ * 256} channels, bias + ReLU) whose epilogue also pools every staged 8 x 16 pixel tile 2x2: `pooled` (dense
+ * [n,(h-2)/2,(w-2)/2,cout] bf16), `idx` (1 byte per pooled element) and the skip copy into `cat` follow
+ * ub_pool2x2_fwd's rules exactly.  y may be NULL: the full-resolution activation is then never written to HBM (the
+ * backward pass does not need it: its ReLU mask is pooled > 0 and the layer's wgrad reads the layer's INPUT). */
+int ub_conv3x3_fwd_pool(const ub_tensor4* x, const void* w_fwd, const float* bias, int cout, const ub_tensor4* y,
+                        void* pooled_bf16, unsigned char* idx, const ub_tensor4* cat, int c_off, void* stream);
 /* dx = full correlation of dy with the rotated weights; if relu_src != NULL the ReLU backward of the
  * layer that produced x is fused: dx *= (relu_src > 0).  (autograd of network.py:131-188) */
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,

@@ -137,6 +137,51 @@ def test_igemm3_three_taps_per_instruction(ops, shape):
         ops.set_option(3, 1)
 
 
+@pytest.mark.parametrize("case", [(2, 18, 18, 64, 64, 12), (1, 34, 26, 64, 128, 20), (1, 70, 70, 128, 128, 8), (2, 23, 31, 64, 64, 9),
+                                  (1, 12, 12, 256, 256, 4)])
+def test_conv3x3_fwd_fused_pool(ops, case):
+    """conv{l}2c + 2x2 max pool + argmax codes + skip copy in one launch == conv kernel followed by the pool kernel,
+    bit for bit (same activation bits, same tie / NaN rules, same crop_and_concat placement); odd output sizes pool in
+    floor mode; y = None never stores the full-resolution activation."""
+    n, h, w, cin, cout, hu = case
+    torch.manual_seed(sum(case))
+    x = nhwc(torch.randn(n, cin, h, w, device=DEV).clamp_min(0))
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device=DEV)
+    wp = ops.pack_weight(wt, ops.PACK_CONV_FWD)
+    ho, wo = h - 2, w - 2
+    hp, wq = ho // 2, wo // 2
+    coff = int((hp - hu) * 0.5)
+    # reference: the two separate kernels (each parity-tested on its own above)
+    y_ref = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=DEV)
+    ops.set_option(3, 0)                                                   # same conv kernel on both sides
+    try:
+        ops.conv3x3_fwd(x, wp, b, y_ref, relu=True)
+    finally:
+        ops.set_option(3, 1)
+    p_ref = torch.empty(n, hp, wq, cout, dtype=torch.bfloat16, device=DEV)
+    i_ref = torch.empty(n, hp, wq, cout, dtype=torch.uint8, device=DEV)
+    square = hp == wq
+    cat_ref = torch.zeros(n, hu, hu, 2 * cout, dtype=torch.bfloat16, device=DEV)
+    if square and ho % 2 == 0 and wo % 2 == 0:
+        ops.pool2x2_fwd(y_ref, p_ref, i_ref, cat_ref[..., :cout], coff)
+    else:                                                                  # the pool kernel wants even, dense input
+        yc = y_ref[:, :2 * hp, :2 * wq].contiguous()
+        ops.pool2x2_fwd(yc, p_ref, i_ref, None, 0)
+    for store in (True, False):
+        y = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV) if store else None
+        pooled = torch.full((n, hp, wq, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        idx = torch.full((n, hp, wq, cout), 9, dtype=torch.uint8, device=DEV)
+        cat = torch.zeros(n, hu, hu, 2 * cout, dtype=torch.bfloat16, device=DEV)
+        use_cat = square and ho % 2 == 0 and wo % 2 == 0
+        ops.conv3x3_fwd_pool(x, wp, b, cout, y, pooled, idx, cat[..., :cout] if use_cat else None, coff)
+        if store:
+            assert torch.equal(y, y_ref)
+        assert torch.equal(pooled, p_ref) and torch.equal(idx, i_ref)
+        if use_cat:
+            assert torch.equal(cat, cat_ref)
+
+
 def test_conv3x3_strided_views_write_in_place(ops):
     n, h, w, cin, cout = 2, 22, 22, 64, 128
     torch.manual_seed(1)
