@@ -31,6 +31,7 @@ namespace {
 int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 int g_igemm3_dbg = 0;
+int g_igemm_dbg = 0;
 int g_igemm3_mode = 1;   // igemm3.cuh (three taps per instruction) for 64 -> 64 channel convs: 0 off, 1 forward only
                         // (measured: fwd 6-10 % faster, dgrad 15 % slower than igemm2), 2 forward + dgrad + fused head  // 0: never use the haloed-patch conv kernel, 1: auto (wide shallow layers), 2: whenever legal
 int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
@@ -172,7 +173,9 @@ int launch_igemm_t(const IgemmParams& P, cudaStream_t st) {
   igemm_kernel<BN><<<grid, 384, C::SMEM_BYTES, st>>>(P);
   return (int)cudaGetLastError();
 }
-int launch_igemm(const IgemmParams& P, int BN, cudaStream_t st) {
+int launch_igemm(const IgemmParams& P0, int BN, cudaStream_t st) {
+  IgemmParams P = P0;
+  P.dbg = g_igemm_dbg;
   switch (BN) {
     case 64: return launch_igemm_t<64>(P, st);
     case 128: return launch_igemm_t<128>(P, st);
@@ -677,6 +680,7 @@ void ub_set_option(int key, int value) {
   if (key == 2) g_igemm2_mode = value;
   if (key == 3) g_igemm3_mode = value;
   if (key == 4) g_igemm3_dbg = value;
+  if (key == 5) g_igemm_dbg = value;
 }
 
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits) {

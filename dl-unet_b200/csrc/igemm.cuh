@@ -46,6 +46,7 @@ struct alignas(64) IgemmParams {
   long long mask_sn, mask_sy, mask_sx;  // element strides of the mask tensor (channel stride 1)
   int out_W, out_H;                     // valid output extent (for the mask read predicate)
   int omap_div;                         // column c -> o_map[c / omap_div], channel coord c % omap_div
+  int dbg;                              // experiment switch (ub_set_option 5): 1 = do not wait for earlier TMA stores
 };
 
 template <int BN>
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
         epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
                   mrow != nullptr, m4, ebuf, row, hw);
         fence_proxy_async_smem();
-        if (et == 0) tma_store_wait_read<0>();
+        if (et == 0 && !(p.dbg & 1)) tma_store_wait_read<0>();
         named_bar_sync(1, 256);
         if (et == 0) {
           const int col0 = n0 + j * 64;
