@@ -1137,15 +1137,18 @@ int ub_loss_fwd_bwd(int kind, const float* logits, const void* label, int label_
       (!dlogits || aligned16(dlogits))) {
     // no crop: every image plane is one linear run -> 8 pixels per thread, all loads issued up front
     long long lb = (total / 8 + 255) / 256;
-    if (lb > 4ll * num_sms()) lb = 4ll * num_sms();   // persistent: 4 CTAs per SM, grid-stride with prefetch
-    if (label_bytes == 1)
-      loss_linear_kernel<uint8_t><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(
-          logits, (const uint8_t*)label, weight, dlogits, loss_out, partials, counter, b, (unsigned int)(plane / 8), kind,
-          grad_scale);
-    else
-      loss_linear_kernel<long long><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(
-          logits, (const long long*)label, weight, dlogits, loss_out, partials, counter, b, (unsigned int)(plane / 8),
-          kind, grad_scale);
+    const long long per_sm = dlogits ? 3 : 4;                // persistent: 3-4 CTAs per SM, grid-stride with prefetch
+    if (lb > per_sm * num_sms()) lb = per_sm * num_sms();
+#define UB_LOSS_LINEAR(T, G)                                                                                        \
+  loss_linear_kernel<T, G><<<(int)lb, 256, 0, (cudaStream_t)stream>>>(logits, (const T*)label, weight, dlogits, loss_out, \
+                                                                      partials, counter, b, (unsigned int)(plane / 8), \
+                                                                      kind, grad_scale)
+    if (label_bytes == 1) {
+      if (dlogits) UB_LOSS_LINEAR(uint8_t, true); else UB_LOSS_LINEAR(uint8_t, false);
+    } else {
+      if (dlogits) UB_LOSS_LINEAR(long long, true); else UB_LOSS_LINEAR(long long, false);
+    }
+#undef UB_LOSS_LINEAR
     return (int)cudaGetLastError();
   }
   if (label_bytes == 1)

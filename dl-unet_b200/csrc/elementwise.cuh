@@ -646,8 +646,8 @@ __device__ __forceinline__ void loss_unit_load(LossUnit<LabelT>& q, unsigned int
 // Persistent grid (4 CTAs per SM), grid-stride over 8-pixel units with a one-unit register prefetch: the loads
 // of unit i+1 are in flight while the ~50 MUFU operations of unit i run, so the SFU time (6 MUFU per pixel for
 // the BCE form, ~12 us at config 5) hides under the HBM time instead of adding to it.
-template <typename LabelT>
-__global__ void __launch_bounds__(256, 4) loss_linear_kernel(const float* __restrict__ logits,
+template <typename LabelT, bool WANT_GRAD>
+__global__ void __launch_bounds__(256, WANT_GRAD ? 3 : 4) loss_linear_kernel(const float* __restrict__ logits,
                                                              const LabelT* __restrict__ label,
                                                              const float* __restrict__ weight,
                                                              float* __restrict__ dlogits, float* __restrict__ loss_out,
@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(256, 4) loss_linear_kernel(const float* __rest
   const unsigned int total_u = (unsigned int)B * plane8;
   const long long plane = (long long)plane8 * 8;
   const unsigned int stride = gridDim.x * blockDim.x;
+  constexpr bool want_grad = WANT_GRAD;
   float acc = 0.0f;
   unsigned int u = blockIdx.x * blockDim.x + threadIdx.x;
   LossUnit<LabelT> nx;
@@ -677,10 +678,12 @@ __global__ void __launch_bounds__(256, 4) loss_linear_kernel(const float* __rest
         const float l0 = fmaxf(z0[i], 0.0f) - y0 * z0[i] + __logf(1.0f + e0);
         const float l1 = fmaxf(z1[i], 0.0f) - y1 * z1[i] + __logf(1.0f + e1);
         acc += wv[i] * (l0 + l1);
-        const float r0 = __fdividef(1.0f, 1.0f + e0), r1 = __fdividef(1.0f, 1.0f + e1);
-        const float s0 = z0[i] >= 0.0f ? r0 : e0 * r0, s1 = z1[i] >= 0.0f ? r1 : e1 * r1;
-        g0[i] = wv[i] * (s0 - y0) * grad_scale;
-        g1[i] = wv[i] * (s1 - y1) * grad_scale;
+        if (want_grad) {   // forward-only calls (validation) skip the two reciprocals: 4 instead of 6 MUFU per pixel
+          const float r0 = __fdividef(1.0f, 1.0f + e0), r1 = __fdividef(1.0f, 1.0f + e1);
+          const float s0 = z0[i] >= 0.0f ? r0 : e0 * r0, s1 = z1[i] >= 0.0f ? r1 : e1 * r1;
+          g0[i] = wv[i] * (s0 - y0) * grad_scale;
+          g1[i] = wv[i] * (s1 - y1) * grad_scale;
+        }
       } else {
         // two classes: logsumexp(z) - z_l = softplus(z_other - z_l), softmax_1 = sigmoid(z1 - z0): 3 MUFU per pixel
         const float d = z1[i] - z0[i];
@@ -689,11 +692,13 @@ __global__ void __launch_bounds__(256, 4) loss_linear_kernel(const float* __rest
         const float p1 = d >= 0.0f ? r : e * r;               // softmax probability of class 1
         const float t = lab ? -d : d;                          // z_other - z_label
         acc += wv[i] * (fmaxf(t, 0.0f) + __logf(1.0f + e));
-        g1[i] = wv[i] * (p1 - (lab ? 1.0f : 0.0f)) * grad_scale;
-        g0[i] = -g1[i];
+        if (want_grad) {
+          g1[i] = wv[i] * (p1 - (lab ? 1.0f : 0.0f)) * grad_scale;
+          g0[i] = -g1[i];
+        }
       }
     }
-    if (dlogits != nullptr) {
+    if (WANT_GRAD) {
       const long long zoff = (long long)u * 8 + (long long)(u / plane8) * plane;
       float4* d0p = reinterpret_cast<float4*>(dlogits + zoff);
       float4* d1p = reinterpret_cast<float4*>(dlogits + zoff + plane);
