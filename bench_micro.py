@@ -79,6 +79,10 @@ def main():
         run(f"pool_bwd+skip_grad_sum {h}x{h}x{c}", nout * (2 + 2 + 1 + 2 + 8),
             [lambda i=i: ops.pool2x2_bwd(dy, dcat[..., :c], coff, idx, y, dxs[i]) for i in range(2)],
             "dy + dcat window + idx + pooled read, 4 positions written: 15 B per pooled element")
+        dbias = torch.zeros(c, device=dev)
+        run(f"pool_bwd+skip_grad_sum+bias_grad {h}x{h}x{c}", nout * (2 + 2 + 1 + 2 + 8),
+            [lambda i=i: ops.pool2x2_bwd(dy, dcat[..., :c], coff, idx, y, dxs[i], dbias) for i in range(2)],
+            "the variant the training step runs: also accumulates the bias gradient of the conv that fed the pool")
         del xs, dxs, cat, dcat
 
     # ---- conv11c, head, SGD
