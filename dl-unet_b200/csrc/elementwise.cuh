@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const __nv_bfloat16* __re
 // gradient (window of dcat at the crop_and_concat offset) -- and (b) the ReLU backward of
 // the conv that fed the pool (gradient passes only where the pooled value > 0).
 template <bool BIAS>
-__global__ void __launch_bounds__(256, BIAS ? 6 : 1) pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, BIAS ? 6 : 7) pool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ dcat,
                                                        const uint8_t* __restrict__ idx,
                                                        const __nv_bfloat16* __restrict__ pooled,
