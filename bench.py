@@ -247,26 +247,32 @@ def main():
     # input pipeline does), and the loss of every step is read back to the host.
     ke = max(1, min(K, 10))
     copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t) for t in (d_img, d_lab, d_w)) for _ in range(2)]   # double-buffered staging
+    consumed = [None, None]
 
-    def upload():
+    def upload(k):
+        dst = slots[k % 2]
         with torch.cuda.stream(copy_stream):
-            bufs = (h_img.to(dev, non_blocking=True), h_lab.to(dev, non_blocking=True), h_w.to(dev, non_blocking=True))
+            if consumed[k % 2] is not None:
+                copy_stream.wait_event(consumed[k % 2])            # the step that read this slot has finished
+            for d, h in zip(dst, (h_img, h_lab, h_w)):
+                d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return bufs, ev
+        return dst, ev
 
     step(d_img, d_lab, d_w)
     barrier()
     t0 = time.perf_counter()
-    nxt = upload()
+    nxt = upload(0)
     for i in range(ke):
         (b_img, b_lab, b_w), ev = nxt
         torch.cuda.current_stream().wait_event(ev)
-        for t in (b_img, b_lab, b_w):
-            t.record_stream(torch.cuda.current_stream())
         if i + 1 < ke:
-            nxt = upload()
+            nxt = upload(i + 1)
         l = step(b_img, b_lab, b_w)
+        consumed[i % 2] = torch.cuda.Event()
+        consumed[i % 2].record(torch.cuda.current_stream())
         l.item()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
