@@ -8,8 +8,9 @@ One "step" = forward + weighted BCE loss + backward (+ gradient all-reduce at N 
 update over one batch of synthetic 572x572 tiles:
   * N = 1: BASELINE config 2 -- batch 16, bf16 operands / fp32 accumulate, on 1 x B200;
   * N > 1: BASELINE config 3 -- global batch 128 split evenly (64 / 32 / 16 tiles per GPU at 2/4/8).
-`value` is device-resident throughput (inputs already in HBM), `e2e` goes through the public API
-(network.Unet / b200.train) with pinned HOST buffers copied in and the loss read back every step.
+The step is b200.train.TrainStep, the call dl-unet_b200/trainer.py makes per batch (CUDA-graph replay at N = 1).
+`value` is device-resident throughput (inputs already in HBM), `e2e` runs the same call with pinned HOST buffers
+uploaded every step (copy stream, double-buffered) and the loss read back every step.
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
 """
 import argparse
