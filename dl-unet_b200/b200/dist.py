@@ -75,5 +75,9 @@ class GradAllReducer:
         self._flush(self.engine.store.total)
         for w in self.works:
             w.wait()  # the compute stream waits for the reduced buckets
+        if self.comm_stream is not None:
+            # rejoin the side stream (a no-op for ordering -- the waits above cover it -- but a CUDA-graph capture of
+            # the step requires every forked stream to join back)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
         self.works = []
         self.start = 0

@@ -112,7 +112,12 @@ class TrainStep:
 
     The graph is keyed on the input shapes and on (lr, momentum): a ReduceLROnPlateau change re-captures."""
 
-    def __init__(self, unet, optimizer, kind="bce", graph=True, global_batch=None):
+    def __init__(self, unet, optimizer, kind="bce", graph=True, global_batch=None, graph_with_allreduce=False):
+        """graph_with_allreduce: also capture when a GradAllReducer is attached (the NCCL all-reduces of the gradient
+        buckets and their side stream become part of the graph).  Experimental and off: measured on 2 x B200 it is no
+        faster than the eager schedule at 64 tiles per GPU (2076 vs 2113 tiles/s) and the process group then hangs at
+        shutdown."""
+        self.graph_with_allreduce = graph_with_allreduce
         self.unet, self.opt = unet, optimizer
         self.kind = ops.LOSS_BCE if kind == "bce" else ops.LOSS_SOFTMAX_CE
         self.use_graph = graph
@@ -153,7 +158,8 @@ class TrainStep:
             labels = labels.to(torch.int64)
         labels, weight = labels.contiguous(), weight.contiguous().float()
         st = self.unet.engine.store
-        if not self.use_graph or st.p_arena is None or st.first_step or self.unet.engine.grad_ready_hook is not None:
+        hooked = self.unet.engine.grad_ready_hook is not None and not self.graph_with_allreduce
+        if not self.use_graph or st.p_arena is None or st.first_step or hooked:
             out = torch.zeros(1, device=images.device)
             self._eager(images, labels, weight, out, self.__dict__.setdefault("_dl", {}))
             return out[0]
@@ -187,7 +193,8 @@ class TrainStep:
         st.m_arena.copy_(m0)
         st.dirty = True
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread_local: NCCL's watchdog thread may query events while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self._eager(img, lab, w, loss, dl)
         # the capture itself executed nothing; parameters are still p0
         # everything the captured kernels address by raw pointer must outlive the graph: the dlogits buffer in `dl`
