@@ -31,6 +31,7 @@ SIGNATURES = {
     "ub_error_string": (C.c_char_p, [_i]),
     "ub_device_error": (_i, [C.POINTER(C.c_uint)]),
     "ub_set_tuning": (None, [_i, _i, _i, _i]),
+    "ub_set_prof_buffer": (None, [_P]),
     "ub_set_option": (None, [_i, _i]),
     "ub_pack_weight": (_i, [_P, _P, _i, _i, _i, _P]),
     "ub_unpack_grad": (_i, [_P, _P, _i, _i, _i, _i, _P]),

@@ -30,6 +30,8 @@ namespace {
 
 int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
+unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
+int g_mask_l2_prefetch = 1;
 int g_igemm3_dbg = 0;
 int g_igemm_dbg = 0;
 int g_igemm3_mode = 1;   // igemm3.cuh (three taps per instruction) for 64 -> 64 channel convs: 0 off, 1 forward only
@@ -288,13 +290,16 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   Igemm2Params P;
   memset(&P, 0, sizeof(P));
   P.store_out = 1;
+  P.prof = g_prof_buffer;
+  P.l2_prefetch = g_mask_l2_prefetch;
   const int head_smem = head ? 3072 : 0;   // head weights + two buffers of per-row partial sums
+  const int mask_smem = relu_src ? 2 * 16384 : 0;   // two slots for the ReLU-mask tiles (dgrad)
   const int K = in->c, N = out->c;
   const int BN = (N % 128 == 0) ? 128 : 64;
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
   const int b_slot = BN * 128;
-  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem;
+  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem - mask_smem;
   const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
   const int nb_stat = 9 * P.kchunks;
   P.stationary = (P.n_tiles_n == 1 && nb_stat <= IG2_MAX_B && nb_stat * b_slot + 2 * a_slot1 <= limit) ? 1 : 0;
@@ -353,7 +358,8 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
     P.store_out = pool->store_out;
   }
   if (P.store_out && (e = make_map4(&P.o_map, out, 8, 16))) return e;
-  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem;
+  P.aux_bytes = 2048 + head_smem;
+  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem + mask_smem;
   if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
   if (pool) {
     if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1, false, true>(P, smem_bytes, st);
@@ -681,7 +687,10 @@ void ub_set_option(int key, int value) {
   if (key == 3) g_igemm3_mode = value;
   if (key == 4) g_igemm3_dbg = value;
   if (key == 5) g_igemm_dbg = value;
+  if (key == 6) g_mask_l2_prefetch = value;
 }
+
+void ub_set_prof_buffer(void* dev_ptr) { g_prof_buffer = reinterpret_cast<unsigned long long*>(dev_ptr); }
 
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits) {
   g_force_bn = force_bn;

@@ -47,6 +47,9 @@ struct alignas(64) Igemm2Params {
   uint8_t* pool_idx;       // same shape, 1 byte per element
   __nv_bfloat16* pool_cat; // concat buffer view (dense in n, y, x) or nullptr
   int pool_C, cat_H, cat_W, cat_C, c_off;
+  int l2_prefetch;            // (unused since the mask tiles travel through shared memory)
+  int aux_bytes;              // bytes between the staging buffers and the mask tile buffers (2048, or 5120 with a head)
+  unsigned long long* prof;   // experiment (ub_set_prof_buffer): per-CTA clock sums of the epilogue phases of thread 128
 };
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
@@ -72,6 +75,9 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   float* sbias = reinterpret_cast<float*>(epi + 2 * 16384 + 1024);
   float* shead = reinterpret_cast<float*>(epi + 2 * 16384 + 2048);       // [2][64] weights + [2] bias (head only)
   float2* hpart = reinterpret_cast<float2*>(epi + 2 * 16384 + 2048 + 1024);  // [2 buffers][128 rows]
+  uint64_t* m_full = reinterpret_cast<uint64_t*>(epi + 2 * 16384 + 640);     // ReLU-mask tiles (dgrad): 2 slots (after the 612 B above)
+  uint64_t* m_empty = m_full + 2;
+  uint8_t* mbuf = epi + 2 * 16384 + p.aux_bytes;                              // 2 x 16 KB, 1024-aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +99,8 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 256);
+      mbar_init(&m_full[i], 1);
+      mbar_init(&m_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -122,15 +130,6 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
       const int x0 = tx * 8 * MT + p.base_off, y0 = ty * 16 + p.base_off, n0 = nt * BN;
-      if (p.mask != nullptr) {
-        // the epilogue reads the ReLU-mask rows of this tile a few microseconds from now: pull them into L2
-        if (elect_one()) {
-          for (int sub = 0; sub < MT; ++sub)
-            for (int j = 0; j < BN / 64; ++j)
-              tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, (tx * MT + sub) * 8, ty * 16, img);
-        }
-        __syncwarp();
-      }
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&a_empty[as], aph ^ 1, 20);
         if (elect_one()) {
@@ -250,6 +249,69 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       }
       resident = true;
     }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ ReLU-mask tile loader (dgrad)
+    // The mask of a chunk (the 8 x 16 pixel x 64 channel tile of the layer's input activation) comes through TMA
+    // into one of two 16 KB slots, two chunks ahead of its use: per-thread global loads of 64 B at a 128 B stride
+    // cost the epilogue ~2200 cycles per chunk (32 sectors per request, L2 latency on the critical path).
+    if (p.mask != nullptr) {
+      uint32_t c = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles_n;
+        int mt = t / p.n_tiles_n;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        for (int sub = 0; sub < MT; ++sub) {
+          for (int j = 0; j < BN / 64; ++j, ++c) {
+            const uint32_t sl = c & 1;
+            mbar_wait(&m_empty[sl], ((c >> 1) & 1) ^ 1, 26);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&m_full[sl], 16384u);
+              tma_load_4d(mbuf + sl * 16384, &p.m_map, &m_full[sl], nt * BN + j * 64, (tx * MT + sub) * 8, ty * 16, img);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == 3 && !HEAD && !POOL) {
+    // ------------------------------------------------------------------ TMA store warp (plain convs)
+    // Issuing a TMA store blocks the issuing thread for ~600 cycles and an epilogue warp that has to do it holds
+    // up the chunk barrier of all eight (measured with the clock probes below: 2400 cycles per chunk against
+    // ~800 of actual epilogue work).  Here the epilogue warps only ARRIVE on FULL[b] when staging buffer b is
+    // written and go on with the next chunk; this warp waits for FULL[b], issues the store, and arrives on
+    // EMPTY[b'] once the store that read buffer b' has finished with it.  Named barriers 2,3 = FULL, 4,5 = EMPTY.
+    uint32_t c = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles_n;
+      int mt = t / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      for (int sub = 0; sub < MT; ++sub) {
+        for (int j = 0; j < BN / 64; ++j, ++c) {
+          const uint32_t b = c & 1;
+          named_bar_sync(2 + b, 288);
+          // hand the OTHER buffer back first (its store was issued a whole chunk ago and has long read it): the
+          // ~600-cycle issue of this chunk's store must not sit between the epilogue and its next buffer
+          if (c >= 1) {
+            if (elect_one()) tma_store_wait_read<0>();
+            __syncwarp();
+            named_bar_arrive(4 + ((c - 1) & 1), 288);
+          }
+          if (elect_one()) {
+            tma_store_4d(&p.o_map, epi + b * 16384, nt * BN + j * 64, (tx * MT + sub) * 8, ty * 16, img);
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------ epilogue
     // 8 warps: warp w reads TMEM lanes 32*(w%4).. and owns the 32-column half h = (w-4)/4 of every chunk
@@ -266,29 +328,10 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
       named_bar_sync(1, 256);
     }
-    // ReLU-backward mask rows are requested ONE CHUNK AHEAD (the next sub-tile / column chunk, or the first chunk of
-    // this CTA's next tile): an L2 hit costs ~1000 cycles under load, about the whole tensor time of a K = 64 tile.
-    auto mask_row = [&](int tt, int sub, int j) -> const __nv_bfloat16* {
-      const int nt = tt % p.n_tiles_n;
-      int mt = tt / p.n_tiles_n;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
-      const int xx = (tx * MT + sub) * 8 + bx, yy = ty * 16 + by;
-      if (xx >= p.out_W || yy >= p.out_H) return nullptr;
-      return p.mask + (long long)img * p.mask_sn + (long long)yy * p.mask_sy + (long long)xx * p.mask_sx + nt * BN + j * 64 +
-             h * 32;
-    };
-    uint4 mcur[4];
-    bool mcur_valid = false;
-    if (mask_on && (int)blockIdx.x < total_tiles) {
-      const __nv_bfloat16* mp = mask_row(blockIdx.x, 0, 0);
-      mcur_valid = mp != nullptr;
-      if (mcur_valid) load_mask(mp, mcur);
-    }
     int it = 0;
     uint32_t chunk_ctr = 0;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = (p.prof && et == 0) ? clock64() : 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles_n;
       int mt = t / p.n_tiles_n;
@@ -303,8 +346,10 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         if (et < BN) sbias[et] = __ldg(p.bias + n0 + et);
         named_bar_sync(1, 256);
       }
+      const long long c0 = (p.prof && et == 0) ? clock64() : 0;
       mbar_wait(&tfull[acc], acc_phase, 25);
       tc_fence_after();
+      if (p.prof && et == 0) prof_acc[0] += clock64() - c0;
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
         const int x0 = (tx * MT + sub) * 8;
@@ -312,40 +357,49 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
 #pragma unroll 1
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
-          // two staging buffers, one barrier per chunk (see igemm.cuh)
+          // two staging buffers; plain convs hand them to the store warp (FULL / EMPTY named barriers), the fused
+          // head / pool variants keep one barrier per chunk among the epilogue warps (see igemm.cuh)
+          constexpr bool async_store = !HEAD && !POOL;
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-          uint4 mnext[4];
-          bool mnext_valid = false;
-          if (mask_on) {
-            int nt_t = t, nsub = sub, nj = j + 1;
-            if (nj == BN / 64) {
-              nj = 0;
-              if (++nsub == MT) {
-                nsub = 0;
-                nt_t = t + gridDim.x;
-              }
-            }
-            if (nt_t < total_tiles) {
-              const __nv_bfloat16* mp = mask_row(nt_t, nsub, nj);
-              mnext_valid = mp != nullptr;
-              if (mnext_valid) load_mask(mp, mnext);
-            }
+          if (async_store && chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 288);   // EMPTY[b]
+          uint4 mcur[4];
+          if (mask_on) {   // this chunk's mask tile: same rows / swizzle as the staging buffer
+            const uint32_t sl = chunk_ctr & 1;
+            mbar_wait(&m_full[sl], (chunk_ctr >> 1) & 1, 27);
+            const uint8_t* mrow = mbuf + sl * 16384 + row * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mcur[i] = *reinterpret_cast<const uint4*>(mrow + (((h * 4 + i) ^ (row & 7)) << 4));
+            mbar_arrive(&m_empty[sl]);
           }
           float2 hp = make_float2(0.0f, 0.0f);
+          const long long c1 = (p.prof && et == 0) ? clock64() : 0;
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    mcur_valid, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL);
-          if (mask_on) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mcur[i] = mnext[i];
-            mcur_valid = mnext_valid;
-          }
+                    true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL);
+          const long long c2 = (p.prof && et == 0) ? clock64() : 0;
           if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
-          if (et == 0 && store_out) tma_store_wait_read<0>();
-          named_bar_sync(1, 256);
-          if (et == 0 && store_out) {
-            tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
-            tma_store_commit();
+          if (async_store) {
+            named_bar_arrive(2 + (chunk_ctr & 1), 288);   // FULL[b]: the store warp takes it from here
+            if (p.prof && et == 0) {
+              prof_acc[1] += c2 - c1;          // TMEM load + arithmetic + staging
+              prof_acc[5] += 1;
+            }
+          } else {
+            if (et == 0 && store_out) tma_store_wait_read<0>();
+            const long long c3 = (p.prof && et == 0) ? clock64() : 0;
+            named_bar_sync(1, 256);
+            const long long c4 = (p.prof && et == 0) ? clock64() : 0;
+            if (et == 0 && store_out) {
+              tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
+              tma_store_commit();
+            }
+            if (p.prof && et == 0) {
+              prof_acc[1] += c2 - c1;          // TMEM load + arithmetic + staging
+              prof_acc[2] += c3 - c2;          // fence + wait for the previous TMA store's smem reads
+              prof_acc[3] += c4 - c3;          // chunk barrier (skew between the 8 epilogue warps)
+              prof_acc[4] += clock64() - c4;   // TMA store issue
+              prof_acc[5] += 1;
+            }
           }
           if (POOL) {
             // 2x2 max pool of the staged 8 x 16 pixel tile: thread = (pooled pixel, channel octet); the staging
@@ -410,7 +464,11 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (et == 0 && (HEAD || POOL)) tma_store_wait_all<0>();
+    if (p.prof && et == 0) {
+      for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 8 + i] = (unsigned long long)prof_acc[i];
+      p.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - prof_t0);
+    }
   }
 
   tc_fence_before();

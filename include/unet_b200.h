@@ -43,6 +43,9 @@ const char* ub_error_string(int code);
 /* Non-zero after a kernel aborted on a pipeline dead-lock guard; host memory out-param. Synchronises. */
 int ub_device_error(unsigned int* out_code);
 /* Tuning overrides for experiments: <=0 restores the heuristic. */
+/* experiment: device buffer of 148 x 8 uint64 that igemm2 launches fill with the clock sums of their epilogue phases
+ * (wait for the MMAs, TMEM load + arithmetic + staging, store wait, chunk barrier, store issue, chunks, total); NULL = off */
+void ub_set_prof_buffer(void* dev_ptr);
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
 /* Experiment switches.  key 1: 3x3 wgrad kernel (0 = tap-per-CTA, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto [default], 4 = tap-row-per-CTA N=192, 5 = shifted-dY kernel for 64 output channels).
  * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default], 2 = wherever legal). */

@@ -38,3 +38,22 @@ if "--sweep" in sys.argv:
         ops.set_option(4, dbg)
         print(f"dbg={dbg}: fwd {timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y)):.1f} us  dgrad {timeit(lambda: ops.conv3x3_dgrad(dy, wf, dx, x)):.1f} us", flush=True)
     ops.set_option(4, 0)
+
+if "--phases" in sys.argv:
+    # epilogue phase clocks of the haloed-patch kernel (thread 128 of every CTA), forward and dgrad
+    from b200 import lib
+    ops.set_option(3, 0)
+    buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    for name, fn in (("fwd", lambda: ops.conv3x3_fwd(x, wf, bias, y)), ("dgrad", lambda: ops.conv3x3_dgrad(dy, wf, dx, x)),
+                     ("dgrad, no mask", lambda: ops.conv3x3_dgrad(dy, wf, dx, None)),
+                     ("dgrad, no L2 prefetch of the mask", lambda: (ops.set_option(6, 0), ops.conv3x3_dgrad(dy, wf, dx, x), ops.set_option(6, 1)))):
+        buf.zero_()
+        lib.load().ub_set_prof_buffer(buf.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        lib.load().ub_set_prof_buffer(None)
+        m = buf.view(148, 8).double().mean(0).tolist()
+        n = max(m[5], 1.0)
+        print(f"{name}: chunks/CTA {m[5]:.0f}  total {m[6] / n:.0f} clk/chunk = wait MMA {m[0] / n:.0f} + tmem+math+stage {m[1] / n:.0f} "
+              f"+ fence/store-wait {m[2] / n:.0f} + barrier {m[3] / n:.0f} + store issue {m[4] / n:.0f} + rest "
+              f"{(m[6] - sum(m[:5])) / n:.0f}", flush=True)
