@@ -191,6 +191,39 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
         }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------- TMA store warp (see igemm2.cuh for the measurements)
+    // The epilogue warps ARRIVE on FULL[b] when staging buffer b is written and carry on; this warp waits for FULL[b],
+    // hands the other buffer back (EMPTY) once its store has read it, and issues the store (~600 cycles of issue
+    // that used to sit in an epilogue warp in front of the chunk barrier).  Named barriers 2,3 = FULL, 4,5 = EMPTY.
+    uint32_t c = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles_n;
+      int mt = t / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+      for (int j = 0; j < BN / 64; ++j, ++c) {
+        const uint32_t b = c & 1;
+        named_bar_sync(2 + b, 288);
+        if (c >= 1) {
+          if (elect_one()) tma_store_wait_read<0>();
+          __syncwarp();
+          named_bar_arrive(4 + ((c - 1) & 1), 288);
+        }
+        if (elect_one()) {
+          const int col0 = n0 + j * 64;
+          const int mi = col0 / p.omap_div;
+          tma_store_4d(&p.o_map[mi], epi + b * 16384, col0 - mi * p.omap_div, x0, y0, img);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tma_store_wait_all<0>();
+    __syncwarp();
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue
     // 8 warps: warp w may read TMEM lanes 32*(w%4).. and owns the 32-column half hw = (w-4)/4 of every chunk
@@ -215,6 +248,7 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
       const uint32_t acc_phase = (it >> 1) & 1;
       if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
         // per-tile bias slice -> smem (every read of the previous slice happened before the last chunk barrier)
+        if (it > 0) named_bar_sync(1, 256);   // every warp has finished reading the previous tile's slice
         if (et < BN) sbias[et] = __ldg(p.bias + (n0 + et) % p.bias_mod);
         named_bar_sync(1, 256);
       }
@@ -228,30 +262,22 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
                n0 + hw * 32;
 #pragma unroll 1
       for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
-        // Two staging buffers, ONE barrier per chunk: before the barrier thread 0 waits until every earlier
-        // TMA store has finished reading smem, so after it the other buffer is free for the next chunk.
+        // Two staging buffers handed to the store warp: wait until the store that last read this one is done with
+        // it (EMPTY), write it, make the writes visible to the async proxy, arrive on FULL.
         uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+        if (chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 288);
         uint4 m4[4];
         // the mask row is requested first: its latency overlaps the TMEM load
         if (mrow != nullptr) load_mask(mrow + j * 64, m4);
         epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
                   mrow != nullptr, m4, ebuf, row, hw);
         fence_proxy_async_smem();
-        if (et == 0 && !(p.dbg & 1)) tma_store_wait_read<0>();
-        named_bar_sync(1, 256);
-        if (et == 0) {
-          const int col0 = n0 + j * 64;
-          const int mi = col0 / p.omap_div;
-          const int cc = col0 - mi * p.omap_div;
-          tma_store_4d(&p.o_map[mi], ebuf, cc, x0, y0, img);
-          tma_store_commit();
-        }
+        named_bar_arrive(2 + (chunk_ctr & 1), 288);
       }
       // all of this thread's TMEM reads of accumulator `acc` are complete
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
     }
-    if (et == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
+        if (it > 0) named_bar_sync(1, 256);   // every warp has finished reading the previous tile's slice
         if (et < BN) sbias[et] = __ldg(p.bias + n0 + et);
         named_bar_sync(1, 256);
       }

@@ -57,3 +57,27 @@ if "--phases" in sys.argv:
         print(f"{name}: chunks/CTA {m[5]:.0f}  total {m[6] / n:.0f} clk/chunk = wait MMA {m[0] / n:.0f} + tmem+math+stage {m[1] / n:.0f} "
               f"+ fence/store-wait {m[2] / n:.0f} + barrier {m[3] / n:.0f} + store issue {m[4] / n:.0f} + rest "
               f"{(m[6] - sum(m[:5])) / n:.0f}", flush=True)
+if "--c128" in sys.argv:
+    # conv21c dgrad shape: 128 -> 64 channels on a 282 -> 284 map (stationary weights, two k-chunks, two patch slots)
+    from b200 import lib
+    dy2 = torch.randn(B, 282, 282, 128, device=dev).to(torch.bfloat16)
+    dx2 = torch.empty(B, 284, 284, 64, dtype=torch.bfloat16, device=dev)
+    wd2 = torch.randn(64, 9 * 128, device=dev).to(torch.bfloat16) / 30
+    buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    fn = lambda: ops.conv3x3_dgrad(dy2, wd2, dx2, None)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"128->64 dgrad 284: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us")
+    lib.load().ub_set_prof_buffer(buf.data_ptr())
+    fn()
+    torch.cuda.synchronize()
+    lib.load().ub_set_prof_buffer(None)
+    m = buf.view(148, 8).double().mean(0).tolist()
+    n = max(m[5], 1.0)
+    print(f"chunks/CTA {m[5]:.0f}  total {m[6] / n:.0f} clk/chunk = wait MMA {m[0] / n:.0f} + tmem+math+stage {m[1] / n:.0f} + rest {(m[6] - m[0] - m[1]) / n:.0f}")
