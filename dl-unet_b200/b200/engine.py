@@ -267,9 +267,11 @@ class Engine:
             e = st.g_off[lname + ".bias"] + _align(st.numel[lname + ".bias"])
             self.grad_ready_hook(s, e)
 
-    def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False):
+    def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False, dx_bias=None, dx_bias_c0=0):
         """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer.  bias_done: the kernel that
-        produced dy (pool / head backward) already accumulated its column sums into the bias gradient."""
+        produced dy (pool / head backward, or the dgrad of the layer after this one) already accumulated its column
+        sums into the bias gradient.  dx_bias: name of the parameter that receives the column sums of dx (channels
+        >= dx_bias_c0) -- the bias gradient of the layer that produced x, fused into this layer's dgrad."""
         st = self.store
         dwp = st.dwp(lname)
         ops.conv3x3_wgrad(x, dy, dwp)
@@ -279,7 +281,7 @@ class Engine:
             ops.colsum(dy, st.g(lname + ".bias"))
         self._ready(lname)
         if dx is not None:
-            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src)
+            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src, st.g(dx_bias) if dx_bias else None, dx_bias_c0)
 
     def backward(self, ws, dlogits):
         """dlogits: fp32 [B,2,So,So] (d loss / d logits).  Fills the gradient arena; if every
@@ -301,8 +303,11 @@ class Engine:
         dy = gr["d12"]
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
-            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=(l == 1))
-            self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None)
+            # each dgrad also accumulates the bias gradient of the layer whose output gradient it produces
+            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=(l == 1),
+                           dx_bias=f"conv{l}1e.bias")
+            self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None, bias_done=True,
+                           dx_bias=f"upconv{l}.bias", dx_bias_c0=C)
             # up-convolution: its output is the upper channel half of the concat buffer
             up_name = f"upconv{l}"
             src = a[f"d{l + 1}2"] if l < 4 else a["e52"]
@@ -312,13 +317,12 @@ class Engine:
             ops.upconv2x2_wgrad(src, dyu, dwp)
             if self.grad_ready_hook is not None:
                 ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
-            ops.colsum(dyu, st.g(up_name + ".bias"))
-            self._ready(up_name)
+            self._ready(up_name)                     # its bias gradient came with conv{l}1e's dgrad
             ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
             dy = dsrc
         # bottleneck
-        self._conv_bwd("conv52c", a["e51"], gr["e52"], gr["e51"], a["e51"])
-        self._conv_bwd("conv51c", a["p4"], gr["e51"], gr["p4"], None)
+        self._conv_bwd("conv52c", a["e51"], gr["e52"], gr["e51"], a["e51"], dx_bias="conv51c.bias")
+        self._conv_bwd("conv51c", a["p4"], gr["e51"], gr["p4"], None, bias_done=True)
         for l in (4, 3, 2, 1):
             C = LEVEL_C[l]
             H = g.enc2[l]
@@ -326,9 +330,10 @@ class Engine:
                 gr[f"e{l}2"].zero_()  # floor-mode pool: the last row / column gets no gradient
             ops.pool2x2_bwd(gr[f"p{l}"], gr[f"cat{l}"][..., :C], g.coff[l], a[f"i{l}"], a[f"p{l}"], gr[f"e{l}2"],
                             st.g(f"conv{l}2c.bias"))
-            self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"], bias_done=True)
+            self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"], bias_done=True,
+                           dx_bias=f"conv{l}1c.bias" if l > 1 else None)     # conv11c: conv1_wgrad sums its own bias
             if l > 1:
-                self._conv_bwd(f"conv{l}1c", a[f"p{l - 1}"], gr[f"e{l}1"], gr[f"p{l - 1}"], None)
+                self._conv_bwd(f"conv{l}1c", a[f"p{l - 1}"], gr[f"e{l}1"], gr[f"p{l - 1}"], None, bias_done=True)
             else:
                 ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
                 self._ready("conv11c")

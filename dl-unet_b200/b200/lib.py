@@ -44,6 +44,7 @@ SIGNATURES = {
     "ub_conv3x3_fwd_head": (_i, [_T4, _P, _P, _T4, _P, _P, _P, _P, _P]),
     "ub_conv3x3_fwd_pool": (_i, [_T4, _P, _P, _i, _T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
+    "ub_conv3x3_dgrad_bias": (_i, [_T4, _P, _T4, _T4, _P, _i, _P]),
     "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_upconv2x2_fwd": (_i, [_T4, _P, _P, _T4, _P]),
     "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),

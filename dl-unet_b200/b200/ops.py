@@ -189,11 +189,17 @@ def conv3x3_fwd_pool(x, w_fwd, bias, cout, y, pooled, idx, cat=None, c_off=0):
                                              _t4p(cat), int(c_off), _stream()), "conv3x3_fwd_pool")
 
 
-def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None):
+def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_c0=0):
+    """dbias (fp32 [C - c0], zeroed by the caller): also receives the column sums of dx over the channels >= c0 -- the
+    bias gradient of the layer that produced this layer's input (fused into the epilogue where supported)."""
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, co = dy.shape
     with _timed("igemm", 2.0 * n * h * w * co * 9 * dx.shape[3]):
-        _chk(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
+        if dbias is None:
+            _chk(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
+        else:
+            _chk(_lib.load().ub_conv3x3_dgrad_bias(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _ptr(dbias), int(dbias_c0),
+                                                   _stream()), "conv3x3_dgrad_bias")
     return dx
 
 

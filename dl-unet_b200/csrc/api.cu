@@ -286,7 +286,7 @@ struct PoolArgs {
 
 int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const ub_tensor4* out, int relu,
                   const ub_tensor4* relu_src, int base_off, cudaStream_t st, const HeadArgs* head = nullptr,
-                  const PoolArgs* pool = nullptr) {
+                  const PoolArgs* pool = nullptr, float* dbias = nullptr, int dbias_c0 = 0) {
   Igemm2Params P;
   memset(&P, 0, sizeof(P));
   P.store_out = 1;
@@ -294,12 +294,13 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   P.l2_prefetch = g_mask_l2_prefetch;
   const int head_smem = head ? 3072 : 0;   // head weights + two buffers of per-row partial sums
   const int mask_smem = relu_src ? 2 * 16384 : 0;   // two slots for the ReLU-mask tiles (dgrad)
+  const int col_smem = dbias ? 1024 : 0;             // column-sum accumulators (fused bias gradient)
   const int K = in->c, N = out->c;
   const int BN = (N % 128 == 0) ? 128 : 64;
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
   const int b_slot = BN * 128;
-  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem - mask_smem;
+  const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem - mask_smem - col_smem;
   const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
   const int nb_stat = 9 * P.kchunks;
   P.stationary = (P.n_tiles_n == 1 && nb_stat <= IG2_MAX_B && nb_stat * b_slot + 2 * a_slot1 <= limit) ? 1 : 0;
@@ -358,8 +359,10 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
     P.store_out = pool->store_out;
   }
   if (P.store_out && (e = make_map4(&P.o_map, out, 8, 16))) return e;
-  P.aux_bytes = 2048 + head_smem;
-  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem + mask_smem;
+  P.aux_bytes = 2048 + head_smem + col_smem;
+  P.dbias = dbias;
+  P.dbias_c0 = dbias_c0;
+  const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem + mask_smem + col_smem;
   if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
   if (pool) {
     if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1, false, true>(P, smem_bytes, st);
@@ -840,14 +843,18 @@ int ub_conv3x3_fwd_pool(const ub_tensor4* x, const void* w_fwd, const float* bia
   return launch_igemm2(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, nullptr, &pa);
 }
 
-int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
-                     void* stream) {
+static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                             void* stream, float* dbias, int dbias_c0, bool* fused) {
   int e;
+  *fused = false;
   if ((e = check_view(dy)) || (e = check_view(dx))) return e;
   if (!w_dgrad || !aligned16(w_dgrad)) return w_dgrad ? UB_E_ALIGN : UB_E_ARG;
   if (dx->n != dy->n || dx->h != dy->h + 2 || dx->w != dy->w + 2) return UB_E_SHAPE;
   if (igemm3_eligible(dy, dx, false)) return launch_igemm3(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream);
-  if (igemm2_eligible(dy, dx)) return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream);
+  if (igemm2_eligible(dy, dx)) {
+    *fused = dbias != nullptr;
+    return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream, nullptr, nullptr, dbias, dbias_c0);
+  }
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
@@ -870,6 +877,26 @@ int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4
   P.omap_div = 1 << 30;
   if ((e = set_mask(P, relu_src, dx))) return e;
   return launch_igemm(P, BN, (cudaStream_t)stream);
+}
+
+int ub_colsum(const void* g, float* out, long long n_pix, int c, long long ld, void* stream);
+
+int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                     void* stream) {
+  bool fused;
+  return conv3x3_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, nullptr, 0, &fused);
+}
+
+int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                          float* dbias, int dbias_c0, void* stream) {
+  if (!dbias || dbias_c0 < 0 || (dbias_c0 % 8)) return UB_E_ARG;
+  bool fused;
+  int e = conv3x3_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, dbias, dbias_c0, &fused);
+  if (e || fused) return e;
+  // the kernel chosen for this shape has no fused column sums: one pass over the channels [c0, C) of dx
+  if (dx->c <= dbias_c0 || dx->sy != (long long)dx->w * dx->sx || dx->sn != (long long)dx->h * dx->sy) return UB_E_SHAPE;
+  return ub_colsum(reinterpret_cast<const __nv_bfloat16*>(dx->ptr) + dbias_c0, dbias, (long long)dx->n * dx->h * dx->w,
+                   dx->c - dbias_c0, dx->sx, stream);
 }
 
 int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream) {

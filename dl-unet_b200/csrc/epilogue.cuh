@@ -22,7 +22,7 @@ __device__ __forceinline__ void load_mask(const __nv_bfloat16* mcols, uint4 (&m4
 __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, int relu, bool mask_on, bool mask_valid,
                                            const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                            const float* shead = nullptr, float2* head_part = nullptr,
-                                           bool stage = true) {
+                                           bool stage = true, float* scol = nullptr) {
   if (sbias != nullptr) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -69,6 +69,30 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
     }
     const int chunk = (h * 4 + c) ^ (row & 7);
     *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
+    if (scol != nullptr) {   // keep the stored (masked, bf16-rounded) values for the column sums below
+      f[c * 8 + 0] = __uint_as_float(o.x << 16); f[c * 8 + 1] = __uint_as_float(o.x & 0xffff0000u);
+      f[c * 8 + 2] = __uint_as_float(o.y << 16); f[c * 8 + 3] = __uint_as_float(o.y & 0xffff0000u);
+      f[c * 8 + 4] = __uint_as_float(o.z << 16); f[c * 8 + 5] = __uint_as_float(o.z & 0xffff0000u);
+      f[c * 8 + 6] = __uint_as_float(o.w << 16); f[c * 8 + 7] = __uint_as_float(o.w & 0xffff0000u);
+    }
+  }
+  if (scol != nullptr) {
+    // Column sums over the warp's 32 pixel rows (the bias gradient of the layer that consumes this gradient):
+    // recursive halving -- each step a lane keeps one half of its columns and receives the partner's sums of that
+    // half -- 31 shuffles instead of 160, and lane l ends up with the total of column l.  scol: this thread's
+    // 32-column slice of the CTA's shared accumulators.
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float keep = up ? f[i + s] : f[i];
+        const float send = up ? f[i] : f[i + s];
+        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    atomicAdd(scol + lane, f[0]);
   }
 }
 
@@ -79,14 +103,14 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
                                           const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                           const float* shead = nullptr, float2* head_part = nullptr,
-                                          bool stage = true) {
+                                          bool stage = true, float* scol = nullptr) {
   uint32_t v[32];
   tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage);
+  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage, scol);
 }
 
 }  // namespace ub

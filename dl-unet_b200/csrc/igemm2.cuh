@@ -49,6 +49,8 @@ struct alignas(64) Igemm2Params {
   int pool_C, cat_H, cat_W, cat_C, c_off;
   int l2_prefetch;            // (unused since the mask tiles travel through shared memory)
   int aux_bytes;              // bytes between the staging buffers and the mask tile buffers (2048, or 5120 with a head)
+  float* dbias;               // fused column sums of the output (bias gradient of the consuming layer) or nullptr
+  int dbias_c0;               // channels >= dbias_c0 are summed, into dbias[channel - dbias_c0]
   unsigned long long* prof;   // experiment (ub_set_prof_buffer): per-CTA clock sums of the epilogue phases of thread 128
 };
 
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   uint64_t* m_full = reinterpret_cast<uint64_t*>(epi + 2 * 16384 + 640);     // ReLU-mask tiles (dgrad): 2 slots (after the 612 B above)
   uint64_t* m_empty = m_full + 2;
   uint8_t* mbuf = epi + 2 * 16384 + p.aux_bytes;                              // 2 x 16 KB, 1024-aligned
+  float* scol = reinterpret_cast<float*>(epi + 2 * 16384 + p.aux_bytes - 1024); // [<= 256] column sums (dbias only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -328,6 +331,11 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
       named_bar_sync(1, 256);
     }
+    const bool colsum_on = p.dbias != nullptr;
+    if (colsum_on) {
+      scol[et] = 0.0f;
+      named_bar_sync(1, 256);
+    }
     int it = 0;
     uint32_t chunk_ctr = 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -375,7 +383,8 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
           float2 hp = make_float2(0.0f, 0.0f);
           const long long c1 = (p.prof && et == 0) ? clock64() : 0;
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL);
+                    true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL,
+                    colsum_on ? scol + n0 + j * 64 + h * 32 : nullptr);
           const long long c2 = (p.prof && et == 0) ? clock64() : 0;
           if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
@@ -466,6 +475,11 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       mbar_arrive(&tempty[acc]);
     }
     if (et == 0 && (HEAD || POOL)) tma_store_wait_all<0>();
+    if (colsum_on) {   // one flush per CTA: 148 x N global atomics in all
+      named_bar_sync(1, 256);
+      const int ch = et;
+      if (ch < p.n_tiles_n * BN && ch >= p.dbias_c0) atomicAdd(p.dbias + ch - p.dbias_c0, scol[ch]);
+    }
     if (p.prof && et == 0) {
       for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 8 + i] = (unsigned long long)prof_acc[i];
       p.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - prof_t0);

@@ -91,6 +91,12 @@ int ub_conv3x3_fwd_pool(const ub_tensor4* x, const void* w_fwd, const float* bia
  * layer that produced x is fused: dx *= (relu_src > 0).  (autograd of network.py:131-188) */
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                      void* stream);
+/* the same, and dbias[c - c0] += sum over pixels of dx[.., c] for the channels c >= c0 (fp32, caller zeroes): the bias
+ * gradient of the layer whose output gradient dx is (c0 > 0: the up-conv half of a concat buffer).  Fused into the
+ * epilogue where the chosen kernel supports it (shared-memory accumulators, one flush per CTA), one extra
+ * column-sum pass over dx otherwise. */
+int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                          float* dbias, int dbias_c0, void* stream);
 /* dw_packed[co][tap][ci] += sum_pixels dy * x   (fp32, caller zeroes it; split-K atomics) */
 int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream);
 

@@ -177,6 +177,28 @@ def test_conv3x3_fwd_fused_pool(ops, case):
     assert torch.equal(outs[1][1], pooled) and torch.equal(outs[1][2], idx) and torch.equal(outs[1][3], cat)
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 20, 64, 64, 0), (1, 70, 70, 64, 128, 64), (2, 33, 41, 128, 128, 0), (1, 12, 12, 256, 512, 0),
+                                   (1, 104, 104, 256, 256, 0)])
+def test_conv3x3_dgrad_fused_bias(ops, shape):
+    """dgrad + column sums of dx over the channels >= c0 (the bias gradient of the layer that produced the input;
+    c0 > 0: only the up-conv half of a concat buffer), fused into the epilogue or -- for shapes that run on the
+    other kernel -- one extra pass: same numbers either way."""
+    n, h, w, cout, cin, c0 = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    dy = nhwc(torch.randn(n, cout, h - 2, w - 2, device=DEV))
+    wd = ops.pack_weight(wt, ops.PACK_CONV_DGRAD)
+    for mask in (nhwc(x), None):
+        ref = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.conv3x3_dgrad(dy, wd, ref, mask)
+        dx = torch.full_like(ref, float("nan"))
+        db = torch.zeros(cin - c0, device=DEV)
+        ops.conv3x3_dgrad(dy, wd, dx, mask, db, c0)
+        assert torch.equal(dx, ref)
+        assert rel_l2(db, ref[..., c0:].float().sum((0, 1, 2))) < FP32_TOL
+
+
 def test_conv3x3_strided_views_write_in_place(ops):
     n, h, w, cin, cout = 2, 22, 22, 64, 128
     torch.manual_seed(1)
