@@ -22,6 +22,9 @@ from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
 # encoder levels whose 2x2 max pool runs inside the epilogue of conv{l}2c (the haloed-patch kernel: <= 256 channels);
 # UB_FUSED_POOL_LEVELS=0 restores the separate pool kernel everywhere (experiments)
 FUSED_POOL_LEVELS = int(__import__("os").environ.get("UB_FUSED_POOL_LEVELS", "2"))
+# bias gradients accumulated by the dgrad that produces the layer's output gradient (UB_FUSE_DGRAD_BIAS=0: separate
+# column-sum kernels, for A/B measurements)
+FUSE_DGRAD_BIAS = __import__("os").environ.get("UB_FUSE_DGRAD_BIAS", "1") != "0"
 
 PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
 # order in which backward finishes each layer's gradients
@@ -267,6 +270,11 @@ class Engine:
             e = st.g_off[lname + ".bias"] + _align(st.numel[lname + ".bias"])
             self.grad_ready_hook(s, e)
 
+    @staticmethod
+    def _bias_from_dgrad(lname):
+        """Layers whose bias gradient is produced by the dgrad of the following conv (not by pool / head backward)."""
+        return lname.endswith("1e") or (lname.endswith("1c") and lname != "conv11c")
+
     def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False, dx_bias=None, dx_bias_c0=0):
         """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer.  bias_done: the kernel that
         produced dy (pool / head backward, or the dgrad of the layer after this one) already accumulated its column
@@ -277,11 +285,12 @@ class Engine:
         ops.conv3x3_wgrad(x, dy, dwp)
         if self.grad_ready_hook is not None:  # data parallel: the layer's gradient must be final now
             ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
-        if not bias_done:
+        if not bias_done or (not FUSE_DGRAD_BIAS and self._bias_from_dgrad(lname)):
             ops.colsum(dy, st.g(lname + ".bias"))
         self._ready(lname)
         if dx is not None:
-            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src, st.g(dx_bias) if dx_bias else None, dx_bias_c0)
+            fuse = dx_bias is not None and FUSE_DGRAD_BIAS
+            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src, st.g(dx_bias) if fuse else None, dx_bias_c0)
 
     def backward(self, ws, dlogits):
         """dlogits: fp32 [B,2,So,So] (d loss / d logits).  Fills the gradient arena; if every
@@ -317,6 +326,8 @@ class Engine:
             ops.upconv2x2_wgrad(src, dyu, dwp)
             if self.grad_ready_hook is not None:
                 ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
+            if not FUSE_DGRAD_BIAS:
+                ops.colsum(dyu, st.g(up_name + ".bias"))
             self._ready(up_name)                     # its bias gradient came with conv{l}1e's dgrad
             ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
             dy = dsrc
