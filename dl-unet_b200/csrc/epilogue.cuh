@@ -26,7 +26,7 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
   if (sbias != nullptr) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);  // same address in every lane: broadcast
+      const float4 b4 = lds_f4(sbias + i);  // same address in every lane: broadcast
       f[i] += b4.x;
       f[i + 1] += b4.y;
       f[i + 2] += b4.z;
@@ -41,8 +41,8 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
     float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 w0 = *reinterpret_cast<const float4*>(shead + i);       // broadcast reads
-      const float4 w1 = *reinterpret_cast<const float4*>(shead + 64 + i);
+      const float4 w0 = lds_f4(shead + i);       // broadcast reads
+      const float4 w1 = lds_f4(shead + 64 + i);
       s0 = fmaf(f[i], w0.x, s0); s0 = fmaf(f[i + 1], w0.y, s0); s0 = fmaf(f[i + 2], w0.z, s0); s0 = fmaf(f[i + 3], w0.w, s0);
       s1 = fmaf(f[i], w1.x, s1); s1 = fmaf(f[i + 1], w1.y, s1); s1 = fmaf(f[i + 2], w1.z, s1); s1 = fmaf(f[i + 3], w1.w, s1);
     }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
       }
     }
     const int chunk = (h * 4 + c) ^ (row & 7);
-    *reinterpret_cast<uint4*>(ebuf + row * 128 + chunk * 16) = o;
+    sts_u4(ebuf + row * 128 + chunk * 16, o);
     if (scol != nullptr) {   // keep the stored (masked, bf16-rounded) values for the column sums below
       f[c * 8 + 0] = __uint_as_float(o.x << 16); f[c * 8 + 1] = __uint_as_float(o.x & 0xffff0000u);
       f[c * 8 + 2] = __uint_as_float(o.y << 16); f[c * 8 + 3] = __uint_as_float(o.y & 0xffff0000u);
@@ -92,7 +92,7 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
         f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
       }
     }
-    atomicAdd(scol + lane, f[0]);
+    reds_add_f32(scol + lane, f[0]);
   }
 }
 

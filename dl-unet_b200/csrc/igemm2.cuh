@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
             mbar_wait(&m_full[sl], (chunk_ctr >> 1) & 1, 27);
             const uint8_t* mrow = mbuf + sl * 16384 + row * 128;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) mcur[i] = *reinterpret_cast<const uint4*>(mrow + (((h * 4 + i) ^ (row & 7)) << 4));
+            for (int i = 0; i < 4; ++i) mcur[i] = lds_u4(mrow + (((h * 4 + i) ^ (row & 7)) << 4));
             mbar_arrive(&m_empty[sl]);
           }
           float2 hp = make_float2(0.0f, 0.0f);
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int r = r00 + (k >> 1) * 8 + (k & 1);
-                unpack8(*reinterpret_cast<const uint4*>(ebuf + r * 128 + ((c8 ^ (r & 7)) << 4)), v[k]);
+                unpack8(lds_u4(ebuf + r * 128 + ((c8 ^ (r & 7)) << 4)), v[k]);
               }
               float m[8];
               uint32_t code[8];
