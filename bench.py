@@ -302,7 +302,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": ke},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "igemm_kernel (3x3 conv fwd + dgrad, up-conv fwd + dgrad)",
+            "roofline": {"bound": "tensor", "kernel": "igemm family: igemm_kernel / igemm2_kernel / igemm3_kernel (3x3 conv fwd + dgrad incl. the fused pool / head / bias-sum epilogues, up-conv fwd + dgrad)",
                          "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                          "peak_kind": f"{peak_kind} sustained bf16 (MEASURED_PEAKS.json)", "traffic": traffic,
                          "launches_timed": ig[2], "ms_per_step": ig[1] / K,
