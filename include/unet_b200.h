@@ -42,13 +42,17 @@ int ub_version(void);
 const char* ub_error_string(int code);
 /* Non-zero after a kernel aborted on a pipeline dead-lock guard; host memory out-param. Synchronises. */
 int ub_device_error(unsigned int* out_code);
-/* Tuning overrides for experiments: <=0 restores the heuristic. */
 /* experiment: device buffer of 148 x 8 uint64 that igemm2 launches fill with the clock sums of their epilogue phases
  * (wait for the MMAs, TMEM load + arithmetic + staging, store wait, chunk barrier, store issue, chunks, total); NULL = off */
 void ub_set_prof_buffer(void* dev_ptr);
+/* Tuning overrides for experiments: <=0 restores the heuristic. */
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
 /* Experiment switches.  key 1: 3x3 wgrad kernel (0 = tap-per-CTA, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto [default], 4 = tap-row-per-CTA N=192, 5 = shifted-dY kernel for 64 output channels).
- * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default], 2 = wherever legal). */
+ * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default], 2 = wherever legal).
+ * key 3: three-taps-per-instruction kernel for 64 -> 64 channel convs (0 = off, 1 = plain forward only [default], 2 = forward, dgrad and fused head).
+ * key 4: igemm3 ablation bits (1 = no pixel shift-and-add, 2 = no staging / store, 4 = TMEM read-out only, 8 = a third of the MMAs, 16 = no patch loads after the first tile): timing experiments only, results are wrong.
+ * key 5: igemm ablation (1 = do not wait for earlier TMA stores): timing experiments only.
+ * key 6: unused (was: TMA L2 prefetch of the ReLU-mask tiles, which now travel through shared memory). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------
