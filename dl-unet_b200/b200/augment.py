@@ -16,21 +16,18 @@ from .geometry import input_size_compute
 from .ops import STATS, _chk, _need_cuda, _ptr, _stream
 
 
-class DeviceAugmenter:
-    def __init__(self, images, targets, crop=388, alpha=3, sigma=10, skip=10, device="cuda"):
-        """images / targets: uint8 arrays or tensors [N, H, W] (targets 0 / 255, as data.py:63 produces them)."""
-        images, targets = torch.as_tensor(np.asarray(images)), torch.as_tensor(np.asarray(targets))
-        if images.dtype != torch.uint8 or targets.dtype != torch.uint8 or images.shape != targets.shape or images.dim() != 3:
-            raise RuntimeError("DeviceAugmenter expects uint8 [N,H,W] image and target stacks of equal shape")
-        self.images, self.targets = images.to(device).contiguous(), targets.to(device).contiguous()
-        _need_cuda(self.images)
-        self.n, self.h, self.w = images.shape
-        self.crop, self.alpha, self.sigma, self.skip = int(crop), float(alpha), float(sigma), int(skip)
-        _, self.input_size, _ = input_size_compute(self.crop)
+class CropSampler:
+    """Host side of the pipeline (no device needed): the crop anchors and their weighted distribution per dataset
+    frame (data.py:66-82) and the random integers of one __getitem__ call (data.py:97-104, 115)."""
+
+    def __init__(self, targets, crop=388, skip=10):
+        """targets: uint8 array [N, H, W] of 0 / 255 masks (data.py:63's gt_bin)."""
+        targets = np.asarray(targets)
+        self.n, self.h, self.w = targets.shape
+        self.crop, self.skip = int(crop), int(skip)
         # data.py:66-82: crop anchors every `skip` pixels, weighted towards windows that are ~50 % foreground
         self.pairs = [(i, j) for i in range(0, self.h - self.crop, self.skip) for j in range(0, self.w - self.crop, self.skip)]
-        self.distribution = [self._crop_distribution(t) for t in targets.numpy()]
-        self._ws = {}
+        self.distribution = [self._crop_distribution(t) for t in targets]
 
     def _crop_distribution(self, gt_bin):
         from scipy.stats import norm
@@ -57,6 +54,20 @@ class DeviceAugmenter:
             y = min(max(0, y), self.w - self.crop)
             out[k] = (idx, x, y, np.random.choice(np.arange(0, 360, 30)))
         return out
+
+
+class DeviceAugmenter(CropSampler):
+    def __init__(self, images, targets, crop=388, alpha=3, sigma=10, skip=10, device="cuda"):
+        """images / targets: uint8 arrays or tensors [N, H, W] (targets 0 / 255, as data.py:63 produces them)."""
+        images, targets = torch.as_tensor(np.asarray(images)), torch.as_tensor(np.asarray(targets))
+        if images.dtype != torch.uint8 or targets.dtype != torch.uint8 or images.shape != targets.shape or images.dim() != 3:
+            raise RuntimeError("DeviceAugmenter expects uint8 [N,H,W] image and target stacks of equal shape")
+        self.images, self.targets = images.to(device).contiguous(), targets.to(device).contiguous()
+        _need_cuda(self.images)
+        CropSampler.__init__(self, targets.numpy(), crop=crop, skip=skip)
+        self.alpha, self.sigma = float(alpha), float(sigma)
+        _, self.input_size, _ = input_size_compute(self.crop)
+        self._ws = {}
 
     def __call__(self, indices=None, draws=None, noise=None):
         """-> (images fp32 [B,1,S,S], labels int64 [B,1,crop,crop]) on the device.  `draws`: int [B,4] from draw()

@@ -149,3 +149,43 @@ def test_weighted_map_matches_reference():
     # reduction is not bit-reproducible from call to call
     torch.testing.assert_close(functions.weighted_map(lab), ref.weighted_map(lab), rtol=1e-5, atol=1e-7)
     assert torch.equal(functions.class_balance(lab), ref.class_balance(lab))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted (GPU box)")
+def test_crop_sampler_matches_reference_dataset_init(tmp_path):
+    """b200.augment.CropSampler (anchors + weighted crop distribution + draw order) against the reference's own
+    ImageDataset.__init__ / __getitem__ code (data.py:66-82, 97-104, 115) on a seeded frame written to disk."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, types, os, numpy as np
+sys.modules.setdefault("wget", types.ModuleType("wget"))
+sys.path.insert(0, "/root/reference")
+import warnings; warnings.simplefilter("ignore")
+import cv2 as cv
+import data as R
+root = sys.argv[1]
+rng = np.random.RandomState(5)
+yy, xx = np.indices((200, 200))
+gt = np.zeros((200, 200), np.uint16)
+for k in range(12):
+    cy, cx = rng.rand(2) * 200; ry, rx = 6 + rng.rand(2) * 30
+    gt[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1] = k + 1
+os.makedirs(os.path.join(root, "01")); os.makedirs(os.path.join(root, "01_GT", "SEG"))
+cv.imwrite(os.path.join(root, "01", "t000.tif"), (rng.rand(200, 200) * 255).astype(np.uint8))
+cv.imwrite(os.path.join(root, "01_GT", "SEG", "man_seg000.tif"), gt)
+ds = R.ImageDataset(root, crop=100, ISBI2012=True)
+np.save(os.path.join(root, "target.npy"), np.asarray(ds.target[0]))
+np.save(os.path.join(root, "dist.npy"), np.asarray(ds.target_weighted_crop_distribution[0]))
+np.save(os.path.join(root, "pairs.npy"), np.asarray(ds.pairs))
+'''
+    r = subprocess.run([sys.executable, "-c", script, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    from b200.augment import CropSampler
+    target = np.load(tmp_path / "target.npy")
+    cs = CropSampler(target[None], crop=100, skip=10)
+    assert np.array_equal(np.asarray(cs.pairs), np.load(tmp_path / "pairs.npy"))
+    np.testing.assert_allclose(cs.distribution[0], np.load(tmp_path / "dist.npy"), rtol=1e-9, atol=1e-15)
+    np.random.seed(3)
+    d = cs.draw([0, 0])
+    assert d.shape == (2, 4) and (d[:, 3] % 30 == 0).all() and (d[:, 1:3] >= 0).all() and (d[:, 1:3] <= 100).all()
