@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.optim as optim
 
+from b200.checkpoint import AsyncCheckpointer
 from b200.train import FusedSGD, TrainStep, weighted_bce_with_logits
 from functions import class_balance, evaluation_metrics, weighted_map
 
@@ -53,8 +54,13 @@ def _first_sample_metrics(logits, labels):
     return evaluation_metrics(pred[0].detach(), labels[0, 0].detach())
 
 
+_CKPT = AsyncCheckpointer()
+
+
 def _save(unet, path):
-    torch.save(unet.state_dict(), path)
+    """torch.save(unet.state_dict(), path) (trainer.py:152,190,219,228) without stalling the training stream: one D2H
+    copy of the parameter arena on a side stream, serialisation in a worker thread (joined before training() returns)."""
+    _CKPT.save(unet, path)
     print('Model has been saved:')
     print(path)
 
@@ -147,7 +153,7 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
             # (so the periodic checkpoint and the low-lr stop below are skipped until the goal is met)
             if val_eval_epoch[0] > goal:
                 path = os.path.join(model_dir, 'unet_weight_save_{}.pth'.format(DATASET))
-                torch.save(unet.state_dict(), path)
+                _CKPT.save(unet, path)
                 print('The goal was reached in epoch {}!'.format(epoch))
                 print('Model has been saved:')
                 print(path)
@@ -167,5 +173,6 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
         if my_patience == scheduler.patience:
             my_patience = -1
 
+    _CKPT.wait()                      # every checkpoint file is complete when training() returns
     print('Training is finished as epoch {} has been reached'.format(epoch))
     print('                                                               ')

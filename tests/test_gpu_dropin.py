@@ -98,3 +98,30 @@ def test_testing_drop_in_writes_reference_outputs(tmp_path, capsys):
     # statistics of the FIRST image only (tester.py:42 drops the concatenation), std over a single value = 0
     assert iou[1] == 0 and pe[1] == 0
     assert abs(pe[0] - ref[1, 0]) <= 0.02 and (np.isnan(iou[0]) == np.isnan(ref[0, 0])) and (np.isnan(iou[0]) or abs(iou[0] - ref[0, 0]) <= 0.05)
+
+
+def test_async_checkpoint_equals_torch_save(tmp_path):
+    """b200.checkpoint.AsyncCheckpointer writes what torch.save(unet.state_dict()) writes (46 keys, fp32, same values),
+    captures the weights of the moment save() was called even if training goes on, and round-trips."""
+    import unet_oracle as O
+    from network import Unet
+    from b200 import train as T
+    from b200.checkpoint import AsyncCheckpointer
+    torch.manual_seed(2)
+    net = Unet().to(DEV)
+    images, labels, weight = O.synthetic_batch(1, 220, seed=3)
+    step = T.TrainStep(net, T.FusedSGD(net), graph=False)
+    step(images.to(DEV), labels.to(DEV), weight.to(DEV))
+    ref = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    ck = AsyncCheckpointer()
+    ck.save(net, str(tmp_path / "a.pth"))
+    for _ in range(3):                                            # training continues while the file is written
+        step(images.to(DEV), labels.to(DEV), weight.to(DEV))
+    ck.wait()
+    got = torch.load(tmp_path / "a.pth")
+    assert list(got.keys()) == O.PARAM_NAMES
+    for k in ref:
+        assert got[k].dtype == torch.float32 and got[k].shape == ref[k].shape and torch.equal(got[k], ref[k]), k
+    assert not torch.equal(ref["conv12c.weight"], net.state_dict()["conv12c.weight"].cpu())   # weights did move on
+    fresh = Unet()
+    fresh.load_state_dict(got)
