@@ -189,3 +189,22 @@ np.save(os.path.join(root, "pairs.npy"), np.asarray(ds.pairs))
     np.random.seed(3)
     d = cs.draw([0, 0])
     assert d.shape == (2, 4) and (d[:, 3] % 30 == 0).all() and (d[:, 1:3] >= 0).all() and (d[:, 1:3] <= 100).all()
+
+
+def test_c_abi_host_side_queries_and_argument_checks():
+    """Entry points that return before any launch: workspace-size queries and argument validation (no GPU needed)."""
+    import ctypes as C
+    from b200 import lib
+    h = lib.load()
+    # weight maps: counts (8 B / sample) + component labels (4 B / px) + 2 candidates (8 B / px), each 256-aligned
+    al = lambda v: (v + 255) & ~255
+    assert h.ub_weight_map_workspace_bytes(16, 388, 388) == al(8 * 16) + al(4 * 16 * 388 * 388) + al(8 * 16 * 388 * 388)
+    assert h.ub_weight_map_workspace_bytes(0, 388, 388) == 0
+    assert h.ub_augment_workspace_bytes(16, 388, 572, C.c_double(10.0)) > 2 * 16 * 2 * 800 * 800 * 8   # two fp64 windows
+    assert h.ub_augment_workspace_bytes(16, 388, 572, C.c_double(40.0)) == 0                         # sigma beyond the smem tile
+    assert h.ub_loss_workspace_bytes() > 0
+    null = C.c_void_p(0)
+    assert h.ub_weight_map(null, 8, 1, 16, 16, C.c_double(20), C.c_double(25), 1, null, null, null, null) == -5      # UB_E_ARG
+    assert h.ub_mask_metrics(null, 1, null, 1, 10, null, null) == -5
+    assert h.ub_mirror_pad(null, null, 1, 10, 20, null) == -5
+    assert b"null" in h.ub_error_string(-5).lower() or h.ub_error_string(-5)
