@@ -1112,10 +1112,13 @@ int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsi
     cc = (int)dcat->sx;
   }
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  if (dbias)
-    pool_bwd_kernel<true><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  if (dbias) {
+    // one resident wave (6 CTAs per SM): every CTA ends with c atomics into dbias, a larger grid only adds contention
+    long long blocks = (total + 255) / 256;
+    if (blocks > 6ll * num_sms()) blocks = 6ll * num_sms();
+    pool_bwd_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, catp, idx, (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n, h, w, c, ch, cw, cc, c_off, dbias);
-  else
+  } else
     pool_bwd_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, catp, idx, (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n, h, w, c, ch, cw, cc, c_off, nullptr);
   return (int)cudaGetLastError();
