@@ -110,6 +110,87 @@ def cpu_reference_steps(steps, warmup, threads=None):
     return 1.0 / dt, cores, dt
 
 
+def cudnn_steps(per_gpu, steps, warmup, device, mode):
+    """The "existing Blackwell kernel" bar: the reference's own operator sequence
+    (network.py:131-190 + trainer.py:54-78, restated in oracle/unet_oracle.py) dispatched by stock PyTorch to
+    cuDNN / ATen CUDA kernels on the same B200, same batch and tile size.  mode "fp32": the reference as written
+    (NCHW fp32, TF32 off as torch defaults); "tf32": same with torch's TF32 switches on; "bf16": autocast(bf16) +
+    channels_last, the usual mixed-precision recipe.  Returns (tiles/s, ms per step)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import unet_oracle as O
+    torch.backends.cudnn.benchmark = True
+    tf32 = mode == "tf32"
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    sd = {k: v.to(device) for k, v in O.init_state_dict(0).items()}
+    images, labels, weight = (t.to(device) for t in O.synthetic_batch(per_gpu, TILE, seed=1000))
+    if mode == "bf16":
+        images = images.contiguous(memory_format=torch.channels_last)
+        sd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+    mom = {}
+
+    def one():
+        if mode == "bf16":
+            params = {k: v.detach().requires_grad_(True) for k, v in sd.items()}
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = O.forward(params, images)
+            preds = O.center_crop_preds(logits.float(), labels.shape[-1])
+            loss = O.loss_bce(preds, labels, weight)
+            grads = torch.autograd.grad(loss, list(params.values()))
+            with torch.no_grad():
+                ks = list(sd.keys())
+                if not mom:
+                    for k, g in zip(ks, grads):
+                        mom[k] = g.clone()
+                else:
+                    torch._foreach_mul_([mom[k] for k in ks], 0.99)
+                    torch._foreach_add_([mom[k] for k in ks], list(grads))
+                torch._foreach_add_([sd[k] for k in ks], [mom[k] for k in ks], alpha=-1e-4)
+            return loss
+        return O.train_step(sd, mom, images, labels, weight)[0]
+
+    for _ in range(max(3, warmup)):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    torch.backends.cudnn.allow_tf32 = True     # torch defaults
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return per_gpu / (ms * 1e-3), ms
+
+
+def run_cudnn(args):
+    """--impl cudnn: stock PyTorch + cuDNN on one B200 (rank 0 only), same metric / config as our arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    per_gpu = args.batch_per_gpu or 16
+    res = {}
+    for mode in ("bf16", "tf32", "fp32"):
+        v, ms = cudnn_steps(per_gpu, max(1, min(args.steps, 10)), args.warmup, dev, mode)
+        res[mode] = {"value": v, "ms_per_step": ms}
+        torch.cuda.empty_cache()
+    best = max(res, key=lambda k: res[k]["value"])
+    print(json.dumps({
+        "impl": "cudnn", "metric": METRIC, "value": res[best]["value"], "unit": UNIT, "n_gpus": 1,
+        "steps": max(1, min(args.steps, 10)), "warmup": max(3, args.warmup), "ms_per_step": res[best]["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": best, "data": "synthetic",
+        "config": dict(workload_config(per_gpu, per_gpu, 1),
+                       what="the reference's operator sequence (oracle/unet_oracle.py = network.py:131-190 + "
+                            "trainer.py:54-78) on stock torch %s + cuDNN %s, device-resident inputs" %
+                            (torch.__version__, torch.backends.cudnn.version())),
+        "modes": res, "gpu_launches": 0,
+    }), file=JSON_OUT, flush=True)
+
+
 def workload_config(per_gpu, global_batch, world):
     """The `config` object both arms report (BASELINE config 2 at N = 1, config 3 at N > 1)."""
     return {"workload": f"original U-Net (64-1024 ch, valid convs) 572x572->388x388 training step "
@@ -147,12 +228,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cudnn"])
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="override the BASELINE batch (diagnostics only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "cudnn":
+        return run_cudnn(args)
 
     import torch
     import torch.distributed as dist

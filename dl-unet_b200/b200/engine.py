@@ -93,8 +93,8 @@ class ParamStore:
         self.p_arena = arena
         self.g_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
         self.m_arena = torch.zeros(self.total, dtype=torch.float32, device=device)
-        self.dwp_arena = None
         self.jobs = None
+        self.arena_id = getattr(self, "arena_id", 0) + 1   # workspaces cache job tables that point into the arenas
         self.packs = {}
         self.device = device
         self.dirty = True
@@ -114,22 +114,28 @@ class ParamStore:
     def versions(self):
         return tuple(p._version for p in self.params().values())
 
-    def _job_table(self):
-        """One-launch pack / unpack over all 21 conv / up-conv layers (ops.JobTable); rebuilt with the arenas."""
-        if getattr(self, "jobs", None) is None:
-            self.packed_grad_arena()
-            entries = []
-            for (lname, kind, cin, cout) in LAYERS:
-                if kind not in ("conv", "up"):
-                    continue
-                w = self.p(lname + ".weight")
+    def _layer_entries(self, slab_of=None):
+        """Job-table rows of the 21 conv / up-conv layers (ops.JobTable).  slab_of(lname) -> (slab workspace, n_slabs);
+        None: a pack-only table (the gradient columns are placeholders)."""
+        entries = []
+        for (lname, kind, cin, cout) in LAYERS:
+            if kind not in ("conv", "up"):
+                continue
+            w = self.p(lname + ".weight")
+            if lname not in self.packs:
                 fshape = (cout, 9 * cin) if kind == "conv" else (4 * cout, cin)
                 dshape = (cin, 9 * cout) if kind == "conv" else (cin, 4 * cout)
                 self.packs[lname] = (torch.empty(fshape, dtype=torch.bfloat16, device=self.device),
                                      torch.empty(dshape, dtype=torch.bfloat16, device=self.device))
-                entries.append((w, self.packs[lname][0], self.packs[lname][1], self.dwp(lname), self.g(lname + ".weight"),
-                                0 if kind == "conv" else 2, cout, cin))
-            self.jobs = ops.JobTable(entries, self.device)
+            slab, n_slabs = slab_of(lname) if slab_of is not None else (self.g(lname + ".weight"), 1)
+            entries.append((w, self.packs[lname][0], self.packs[lname][1], slab, self.g(lname + ".weight"),
+                            0 if kind == "conv" else 2, cout, cin, n_slabs))
+        return entries
+
+    def _job_table(self):
+        """One-launch pack over all 21 conv / up-conv layers; rebuilt with the arenas."""
+        if getattr(self, "jobs", None) is None:
+            self.jobs = ops.JobTable(self._layer_entries(), self.device)
         return self.jobs
 
     def refresh_packs(self):
@@ -141,22 +147,9 @@ class ParamStore:
         self.pack_versions = v
         self.dirty = False
 
-    def packed_grad_arena(self):
-        """fp32 scratch the wgrad kernels accumulate into (packed layout), zeroed per backward."""
-        if self.dwp_arena is None:
-            n = sum(_align(self.numel[l + ".weight"]) for (l, k, _, _) in LAYERS if k in ("conv", "up"))
-            self.dwp_arena = torch.empty(n, dtype=torch.float32, device=self.device)
-            self.dwp_off = {}
-            off = 0
-            for (l, k, _, _) in LAYERS:
-                if k in ("conv", "up"):
-                    self.dwp_off[l] = off
-                    off += _align(self.numel[l + ".weight"])
-        return self.dwp_arena
 
-    def dwp(self, lname):
-        self.packed_grad_arena()
-        return self.dwp_arena[self.dwp_off[lname]:self.dwp_off[lname] + self.numel[lname + ".weight"]]
+# index of each conv / up-conv layer in the job tables
+JOB_INDEX = {l: i for i, l in enumerate(n for (n, k, _, _) in LAYERS if k in ("conv", "up"))}
 
 
 class Workspace:
@@ -192,6 +185,34 @@ class Workspace:
             for l in range(1, FUSED_POOL_LEVELS + 1):
                 self.grad[f"e{l}2"] = torch.empty(B, g.enc2[l], g.enc2[l], LEVEL_C[l], **bf)
         self.image = None
+        self.slabs = None   # weight-gradient slab workspace + unpack job table, built on the first backward
+
+    def wgrad_input_size(self, lname):
+        """Spatial size of the INPUT of a conv / up-conv layer (its weight gradient reduces over the output pixels)."""
+        g = self.geom
+        if lname.startswith("upconv"):
+            return g.up[int(lname[-1])] // 2
+        lvl, pos, side = int(lname[4]), int(lname[5]), lname[6]
+        out = ((g.enc1 if pos == 1 else g.enc2) if side == "c" else (g.dec1 if pos == 1 else g.dec2))[lvl]
+        return out + 2
+
+    def grad_slabs(self, store):
+        """Deterministic split-K: the wgrad kernel of every layer stores `n` partial gradients (slabs) side by side; the
+        slab counts depend on the layer shape at this batch, so the workspace and the unpack job table live here."""
+        if self.slabs is None or self.slabs["arena_id"] != store.arena_id:
+            counts, off, total = {}, {}, 0
+            for (lname, kind, cin, cout) in LAYERS:
+                if kind not in ("conv", "up"):
+                    continue
+                h = self.wgrad_input_size(lname)
+                counts[lname] = ops.wgrad_slabs(ops.PACK_CONV_FWD if kind == "conv" else ops.PACK_UP_FWD, self.B, h, h, cin, cout)
+                off[lname] = total
+                total += counts[lname] * store.numel[lname + ".weight"]
+            arena = torch.empty(total, dtype=torch.float32, device=store.device)
+            view = lambda l: arena[off[l]:off[l] + counts[l] * store.numel[l + ".weight"]]
+            table = ops.JobTable(store._layer_entries(lambda l: (view(l), counts[l])), store.device)
+            self.slabs = {"arena": arena, "view": view, "counts": counts, "table": table, "arena_id": store.arena_id}
+        return self.slabs
 
 
 class Engine:
@@ -281,10 +302,9 @@ class Engine:
         sums into the bias gradient.  dx_bias: name of the parameter that receives the column sums of dx (channels
         >= dx_bias_c0) -- the bias gradient of the layer that produced x, fused into this layer's dgrad."""
         st = self.store
-        dwp = st.dwp(lname)
-        ops.conv3x3_wgrad(x, dy, dwp)
+        ops.conv3x3_wgrad(x, dy, self._slabs["view"](lname))
         if self.grad_ready_hook is not None:  # data parallel: the layer's gradient must be final now
-            ops.unpack_grad(dwp, st.grad_view(lname + ".weight"), ops.PACK_CONV_FWD, self._accumulate)
+            self._slabs["table"].unpack_layer(JOB_INDEX[lname], self._accumulate)
         if not bias_done or (not FUSE_DGRAD_BIAS and self._bias_from_dgrad(lname)):
             ops.colsum(dy, st.g(lname + ".bias"))
         self._ready(lname)
@@ -302,7 +322,7 @@ class Engine:
             p.grad is not None and p.grad.data_ptr() == st.grad_view(n).data_ptr() for n, p in st.params().items())
         if not self._accumulate:
             st.g_arena.zero_()
-        st.packed_grad_arena().zero_()
+        self._slabs = ws.grad_slabs(st)      # every slab is fully overwritten by its wgrad kernel: nothing to zero
         P, pk = st.p, st.packs
         dlogits = dlogits.contiguous().float()
 
@@ -322,10 +342,9 @@ class Engine:
             src = a[f"d{l + 1}2"] if l < 4 else a["e52"]
             dsrc = gr[f"d{l + 1}2"] if l < 4 else gr["e52"]
             dyu = gr[f"cat{l}"][..., C:]
-            dwp = st.dwp(up_name)
-            ops.upconv2x2_wgrad(src, dyu, dwp)
+            ops.upconv2x2_wgrad(src, dyu, self._slabs["view"](up_name))
             if self.grad_ready_hook is not None:
-                ops.unpack_grad(dwp, st.grad_view(up_name + ".weight"), ops.PACK_UP_FWD, self._accumulate)
+                self._slabs["table"].unpack_layer(JOB_INDEX[up_name], self._accumulate)
             if not FUSE_DGRAD_BIAS:
                 ops.colsum(dyu, st.g(up_name + ".bias"))
             self._ready(up_name)                     # its bias gradient came with conv{l}1e's dgrad
@@ -349,7 +368,7 @@ class Engine:
                 ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
                 self._ready("conv11c")
         if self.grad_ready_hook is None:
-            st._job_table().unpack_all(self._accumulate)   # single device: all 21 layers in one launch
+            self._slabs["table"].unpack_all(self._accumulate)   # single device: all 21 layers in one launch
         if self.grad_done_hook is not None:
             self.grad_done_hook()
 

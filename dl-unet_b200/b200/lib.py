@@ -34,17 +34,18 @@ SIGNATURES = {
     "ub_set_prof_buffer": (None, [_P]),
     "ub_set_option": (None, [_i, _i]),
     "ub_pack_weight": (_i, [_P, _P, _i, _i, _i, _P]),
-    "ub_unpack_grad": (_i, [_P, _P, _i, _i, _i, _i, _P]),
+    "ub_unpack_grad": (_i, [_P, _i, _ll, _P, _i, _i, _i, _i, _P]),
     "ub_job_table_bytes": (_i, [_i]),
     "ub_job_table_fill": (_i, [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
-                               C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+                               C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ub_pack_all": (_i, [_P, _i, _ll, _P]),
-    "ub_unpack_all": (_i, [_P, _i, _ll, _i, _P]),
+    "ub_unpack_range": (_i, [_P, _i, _i, _i, _i, _P]),
     "ub_conv3x3_fwd": (_i, [_T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_fwd_head": (_i, [_T4, _P, _P, _T4, _P, _P, _P, _P, _P]),
     "ub_conv3x3_fwd_pool": (_i, [_T4, _P, _P, _i, _T4, _P, _P, _T4, _i, _P]),
     "ub_conv3x3_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
     "ub_conv3x3_dgrad_bias": (_i, [_T4, _P, _T4, _T4, _P, _i, _P]),
+    "ub_wgrad_slabs": (_i, [_i, _i, _i, _i, _i, _i]),
     "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_upconv2x2_fwd": (_i, [_T4, _P, _P, _T4, _P]),
     "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
@@ -66,6 +67,10 @@ SIGNATURES = {
     "ub_mask_metrics": (_i, [_P, _i, _P, _i, _ll, _P, _P]),
     "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),
     "ub_sgd_momentum": (_i, [_P, _P, _P, _ll, _f, _f, _i, _P]),
+}
+# include/unet_b200_diag.h: only in libunet_b200_diag.so (make libunet_b200_diag.so), never in the product library
+DIAG_SIGNATURES = {
+    "ub_last_wgrad_plan": (None, [C.POINTER(_i)]),
     "ub_naive_conv3x3": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _P]),
     "ub_probe_run": (_i, [_i, C.POINTER(C.c_float), _i]),
 }
@@ -96,6 +101,25 @@ def load():
             k, v = kv.split("=")
             lib.ub_set_option(int(k), int(v))
     return _lib
+
+
+_diag = None
+
+
+def load_diag():
+    """The diagnostics build (product library + naive comparator + UMMA probes); bring-up scripts only."""
+    global _diag
+    if _diag is None:
+        path = os.path.join(os.path.dirname(LIB_PATH), "libunet_b200_diag.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is not built: make -C {os.path.dirname(LIB_PATH)} libunet_b200_diag.so")
+        lib = C.CDLL(path)
+        for name, (res, args) in list(SIGNATURES.items()) + list(DIAG_SIGNATURES.items()):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = lib
+    return _diag
 
 
 def check(code, what=""):

@@ -124,12 +124,36 @@ def pack_weight(w, mode, out=None):
     return out
 
 
-def unpack_grad(packed, dw, mode, accumulate=False):
+def wgrad_slabs(kind, n, h_x, w_x, cin, cout):
+    """Number of split-K slabs the weight-gradient kernel of this shape writes (kind: PACK_CONV_FWD for a 3x3 conv
+    whose INPUT is h_x x w_x, PACK_UP_FWD for an up-convolution).  A pure host query."""
+    r = _lib.load().ub_wgrad_slabs(int(kind), int(n), int(h_x), int(w_x), int(cin), int(cout))
+    if r < 0:
+        check(r, "wgrad_slabs")
+    return r
+
+
+def wgrad_workspace(kind, x, cout, fill=None):
+    """Slab workspace [n_slabs, numel] for conv3x3_wgrad (kind PACK_CONV_FWD) / upconv2x2_wgrad (PACK_UP_FWD) of the NHWC
+    input x; the kernels overwrite every element (fill: test pattern to prove it)."""
+    n, h, w, cin = x.shape
+    taps = 9 if kind == PACK_CONV_FWD else 4
+    ws = torch.empty(wgrad_slabs(kind, n, h, w, cin, cout), cout * taps * cin, dtype=torch.float32, device=x.device)
+    if fill is not None:
+        ws.fill_(fill)
+    return ws
+
+
+def unpack_grad(slabs, dw, mode, accumulate=False):
+    """slabs: fp32 [n_slabs, packed layout] as written by conv3x3_wgrad / upconv2x2_wgrad -> dw (torch layout),
+    summed in slab order."""
     if mode == PACK_CONV_FWD:
         cout, cin = dw.shape[0], dw.shape[1]
     else:
         cin, cout = dw.shape[0], dw.shape[1]
-    _chk(_lib.load().ub_unpack_grad(_ptr(packed), _ptr(dw), mode, cout, cin, int(accumulate), _stream()), "unpack_grad")
+    slabs = slabs.reshape(-1, dw.numel())
+    _chk(_lib.load().ub_unpack_grad(_ptr(slabs), slabs.shape[0], dw.numel(), _ptr(dw), mode, cout, cin, int(accumulate),
+                                    _stream()), "unpack_grad")
     return dw
 
 
@@ -137,27 +161,41 @@ class JobTable:
     """Device-side table of all conv / up-conv layers for the one-launch pack / unpack kernels."""
 
     def __init__(self, entries, device):
-        """entries: list of (w fp32 torch-layout, dst_fwd bf16, dst_dgrad bf16, packed_grad fp32, dw fp32, kind, cout, cin)."""
-        import numpy as np
+        """entries: list of (w fp32 torch-layout, dst_fwd bf16, dst_dgrad bf16, grad slabs fp32, dw fp32, kind, cout, cin,
+        n_slabs)."""
         n = len(entries)
         lib = _lib.load()
         nbytes = lib.ub_job_table_bytes(n)
         host = torch.empty(nbytes, dtype=torch.uint8)
         arr = lambda col: (C.c_void_p * n)(*[e[col].data_ptr() for e in entries])
         iarr = lambda col: (C.c_int * n)(*[int(e[col]) for e in entries])
-        tiles = lib.ub_job_table_fill(C.c_void_p(host.data_ptr()), n, arr(0), arr(1), arr(2), arr(3), arr(4), iarr(5), iarr(6), iarr(7))
+        ubegin = (C.c_int * (n + 1))()
+        tiles = lib.ub_job_table_fill(C.c_void_p(host.data_ptr()), n, arr(0), arr(1), arr(2), arr(3), arr(4), iarr(5), iarr(6),
+                                      iarr(7), iarr(8), ubegin)
         if tiles < 0:
             check(tiles, "job_table_fill")
         self.table = host.to(device)
         self.n = n
         self.total = tiles
+        self.utile_begin = list(ubegin)
         self.keep = entries  # keep the tensors alive
 
+    def _numel(self):
+        return sum(e[0].numel() for e in self.keep)
+
     def pack_all(self):
-        _chk(_lib.load().ub_pack_all(_ptr(self.table), self.n, self.total, _stream()), "pack_all")
+        with _timed("hbm:pack_all", self._numel() * 8.0):                  # fp32 master in, two bf16 operands out
+            _chk(_lib.load().ub_pack_all(_ptr(self.table), self.n, self.total, _stream()), "pack_all")
 
     def unpack_all(self, accumulate=False):
-        _chk(_lib.load().ub_unpack_all(_ptr(self.table), self.n, self.total, int(accumulate), _stream()), "unpack_all")
+        """Every layer: sum the gradient slabs in fixed order and write the torch-layout gradients."""
+        with _timed("hbm:unpack_all", sum(e[0].numel() * 4.0 * (e[8] + 1) for e in self.keep)):   # slabs in, gradient out
+            _chk(_lib.load().ub_unpack_range(_ptr(self.table), self.n, 0, self.utile_begin[self.n], int(accumulate), _stream()),
+                 "unpack_all")
+
+    def unpack_layer(self, i, accumulate=False):
+        _chk(_lib.load().ub_unpack_range(_ptr(self.table), self.n, self.utile_begin[i], self.utile_begin[i + 1],
+                                         int(accumulate), _stream()), "unpack_layer")
 
 
 # ---------------------------------------------------------------- tensor-pipe ops
@@ -204,6 +242,8 @@ def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_c0=0):
 
 
 def conv3x3_wgrad(x, dy, dw_packed):
+    """dw_packed: fp32 slab workspace of wgrad_slabs(...) * Cout * 9 * Cin elements, fully overwritten (no zeroing,
+    no atomics: the slabs are summed by unpack_grad / JobTable.unpack_*)."""
     _need_cuda(x, dy, dw_packed)
     n, h, w, co = dy.shape
     with _timed("wgrad", 2.0 * n * h * w * co * 9 * x.shape[3]):
@@ -240,19 +280,23 @@ def conv1_fwd(image, w, bias, y):
     """image fp32 [N,1,H,W] -> y bf16 [N,H-2,W-2,64], bias + ReLU fused (network.py:131)."""
     _need_cuda(image, w, bias, y)
     n, _, h, wd = image.shape
-    _chk(_lib.load().ub_conv1_fwd(_ptr(image), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, _stream()), "conv1_fwd")
+    with _timed("hbm:conv1_fwd", n * (h * wd * 4.0 + (h - 2) * (wd - 2) * 128.0)):
+        _chk(_lib.load().ub_conv1_fwd(_ptr(image), _ptr(w), _ptr(bias), _ptr(y), n, h, wd, _stream()), "conv1_fwd")
     return y
 
 
 def conv1_wgrad(image, dy, dw, db):
     n, _, h, wd = image.shape
-    _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
+    with _timed("hbm:conv1_wgrad", n * (h * wd * 4.0 + (h - 2) * (wd - 2) * 128.0)):
+        _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
 
 
 def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
     _need_cuda(x, y, idx)
     n, h, w, c = x.shape
-    _chk(_lib.load().ub_pool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), _t4p(cat), int(c_off), n, h, w, c, _stream()), "pool2x2_fwd")
+    # SURVEY.md 8(d): 4 x 2 B read + 2 B value + 1 B index per output element (+ 2 B for the skip copy)
+    with _timed("hbm:pool_fwd", n * (h // 2) * (w // 2) * c * (13.0 if cat is not None else 11.0)):
+        _chk(_lib.load().ub_pool2x2_fwd(_ptr(x), _ptr(y), _ptr(idx), _t4p(cat), int(c_off), n, h, w, c, _stream()), "pool2x2_fwd")
     return y, idx
 
 
@@ -260,8 +304,11 @@ def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx, dbias=None):
     """dbias (fp32 [C], zeroed by the caller): also receives the column sums of dx (bias gradient of the conv
     that fed the pool)."""
     n, h, w, c = dx.shape
-    _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), _ptr(dbias),
-                                     n, h, w, c, _stream()), "pool2x2_bwd")
+    # SURVEY.md 8(d): 2 B dY + 1 B index read + 4 x 2 B dX written per pooled element (the second gradient producer
+    # and the ReLU mask this kernel also reads are not counted)
+    with _timed("hbm:pool_bwd", n * (h // 2) * (w // 2) * c * 11.0):
+        _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), _ptr(dbias),
+                                         n, h, w, c, _stream()), "pool2x2_bwd")
     return dx
 
 
@@ -273,8 +320,9 @@ def head_fwd(x, w, bias, logits=None, argmax=None):
 def head_bwd(x, w, dlogits, dx, dw, db, dbias_x=None):
     """dbias_x (fp32 [64], zeroed by the caller): also receives the column sums of dx (bias gradient of conv12e)."""
     n, h, wd, _ = x.shape
-    _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dbias_x), n, h, wd,
-                                  _stream()), "head_bwd")
+    with _timed("hbm:head_bwd", n * h * wd * (128.0 + 8.0 + 128.0)):      # x, dlogits in; dx out
+        _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dbias_x), n, h, wd,
+                                      _stream()), "head_bwd")
 
 
 LOSS_BCE, LOSS_SOFTMAX_CE = 0, 1
@@ -291,8 +339,10 @@ def loss_fwd_bwd(kind, logits, label, weight, dlogits, loss_out, workspace, grad
     b, _, hp, wp = logits.shape
     l = label.shape[-1]
     lb = {torch.uint8: 1, torch.int64: 8}[label.dtype]
-    _chk(_lib.load().ub_loss_fwd_bwd(kind, _ptr(logits), _ptr(label), lb, _ptr(weight), _ptr(dlogits), _ptr(loss_out),
-                                      _ptr(workspace), b, hp, wp, l, float(grad_scale), _stream()), "loss_fwd_bwd")
+    # 2 logits + label + weight read, 2 dlogits written per pixel (fp32 logits: 21 B with uint8 labels)
+    with _timed("hbm:loss", b * l * l * (8.0 + lb + 4.0 + (8.0 if dlogits is not None else 0.0))):
+        _chk(_lib.load().ub_loss_fwd_bwd(kind, _ptr(logits), _ptr(label), lb, _ptr(weight), _ptr(dlogits), _ptr(loss_out),
+                                          _ptr(workspace), b, hp, wp, l, float(grad_scale), _stream()), "loss_fwd_bwd")
 
 
 def colsum(g, out):
@@ -301,26 +351,28 @@ def colsum(g, out):
     ld = g.stride(2)
     if g.stride(1) != w * ld or (n > 1 and g.stride(0) != h * w * ld):
         raise RuntimeError("colsum needs a view that is dense over pixels")
-    _chk(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
+    with _timed("hbm:colsum", n * h * w * c * 2.0):
+        _chk(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
 
 
 def sgd_momentum(p, g, buf, lr, momentum, first_step):
-    _chk(_lib.load().ub_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum),
-                                      int(first_step), _stream()), "sgd_momentum")
+    with _timed("hbm:sgd", p.numel() * 20.0):                              # 20 B per parameter
+        _chk(_lib.load().ub_sgd_momentum(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum),
+                                          int(first_step), _stream()), "sgd_momentum")
 
 
 def naive_conv3x3(x, w_fwd, bias, relu):
     n, h, w, cin = x.shape
     cout = w_fwd.shape[0]
     y = torch.empty((n, h - 2, w - 2, cout), dtype=torch.float32, device=x.device)
-    _chk(_lib.load().ub_naive_conv3x3(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), n, h, w, cin, cout, int(relu),
+    _chk(_lib.load_diag().ub_naive_conv3x3(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), n, h, w, cin, cout, int(relu),
                                        _stream()), "naive_conv3x3")
     return y
 
 
 def probe_run(cap_rows=128, which=0):
     buf = (C.c_float * (cap_rows * 6))(*([-1.0] * (cap_rows * 6)))
-    _chk(_lib.load().ub_probe_run(which, buf, cap_rows * 6), "probe")
+    _chk(_lib.load_diag().ub_probe_run(which, buf, cap_rows * 6), "probe")
     rows = []
     for i in range(cap_rows):
         r = list(buf[i * 6:(i + 1) * 6])

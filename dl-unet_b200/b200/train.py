@@ -172,6 +172,10 @@ class TrainStep:
         g["lab"].copy_(labels, non_blocking=True)
         g["w"].copy_(weight, non_blocking=True)
         g["graph"].replay()
+        # the replay ran pack_all (from the PRE-step masters) and then the SGD kernel, all without Python: the bf16
+        # operand caches are now one step behind the fp32 masters, so the next forward outside the graph (validation,
+        # predict) must re-derive them
+        st.dirty = True
         self.logits = g["logits"]
         return g["loss"][0]
 

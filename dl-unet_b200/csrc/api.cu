@@ -2,6 +2,9 @@
 // TMA tensor-map construction, tile selection and kernel launches.  No torch types, no
 // allocation, no synchronisation (except the two diagnostic entry points).
 #include "../../include/unet_b200.h"
+#ifdef UB_DIAGNOSTICS
+#include "../../include/unet_b200_diag.h"
+#endif
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -10,6 +13,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "elementwise.cuh"
@@ -17,8 +22,9 @@
 #include "augment.cuh"
 #include "igemm.cuh"
 #include "igemm2.cuh"
-#include "igemm3.cuh"
+#ifdef UB_DIAGNOSTICS
 #include "probe.cuh"
+#endif
 #include "wgrad.cuh"
 #include "wgrad3.cuh"
 #include "wgrad4.cuh"
@@ -32,10 +38,7 @@ int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_mask_l2_prefetch = 1;
-int g_igemm3_dbg = 0;
 int g_igemm_dbg = 0;
-int g_igemm3_mode = 1;   // igemm3.cuh (three taps per instruction) for 64 -> 64 channel convs: 0 off, 1 forward only
-                        // (measured: fwd 6-10 % faster, dgrad 15 % slower than igemm2), 2 forward + dgrad + fused head  // 0: never use the haloed-patch conv kernel, 1: auto (wide shallow layers), 2: whenever legal
 int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -78,20 +81,59 @@ int check_view(const ub_tensor4* t) {
   return 0;
 }
 
+// Encoded tensor maps are cached by (pointer, extents, strides, box): a training step re-issues the same ~300
+// descriptors every iteration (the activation buffers are allocated once per shape), and cuTensorMapEncodeTiled
+// costs a few microseconds of host time each -- which matters when the step is issued eagerly (data parallel).
+struct MapKey {
+  uint64_t v[8];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 8; ++i) h = (h ^ k.v[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+std::mutex g_map_mutex;
+int g_map_cache_on = 1;
+
+template <typename Encode>
+int cached_map(CUtensorMap* m, const MapKey& key, Encode encode) {
+  if (!g_map_cache_on) return encode(m);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *m = it->second;
+    return 0;
+  }
+  const int e = encode(m);
+  if (e) return e;
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, *m);
+  return 0;
+}
+
 // 4-D NHWC bf16 map over a (possibly strided) view: dims {c, w, h, n}, box {64, bw, bh, 1}, SWIZZLE_128B.
 int make_map4(CUtensorMap* m, void* ptr, int c, int w, int h, int n, long long sx, long long sy, long long sn,
               int bw, int bh, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return UB_E_DRIVER;
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  // the swizzle span equals the box row: 64 channels = 128 B, 32 channels = 64 B
-  const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
+  const MapKey key = {{(uint64_t)(uintptr_t)ptr, ((uint64_t)(uint32_t)c << 32) | (uint32_t)w, ((uint64_t)(uint32_t)h << 32) | (uint32_t)n,
+                       (uint64_t)sx, (uint64_t)sy, (uint64_t)sn, ((uint64_t)(uint32_t)bw << 32) | (uint32_t)bh,
+                       (4ull << 32) | (uint32_t)box_c}};
+  return cached_map(m, key, [&](CUtensorMap* out) {
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    // the swizzle span equals the box row: 64 channels = 128 B, 32 channels = 64 B
+    const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
+  });
 }
 int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh, int box_c = 64) {
   return make_map4(m, t->ptr, t->c, t->w, t->h, t->n, t->sx, t->sy, t->sn, bw, bh, box_c);
@@ -100,14 +142,17 @@ int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh, int box_c = 6
 int make_map2(CUtensorMap* m, const void* ptr, long long k, long long rows, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return UB_E_DRIVER;
-  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
+  const MapKey key = {{(uint64_t)(uintptr_t)ptr, (uint64_t)k, (uint64_t)rows, (uint64_t)box_rows, 0, 0, 0, 2ull << 32}};
+  return cached_map(m, key, [&](CUtensorMap* out) {
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
+  });
 }
 
 // Patch (BW x BH <= 128 pixels) that covers a W x H image with the fewest tiles.
@@ -134,17 +179,27 @@ void pick_patch(int W, int H, int& BW, int& BH) {
     }
   }
 }
-void pick_kpatch(int W, int H, int& KW, int& KH) {
-  long long best = -1;
+// Pixel chunk of the deep wgrad kernel: a KW x KH patch of rows = KW * KH pixels, rows a multiple of 16 (the MMA K)
+// between 48 and rows_max (at least three pipeline stages of `blocks` 64-channel blocks must fit in shared memory),
+// chosen to tile the W x H map with the least padding; ties go to the larger chunk.
+void pick_kpatch(int W, int H, int blocks, int& KW, int& KH) {
+  const int budget = WgradCfg::SMEM_LIMIT;
+  int rows_max = (budget / 3 / (blocks * 128)) / 16 * 16;
+  if (rows_max > 128) rows_max = 128;
+  double best = -1.0;
   KW = 8;
   KH = 8;
-  for (int kw = 64; kw >= 1; kw >>= 1) {
-    const int kh = 64 / kw;
-    const long long chunks = (long long)((W + kw - 1) / kw) * ((H + kh - 1) / kh);
-    if (best < 0 || chunks < best) {
-      best = chunks;
-      KW = kw;
-      KH = kh;
+  for (int kh = 1; kh <= 128 && kh <= H + 15; ++kh) {
+    for (int kw = 1; kw * kh <= rows_max && kw <= W + 15; ++kw) {
+      const int rows = kw * kh;
+      if ((rows % 16) || rows < 48) continue;
+      const double padded = (double)((W + kw - 1) / kw * kw) * (double)((H + kh - 1) / kh * kh);
+      const double cost = padded * (1.0 + 1.0 / rows) + (kw < 4 ? 0.02 * padded : 0.0);   // very narrow boxes: short TMA runs
+      if (best < 0.0 || cost < best) {
+        best = cost;
+        KW = kw;
+        KH = kh;
+      }
     }
   }
 }
@@ -187,24 +242,23 @@ int launch_igemm(const IgemmParams& P0, int BN, cudaStream_t st) {
 }
 
 template <int BN>
-int launch_wgrad_t(const WgradParams& P, cudaStream_t st) {
-  using C = WgradCfg<BN>;
+int launch_wgrad_t(const WgradParams& P, int smem_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const long long grid = (long long)P.n_taps * P.m_tiles * P.n_tiles * P.splits;
-  wgrad_kernel<BN><<<(int)grid, 256, C::SMEM_BYTES, st>>>(P);
+  const long long units = (long long)P.items * P.splits;
+  const int grid = (int)(units < num_sms() ? units : num_sms());
+  wgrad_kernel<BN><<<grid, 256, smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
 }
-int launch_wgrad(const WgradParams& P, int BN, cudaStream_t st) {
+int launch_wgrad(const WgradParams& P, int BN, int smem_bytes, cudaStream_t st) {
   switch (BN) {
-    case 64: return launch_wgrad_t<64>(P, st);
-    case 128: return launch_wgrad_t<128>(P, st);
-    case 256: return launch_wgrad_t<256>(P, st);
+    case 64: return launch_wgrad_t<64>(P, smem_bytes, st);
+    case 128: return launch_wgrad_t<128>(P, smem_bytes, st);
+    case 256: return launch_wgrad_t<256>(P, smem_bytes, st);
   }
   return UB_E_SHAPE;
 }
@@ -249,25 +303,6 @@ bool igemm2_eligible(const ub_tensor4* in, const ub_tensor4* out) {
   if (in->c > 256 || out->c > 256) return false;
   if (g_igemm2_mode == 1 && out->w < 96) return false;
   return true;
-}
-
-template <bool HEAD>
-int launch_igemm3_t(const Igemm3Params& P, int smem_bytes, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm3_kernel<HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm3_kernel<HEAD><<<grid, 384, smem_bytes, st>>>(P);
-  return (int)cudaGetLastError();
-}
-
-bool igemm3_eligible(const ub_tensor4* in, const ub_tensor4* out, bool plain_forward) {
-  if (in->c != 64 || out->c != 64) return false;
-  return g_igemm3_mode == 2 || (g_igemm3_mode == 1 && plain_forward);
 }
 
 struct HeadArgs {
@@ -376,73 +411,42 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   return UB_E_SHAPE;
 }
 
-// Three-taps-per-instruction 3x3 conv for 64 -> 64 channels (fwd: base_off 0, dgrad: base_off -2), igemm3.cuh.
-int launch_igemm3(const ub_tensor4* in, const void* w, const float* bias, const ub_tensor4* out, int relu,
-                  const ub_tensor4* relu_src, int base_off, cudaStream_t st, const HeadArgs* head = nullptr) {
-  Igemm3Params P;
-  memset(&P, 0, sizeof(P));
-  P.store_out = 1;
-  P.dbg = g_igemm3_dbg;
-  P.kchunks = in->c / 64;
-  P.n_a = IG3_MAX_A;
-  P.tiles_x = (out->w + IG3_TW - 1) / IG3_TW;
-  P.tiles_y = (out->h + IG3_TH - 1) / IG3_TH;
-  P.n_img = out->n;
-  P.base_off = base_off;
-  P.bias = bias;
-  P.relu = relu;
-  P.out_W = out->w;
-  P.out_H = out->h;
-  int e;
-  if (relu_src) {
-    if ((e = check_view(relu_src))) return e;
-    if (relu_src->n != out->n || relu_src->h != out->h || relu_src->w != out->w || relu_src->c != out->c) return UB_E_SHAPE;
-    P.mask = reinterpret_cast<const __nv_bfloat16*>(relu_src->ptr);
-    P.mask_sn = relu_src->sn;
-    P.mask_sy = relu_src->sy;
-    P.mask_sx = relu_src->sx;
-    if ((e = make_map4(&P.m_map, relu_src, IG3_TW, IG3_TH))) return e;
-  }
-  if (head) {
-    P.head_w = head->w;
-    P.head_b = head->b;
-    P.logits = head->logits;
-    P.argmax = head->argmax;
-    P.store_out = head->store_out;
-  }
-  if ((e = make_map4(&P.a_map, in, 32, 6))) return e;
-  if ((e = make_map2(&P.b_map, w, 9ll * in->c, 64, 64))) return e;
-  if (P.store_out && (e = make_map4(&P.o_map, out, IG3_TW, IG3_TH))) return e;
-  const int smem_bytes = P.n_a * IG3_A_BYTES + 9 * P.kchunks * IG3_B_BYTES + 2 * IG3_E_BYTES + 5120 + 1024;
-  return head ? launch_igemm3_t<true>(P, smem_bytes, st) : launch_igemm3_t<false>(P, smem_bytes, st);
-}
-
-// Split-K factor: fill an integer number of waves (1 CTA per SM) as completely as possible while every
-// split keeps at least `min_chunks` pipeline iterations.
-int pick_splits(long long items, long long chunks, int min_chunks) {
-  if (g_force_splits > 0) return g_force_splits;
+// Split-K factor.  `items` output tiles share `chunks` pixel chunks; with s splits the work units are items * s and
+// every unit reduces per = ceil(chunks / s) chunks.  One CTA per SM: time ~ waves * (per + overhead), where overhead is
+// the non-overlapped cost of a unit in chunk times (prologue / read-out).  Returns the s that minimises it, with every
+// split non-empty (the slabs are stored, not accumulated: an empty split would leave its slab unwritten).
+struct SplitPlan {
+  int splits, per;
+};
+SplitPlan plan_splits(long long items, long long chunks, int min_chunks, double overhead) {
   const int sms = num_sms();
   long long max_splits = chunks / min_chunks;
   if (max_splits < 1) max_splits = 1;
+  if (max_splits > 1024) max_splits = 1024;
   long long best_s = 1;
-  double best_eff = -1.0;
-  for (int waves = 1; waves <= 6; ++waves) {
-    long long s = (long long)waves * sms / items;
-    if (s < 1) s = 1;
-    if (s > max_splits) s = max_splits;
-    const long long ctas = items * s;
-    const long long w = (ctas + sms - 1) / sms;
-    // efficiency of the last wave x a mild preference for more (shorter) waves up to ~3
-    const double eff = (double)ctas / (double)(w * sms) - 0.03 * (w > 3 ? w - 3 : 0) - (w < 2 ? 0.05 : 0.0);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best_s = s;
+  double best_t = -1.0;
+  if (g_force_splits > 0) {
+    best_s = g_force_splits < chunks ? g_force_splits : chunks;
+  } else {
+    for (long long s = 1; s <= max_splits; ++s) {
+      const long long per = (chunks + s - 1) / s;
+      const long long eff = (chunks + per - 1) / per;   // splits that are actually non-empty
+      const long long waves = (items * eff + sms - 1) / sms;
+      // slab traffic: every unit writes its tile once and the unpack kernel reads it back
+      const double t = (double)waves * ((double)per + overhead) + 0.1 * (double)(items * eff);
+      if (best_t < 0.0 || t < best_t - 1e-9) {
+        best_t = t;
+        best_s = eff;
+      }
     }
   }
-  return (int)best_s;
+  SplitPlan sp;
+  sp.per = (int)((chunks + best_s - 1) / best_s);
+  sp.splits = (int)((chunks + sp.per - 1) / sp.per);
+  return sp;
 }
 
-int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st, int* slabs_out) {
   Wgrad3Params P;
   memset(&P, 0, sizeof(P));
   // chunk = 16 x KH output pixels; pick the KH that pads the image least (ties: larger chunk)
@@ -469,7 +473,14 @@ int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   P.dw = dw;
   const long long items = (long long)P.m_tiles * P.ci_tiles;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  P.splits = pick_splits(items, chunks, 6);
+  const SplitPlan sp = plan_splits(items, chunks, 6, 6.0);
+  P.splits = sp.splits;
+  P.per = sp.per;
+  P.slab_stride = (long long)dy->c * 9 * x->c;
+  if (slabs_out) {
+    *slabs_out = P.splits;
+    return 0;
+  }
   int e;
   if ((e = make_map4(&P.g_map, dy, 16, P.KH, 64))) return e;
   if ((e = make_map4(&P.x_map, x, 18, P.KH + 2, 32))) return e;
@@ -486,7 +497,7 @@ int launch_wgrad3(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   return (int)cudaGetLastError();
 }
 
-int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st, int* slabs_out) {
   Wgrad4Params P;
   memset(&P, 0, sizeof(P));
   long long best = -1;
@@ -508,7 +519,14 @@ int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   P.ci_tiles = x->c / 64;
   P.dw = dw;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  P.splits = pick_splits(P.ci_tiles, chunks, 6);
+  const SplitPlan sp = plan_splits(P.ci_tiles, chunks, 6, 6.0);
+  P.splits = sp.splits;
+  P.per = sp.per;
+  P.slab_stride = (long long)dy->c * 9 * x->c;
+  if (slabs_out) {
+    *slabs_out = P.splits;
+    return 0;
+  }
   P.nstage = Wgrad4Cfg::nstage(P.KH);
   P.stage_bytes = Wgrad4Cfg::stage_bytes(P.KH);
   P.g_bytes = Wgrad4Cfg::g_bytes(P.KH);
@@ -525,7 +543,7 @@ int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   return (int)cudaGetLastError();
 }
 
-int launch_wgrad5(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st) {
+int launch_wgrad5(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStream_t st, int* slabs_out) {
   Wgrad5Params P;
   memset(&P, 0, sizeof(P));
   long long best = -1;
@@ -550,7 +568,14 @@ int launch_wgrad5(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
   P.dw = dw;
   const long long items = 3ll * P.m_tiles * P.ci_groups;
   const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  P.splits = pick_splits(items, chunks, 6);
+  const SplitPlan sp = plan_splits(items, chunks, 6, 6.0);
+  P.splits = sp.splits;
+  P.per = sp.per;
+  P.slab_stride = (long long)dy->c * 9 * x->c;
+  if (slabs_out) {
+    *slabs_out = P.splits;
+    return 0;
+  }
   P.nstage = Wgrad5Cfg::nstage(P.KH);
   P.stage_bytes = Wgrad5Cfg::stage_bytes(P.KH);
   P.g_bytes = Wgrad5Cfg::g_bytes(P.KH);
@@ -687,10 +712,8 @@ int ub_device_error(unsigned int* out_code) {
 void ub_set_option(int key, int value) {
   if (key == 1) g_wgrad_mode = value;
   if (key == 2) g_igemm2_mode = value;
-  if (key == 3) g_igemm3_mode = value;
-  if (key == 4) g_igemm3_dbg = value;
   if (key == 5) g_igemm_dbg = value;
-  if (key == 6) g_mask_l2_prefetch = value;
+  if (key == 7) g_map_cache_on = value;
 }
 
 void ub_set_prof_buffer(void* dev_ptr) { g_prof_buffer = reinterpret_cast<unsigned long long*>(dev_ptr); }
@@ -712,11 +735,12 @@ int ub_pack_weight(const float* w, void* dst, int mode, int cout, int cin, void*
 int ub_job_table_bytes(int n_jobs) { return (int)(n_jobs * sizeof(PackJob)); }
 
 int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* const* dst_a, void* const* dst_b,
-                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin) {
-  if (!table_host || n_jobs <= 0) return UB_E_ARG;
+                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin,
+                      const int* slabs, int* utile_begin_out) {
+  if (!table_host || n_jobs <= 0 || !slabs || !utile_begin_out) return UB_E_ARG;
   PackJob* t = reinterpret_cast<PackJob*>(table_host);
   long long begin = 0;
-  int tiles = 0;
+  int tiles = 0, utiles = 0;
   for (int i = 0; i < n_jobs; ++i) {
     t[i].w = (const float*)w[i];
     t[i].dst_a = (__nv_bfloat16*)dst_a[i];
@@ -727,12 +751,20 @@ int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* 
     t[i].cout = cout[i];
     t[i].cin = cin[i];
     t[i].elem_begin = begin;
-    begin += (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
-    if ((cout[i] % 32) || (cin[i] % 32)) return UB_E_SHAPE;
+    const long long numel = (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
+    begin += numel;
+    if ((cout[i] % 32) || (cin[i] % 32) || slabs[i] < 1) return UB_E_SHAPE;
     t[i].tile_begin = tiles;
     tiles += (cout[i] / 32) * (cin[i] / 32);
+    t[i].slabs = slabs[i];
+    t[i].slab_stride = numel;
+    t[i].lanes = slabs[i] >= 32 ? 8 : slabs[i] >= 16 ? 4 : slabs[i] >= 8 ? 2 : 1;
+    t[i].utile_begin = utiles;
+    utile_begin_out[i] = utiles;
+    utiles += (cout[i] / (8 / t[i].lanes)) * (cin[i] / 32);
   }
-  return tiles;  // >= 0: total tile count, to be passed back as `total`
+  utile_begin_out[n_jobs] = utiles;
+  return tiles;  // >= 0: total pack tile count, to be passed back as `total` of ub_pack_all
 }
 
 int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream) {
@@ -742,17 +774,19 @@ int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream
   return (int)cudaGetLastError();
 }
 
-int ub_unpack_all(const void* table_dev, int n_jobs, long long total, int accumulate, void* stream) {
-  if (!table_dev || n_jobs <= 0) return UB_E_ARG;
+int ub_unpack_range(const void* table_dev, int n_jobs, int tile_lo, int tile_hi, int accumulate, void* stream) {
+  if (!table_dev || n_jobs <= 0 || tile_lo < 0 || tile_hi <= tile_lo) return UB_E_ARG;
+  const long long total = tile_hi - tile_lo;
   const int grid = (int)(total < 16ll * num_sms() ? total : 16ll * num_sms());
-  unpack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, (int)total, accumulate);
+  unpack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, tile_lo, tile_hi, accumulate);
   return (int)cudaGetLastError();
 }
 
-int ub_unpack_grad(const float* packed, float* dw, int mode, int cout, int cin, int accumulate, void* stream) {
-  if (!packed || !dw || (mode != 0 && mode != 2)) return UB_E_ARG;
+int ub_unpack_grad(const float* slabs, int n_slabs, long long slab_stride, float* dw, int mode, int cout, int cin,
+                   int accumulate, void* stream) {
+  if (!slabs || !dw || (mode != 0 && mode != 2) || n_slabs < 1) return UB_E_ARG;
   const long long total = (long long)cout * cin * (mode == 0 ? 9 : 4);
-  unpack_grad_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(packed, dw, mode, cout, cin, accumulate);
+  unpack_grad_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(slabs, n_slabs, slab_stride, dw, mode, cout, cin, accumulate);
   return (int)cudaGetLastError();
 }
 
@@ -762,7 +796,6 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
   if ((e = check_view(x)) || (e = check_view(y))) return e;
   if (!w_fwd || !aligned16(w_fwd) || (bias && !aligned16(bias))) return w_fwd ? UB_E_ALIGN : UB_E_ARG;
   if (y->n != x->n || y->h != x->h - 2 || y->w != x->w - 2 || y->h <= 0 || y->w <= 0) return UB_E_SHAPE;
-  if (igemm3_eligible(x, y, true)) return launch_igemm3(x, w_fwd, bias, y, relu, nullptr, 0, (cudaStream_t)stream);
   if (igemm2_eligible(x, y)) return launch_igemm2(x, w_fwd, bias, y, relu, nullptr, 0, (cudaStream_t)stream);
   IgemmParams P;
   memset(&P, 0, sizeof(P));
@@ -808,7 +841,6 @@ int ub_conv3x3_fwd_head(const ub_tensor4* x, const void* w_fwd, const float* bia
     out.c = 64;
   }
   HeadArgs h{head_w, head_b, logits, argmax, y ? 1 : 0};
-  if (igemm3_eligible(x, &out, false)) return launch_igemm3(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, &h);
   return launch_igemm2(x, w_fwd, bias, &out, 1, nullptr, 0, (cudaStream_t)stream, &h);
 }
 
@@ -850,7 +882,6 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   if ((e = check_view(dy)) || (e = check_view(dx))) return e;
   if (!w_dgrad || !aligned16(w_dgrad)) return w_dgrad ? UB_E_ALIGN : UB_E_ARG;
   if (dx->n != dy->n || dx->h != dy->h + 2 || dx->w != dy->w + 2) return UB_E_SHAPE;
-  if (igemm3_eligible(dy, dx, false)) return launch_igemm3(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream);
   if (igemm2_eligible(dy, dx)) {
     *fused = dbias != nullptr;
     return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream, nullptr, nullptr, dbias, dbias_c0);
@@ -899,58 +930,114 @@ int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_te
                    dx->c - dbias_c0, dx->sx, stream);
 }
 
-int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream) {
-  int e;
-  if ((e = check_view(x)) || (e = check_view(dy))) return e;
-  if (!dw_packed || !aligned16(dw_packed)) return dw_packed ? UB_E_ALIGN : UB_E_ARG;
-  if (dy->n != x->n || dy->h != x->h - 2 || dy->w != x->w - 2) return UB_E_SHAPE;
-  // measured on B200 (profiles/r1_layer_table.log): the haloed-patch kernel wins while the input has few
-  // channels (dY is re-read Cin/32 times), the tap-per-CTA kernel wins for the deep, spatially small layers
-  // kernel choice measured per layer on B200 with wave-aware split-K (profiles/r1_layer_table_batch16_v3.log):
-  //   Cin <= 128                          : haloed patch, all nine taps, 32-channel tile (wgrad3)
-  //   Cout == 64                          : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
-  //   256-channel wide maps                : one tap row per CTA, N = 192 (wgrad5)
-  //   everything deeper                    : one tap per CTA, N = 256 (wgrad_kernel)
-  int mode = g_wgrad_mode;
-  if (mode == 3) {
-    if (dy->c == 64) mode = 5;                       // 64 output channels: shifted-dY trick (wgrad4)
-    else if (x->c <= 128) mode = 2;
-    else if (x->c <= 256 && dy->w >= 160) mode = 4;
-    else mode = 0;
-  }
-  if (mode == 5 && dy->c == 64) return launch_wgrad4(x, dy, dw_packed, (cudaStream_t)stream);
-  if (mode == 5) mode = 2;
-  if (mode == 4) return launch_wgrad5(x, dy, dw_packed, (cudaStream_t)stream);
-  if (mode == 1 || mode == 2) return launch_wgrad3(x, dy, dw_packed, (cudaStream_t)stream);
+// Deep-layer / up-conv weight gradient on the persistent tap-per-unit kernel (wgrad.cuh).  slabs_out != nullptr:
+// plan only (no tensor maps, no launch).
+static int g_last_plan[8];   // diagnostics: KW, KH, nstage, items, splits, per, BN, grid of the last generic wgrad plan
+static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int upconv, float* dw, cudaStream_t st,
+                                int* slabs_out) {
   WgradParams P;
   memset(&P, 0, sizeof(P));
-  pick_kpatch(dy->w, dy->h, P.KW, P.KH);
-  P.chunks_x = (dy->w + P.KW - 1) / P.KW;
-  P.chunks_y = (dy->h + P.KH - 1) / P.KH;
-  P.n_img = dy->n;
-  P.n_taps = 9;
-  for (int t = 0; t < 9; ++t) {
-    P.tap_amap[t] = 0;
-    P.tap_dx[t] = t % 3;
-    P.tap_dy[t] = t / 3;
-  }
-  P.Cout = dy->c;
-  P.Cin = x->c;
-  P.upconv_layout = 0;
-  P.dw = dw_packed;
+  const int W = upconv ? x->w : dy->w, H = upconv ? x->h : dy->h;   // the pixel space the reduction runs over
   const int BN = (g_force_bn > 0 && x->c % g_force_bn == 0) ? g_force_bn
                  : (x->c % 256 == 0)                        ? 256
                  : (x->c % 128 == 0)                        ? 128
                                                             : 64;
-  P.m_tiles = (dy->c + 127) / 128;
+  pick_kpatch(W, H, 2 + BN / 64, P.KW, P.KH);
+  P.ksteps = P.KW * P.KH / 16;
+  P.blk_bytes = P.KW * P.KH * 128;
+  P.stage_bytes = (2 + BN / 64) * P.blk_bytes;
+  P.nstage = WgradCfg::SMEM_LIMIT / P.stage_bytes;
+  if (P.nstage > WgradCfg::MAX_STAGES) P.nstage = WgradCfg::MAX_STAGES;
+  if (P.nstage < 2) return UB_E_SHAPE;
+  P.chunks_x = (W + P.KW - 1) / P.KW;
+  P.chunks_y = (H + P.KH - 1) / P.KH;
+  P.total_chunks = x->n * P.chunks_x * P.chunks_y;
+  P.upconv = upconv;
+  P.Cout = dy->c;
+  P.Cin = x->c;
+  P.m_rows = upconv ? 4 * dy->c : dy->c;
+  P.n_taps = upconv ? 1 : 9;
+  for (int t = 0; t < 9; ++t) {
+    P.tap_dx[t] = upconv ? 0 : t % 3;
+    P.tap_dy[t] = upconv ? 0 : t / 3;
+  }
+  P.m_tiles = (P.m_rows + 127) / 128;
   P.n_tiles = x->c / BN;
-  const long long items = (long long)P.n_taps * P.m_tiles * P.n_tiles;
-  const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  P.splits = pick_splits(items, chunks, 8);
-  if ((e = make_map4(&P.a_map[0], dy, P.KW, P.KH))) return e;
-  for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
+  P.items = P.n_taps * P.m_tiles * P.n_tiles;
+  const SplitPlan sp = plan_splits(P.items, P.total_chunks, 4, 2.0);
+  P.splits = sp.splits;
+  P.per = sp.per;
+  P.slab_stride = (long long)P.m_rows * P.n_taps * P.Cin;
+  {
+    const long long units = (long long)P.items * P.splits;
+    const int plan[8] = {P.KW, P.KH, P.nstage, P.items, P.splits, P.per, BN, (int)(units < num_sms() ? units : num_sms())};
+    memcpy(g_last_plan, plan, sizeof(plan));
+  }
+  if (slabs_out) {
+    *slabs_out = P.splits;
+    return 0;
+  }
+  P.dw = dw;
+  int e;
+  if (upconv) {
+    for (int ab = 0; ab < 4; ++ab) {
+      const int a = ab >> 1, b = ab & 1;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(dy->ptr) + a * dy->sy + b * dy->sx;
+      if ((e = make_map4(&P.a_map[ab], base, dy->c, x->w, x->h, x->n, 2 * dy->sx, 2 * dy->sy, dy->sn, P.KW, P.KH)))
+        return e;
+    }
+  } else {
+    if ((e = make_map4(&P.a_map[0], dy, P.KW, P.KH))) return e;
+    for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
+  }
   if ((e = make_map4(&P.b_map, x, P.KW, P.KH))) return e;
-  return launch_wgrad(P, BN, (cudaStream_t)stream);
+  const int smem_bytes = P.nstage * P.stage_bytes + WgradCfg::BAR_BYTES + 1024;
+  return launch_wgrad(P, BN, smem_bytes, st);
+}
+
+// kernel choice measured per layer on B200 (profiles/r1_layer_table_batch16_v3.log ... r2_*):
+//   Cout == 64                           : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
+//   Cin <= 128                           : haloed patch, all nine taps, 32-channel tile (wgrad3)
+//   256-channel wide maps                : one tap row per CTA, N = 192 (wgrad5)
+//   everything deeper                    : one tap per unit, N = 256, persistent (wgrad_kernel)
+static int conv3x3_wgrad_impl(const ub_tensor4* x, const ub_tensor4* dy, float* slabs, cudaStream_t st, int* slabs_out) {
+  int mode = g_wgrad_mode;
+  if (mode == 3) {
+    if (dy->c == 64) mode = 5;
+    else if (x->c <= 128) mode = 2;
+    else if (x->c <= 256 && dy->w >= 160) mode = 4;
+    else mode = 0;
+  }
+  if (mode == 5 && dy->c == 64) return launch_wgrad4(x, dy, slabs, st, slabs_out);
+  if (mode == 5) mode = 2;
+  if (mode == 4) return launch_wgrad5(x, dy, slabs, st, slabs_out);
+  if (mode == 1 || mode == 2) return launch_wgrad3(x, dy, slabs, st, slabs_out);
+  return launch_wgrad_generic(x, dy, 0, slabs, st, slabs_out);
+}
+
+int ub_wgrad_slabs(int kind, int n, int h_x, int w_x, int cin, int cout) {
+  if ((kind != 0 && kind != 2) || n <= 0 || h_x <= 0 || w_x <= 0 || cin <= 0 || cout <= 0 || (cin % 64) || (cout % 64))
+    return UB_E_SHAPE;
+  ub_tensor4 x{nullptr, n, h_x, w_x, cin, (long long)h_x * w_x * cin, (long long)w_x * cin, cin};
+  ub_tensor4 dy;
+  if (kind == 0) {
+    if (h_x < 3 || w_x < 3) return UB_E_SHAPE;
+    dy = ub_tensor4{nullptr, n, h_x - 2, w_x - 2, cout, (long long)(h_x - 2) * (w_x - 2) * cout, (long long)(w_x - 2) * cout, cout};
+  } else {
+    dy = ub_tensor4{nullptr, n, 2 * h_x, 2 * w_x, cout, 4ll * h_x * w_x * cout, 2ll * w_x * cout, cout};
+  }
+  int slabs = 0;
+  const int e = kind == 0 ? conv3x3_wgrad_impl(&x, &dy, nullptr, nullptr, &slabs)
+                          : launch_wgrad_generic(&x, &dy, 1, nullptr, nullptr, &slabs);
+  return e ? e : slabs;
+}
+
+int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream) {
+  int e;
+  if ((e = check_view(x)) || (e = check_view(dy))) return e;
+  if (!dw_slabs || !aligned16(dw_slabs)) return dw_slabs ? UB_E_ALIGN : UB_E_ARG;
+  if (dy->n != x->n || dy->h != x->h - 2 || dy->w != x->w - 2) return UB_E_SHAPE;
+  return conv3x3_wgrad_impl(x, dy, dw_slabs, (cudaStream_t)stream, nullptr);
 }
 
 int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, void* stream) {
@@ -1011,42 +1098,12 @@ int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tenso
   return launch_igemm(P, BN, (cudaStream_t)stream);
 }
 
-int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream) {
+int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream) {
   int e;
   if ((e = check_view(x)) || (e = check_view(dy))) return e;
-  if (!dw_packed || !aligned16(dw_packed)) return dw_packed ? UB_E_ALIGN : UB_E_ARG;
+  if (!dw_slabs || !aligned16(dw_slabs)) return dw_slabs ? UB_E_ALIGN : UB_E_ARG;
   if (dy->n != x->n || dy->h != 2 * x->h || dy->w != 2 * x->w) return UB_E_SHAPE;
-  WgradParams P;
-  memset(&P, 0, sizeof(P));
-  pick_kpatch(x->w, x->h, P.KW, P.KH);
-  P.chunks_x = (x->w + P.KW - 1) / P.KW;
-  P.chunks_y = (x->h + P.KH - 1) / P.KH;
-  P.n_img = x->n;
-  P.n_taps = 4;
-  for (int ab = 0; ab < 4; ++ab) {
-    const int a = ab >> 1, b = ab & 1;
-    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(dy->ptr) + a * dy->sy + b * dy->sx;
-    if ((e = make_map4(&P.a_map[ab], base, dy->c, x->w, x->h, x->n, 2 * dy->sx, 2 * dy->sy, dy->sn, P.KW, P.KH)))
-      return e;
-    P.tap_amap[ab] = ab;
-    P.tap_dx[ab] = 0;
-    P.tap_dy[ab] = 0;
-  }
-  P.Cout = dy->c;
-  P.Cin = x->c;
-  P.upconv_layout = 1;
-  P.dw = dw_packed;
-  const int BN = (g_force_bn > 0 && x->c % g_force_bn == 0) ? g_force_bn
-                 : (x->c % 256 == 0)                        ? 256
-                 : (x->c % 128 == 0)                        ? 128
-                                                            : 64;
-  P.m_tiles = (dy->c + 127) / 128;
-  P.n_tiles = x->c / BN;
-  const long long items = (long long)P.n_taps * P.m_tiles * P.n_tiles;
-  const long long chunks = (long long)P.n_img * P.chunks_x * P.chunks_y;
-  P.splits = pick_splits(items, chunks, 8);
-  if ((e = make_map4(&P.b_map, x, P.KW, P.KH))) return e;
-  return launch_wgrad(P, BN, (cudaStream_t)stream);
+  return launch_wgrad_generic(x, dy, 1, dw_slabs, (cudaStream_t)stream, nullptr);
 }
 
 int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y, int n, int h, int w_, void* stream) {
@@ -1356,6 +1413,9 @@ int ub_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr,
   return (int)cudaGetLastError();
 }
 
+#ifdef UB_DIAGNOSTICS
+void ub_last_wgrad_plan(int* out8) { memcpy(out8, g_last_plan, sizeof(g_last_plan)); }
+
 int ub_naive_conv3x3(const void* x, const void* w_fwd, const float* bias, float* y, int n, int h, int w_, int cin,
                      int cout, int relu, void* stream) {
   if (!x || !w_fwd || !y) return UB_E_ARG;
@@ -1492,5 +1552,7 @@ int ub_probe_run(int which, float* out_host, int cap) {
   cudaFree(dout);
   return nout > 0 ? 0 : UB_E_ARG;
 }
+
+#endif  // UB_DIAGNOSTICS
 
 }  // extern "C"

@@ -827,7 +827,11 @@ struct PackJob {
   int kind;                // 0 = 3x3 conv, 2 = 2x2 up-conv
   int cout, cin;
   long long elem_begin;    // prefix sum of element counts over the jobs
-  int tile_begin;          // prefix sum of 32x32-channel tile counts
+  int tile_begin;          // prefix sum of 32x32-channel tile counts (pack_all)
+  int slabs;               // split-K slabs the wgrad kernel of this layer leaves (unpack source = their sum)
+  int lanes;               // 1, 2, 4 or 8 slab lanes per unpack tile (CO_T = 8 / lanes channels per tile)
+  int utile_begin;         // prefix sum of unpack tile counts: (cout / CO_T) * (cin / 32)
+  long long slab_stride;   // elements between slabs
 };
 
 // Tiled through shared memory so that the fp32 side is read/written in long contiguous runs and the
@@ -890,53 +894,69 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int n_tiles,
-                                                         int accumulate) {
-  __shared__ float T[32 * 289];
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const PackJob jb = jobs[find_tile_job(jobs, n_jobs, tile)];
-    const int lt = tile - jb.tile_begin;
+// Gradient slabs -> torch layout, all layers (or a range of them) in one launch.  The wgrad kernels leave `slabs`
+// partial gradients per layer (deterministic split-K: split s stored slab s, `slab_stride` elements apart); this
+// kernel sums them IN FIXED ORDER and transposes packed -> torch layout through shared memory:
+//   conv    packed [co][t][ci]    -> dW[co][ci][t]    tile = CO_T co x 32 ci x 9 taps  (288 contiguous floats per co)
+//   up-conv packed [(ab,co)][ci]  -> dW[ci][co][ab]   tile = 32 ci x CO_T co x 4 taps
+// 256 threads = 32 ci x 8 rows; the 8 rows are CO_T channels x LANES slab lanes (CO_T * LANES = 8): lane l sums
+// slabs l, l + LANES, ... and the lanes are added in order, so layers with hundreds of slabs (the wide shallow
+// ones, whose K dimension is split across the whole chip) still expose enough parallel loads.
+__global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int tile_lo,
+                                                         int tile_hi, int accumulate) {
+  __shared__ float P[8 * 9 * 32];
+  const int ci = threadIdx.x & 31, y = threadIdx.x >> 5;
+  for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].utile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    const PackJob jb = jobs[lo];
+    const int lt = tile - jb.utile_begin;
     const int Cin = jb.cin, Cout = jb.cout;
+    const int lanes = jb.lanes, co_t = 8 / lanes;
+    const int ci_tiles = Cin >> 5;
+    const int co0 = (lt / ci_tiles) * co_t, ci0 = (lt % ci_tiles) * 32;
+    const int co = co0 + y / lanes, lane = y % lanes;
+    const int T = jb.kind == 0 ? 9 : 4;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      const float* src = jb.packed + (jb.kind == 0 ? ((long long)co * 9 + t) * Cin : ((long long)t * Cout + co) * Cin) + ci0 + ci;
+      float v = 0.0f;
+#pragma unroll 8
+      for (int s = lane; s < jb.slabs; s += lanes) v += __ldcg(src + (long long)s * jb.slab_stride);
+      P[(y * 9 + t) * 32 + ci] = v;
+    }
     __syncthreads();
     if (jb.kind == 0) {
-      const int ci_tiles = Cin >> 5;
-      const int co0 = (lt / ci_tiles) * 32, ci0 = (lt % ci_tiles) * 32;
-      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // packed [co][t][ci]: 32 contiguous ci per (co, t)
-        const int ci = e & 31, r = e >> 5;
-        const int t = r % 9, co = r / 9;
-        T[co * 289 + ci * 9 + t] = __ldg(jb.packed + ((long long)(co0 + co) * 9 + t) * Cin + ci0 + ci);
-      }
-      __syncthreads();
-      for (int e = threadIdx.x; e < 32 * 288; e += 256) {      // torch [co][ci][t]: 288 contiguous floats per co
-        const int co = e / 288, k = e - co * 288;
-        float* d = jb.dw + ((long long)(co0 + co) * Cin + ci0) * 9 + k;
-        const float v = T[co * 289 + k];
+      for (int e = threadIdx.x; e < co_t * 288; e += 256) {     // torch [co][ci][t]: 288 contiguous floats per co
+        const int c = e / 288, k = e - c * 288;
+        const int i = k / 9, t = k - i * 9;
+        float v = P[((c * lanes) * 9 + t) * 32 + i];
+        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * 32 + i];
+        float* d = jb.dw + ((long long)(co0 + c) * Cin + ci0) * 9 + k;
         *d = accumulate ? *d + v : v;
       }
     } else {
-      const int co_tiles = Cout >> 5;
-      const int ci0 = (lt / co_tiles) * 32, co0 = (lt % co_tiles) * 32;
-      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // packed [(ab,co)][ci]
-        const int ci = e & 31, r = e >> 5;
-        const int co = r & 31, ab = r >> 5;
-        T[ci * 129 + co * 4 + ab] = __ldg(jb.packed + ((long long)ab * Cout + co0 + co) * Cin + ci0 + ci);
-      }
-      __syncthreads();
-      for (int e = threadIdx.x; e < 32 * 128; e += 256) {      // torch [ci][co][ab]
-        const int ci = e >> 7, k = e & 127;
-        float* d = jb.dw + ((long long)(ci0 + ci) * Cout + co0) * 4 + k;
-        const float v = T[ci * 129 + k];
+      for (int e = threadIdx.x; e < 32 * co_t * 4; e += 256) {   // torch [ci][co][ab]: co_t * 4 contiguous floats per ci
+        const int i = e / (co_t * 4), k = e - i * (co_t * 4);
+        const int c = k >> 2, t = k & 3;
+        float v = P[((c * lanes) * 9 + t) * 32 + i];
+        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * 32 + i];
+        float* d = jb.dw + ((long long)(ci0 + i) * Cout + co0) * 4 + k;
         *d = accumulate ? *d + v : v;
       }
     }
   }
 }
 
-// Packed fp32 weight gradient (wgrad kernel layout) -> torch layout, scaled.
+// Packed fp32 weight-gradient slabs (wgrad kernel layout) -> torch layout, one layer, plain gather (tests / tools).
 //  mode 0 conv   : src[co][(r,s)][ci] -> dW[co][ci][r][s]
 //  mode 2 upconv : src[(a,b,co)][ci]  -> dW[ci][co][a][b]
-__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ src, float* __restrict__ dw,
-                                                          int mode, int Cout, int Cin, int accumulate) {
+__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ src, int slabs, long long slab_stride,
+                                                          float* __restrict__ dw, int mode, int Cout, int Cin,
+                                                          int accumulate) {
   const int T = (mode == 0) ? 9 : 4;
   const long long total = (long long)Cout * Cin * T;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -955,7 +975,8 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restric
       const int ci = (int)(r / Cout);
       s = ((long long)ab * Cout + co) * Cin + ci;
     }
-    const float v = __ldg(src + s);
+    float v = 0.0f;
+    for (int k = 0; k < slabs; ++k) v += __ldg(src + (long long)k * slab_stride + s);
     dw[i] = accumulate ? dw[i] + v : v;
   }
 }
@@ -993,6 +1014,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
   }
 }
 
+#ifdef UB_DIAGNOSTICS
 // Naive direct 3x3 valid conv on NHWC bf16 (fp32 accumulate): test-only comparator that
 // shares nothing with the tcgen05 path.  One thread per output element.
 __global__ void naive_conv3x3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wpk,
@@ -1017,5 +1039,6 @@ __global__ void naive_conv3x3_kernel(const __nv_bfloat16* __restrict__ x, const 
     y[i] = relu ? fmaxf(a, 0.0f) : a;
   }
 }
+#endif  // UB_DIAGNOSTICS
 
 }  // namespace ub

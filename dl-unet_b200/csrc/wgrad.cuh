@@ -1,90 +1,100 @@
-// Weight-gradient kernel (reference: the autograd reverse of network.py:131-190,
-// trainer.py:77).
+// Weight-gradient kernel of the deep 3x3 convolutions and of the 2x2 up-convolutions (reference: the
+// autograd reverse of network.py:131-190, trainer.py:77).
 //
-//   dW[co, tap, ci] = sum_{pixels p} dY[p, co] * X[p + tap_offset, ci]
+//   conv    : dW[co, tap, ci]     = sum_{pixels p} dY[p, co]      * X[p + tap_offset, ci]
+//   up-conv : dW[(a,b,co), ci]    = sum_{pixels p} dY[2p+(a,b), co] * X[p, ci]
 //
-// Both operands are NHWC, i.e. the reduction index (pixel) is the strided one and
-// the channel is contiguous: both are "MN-major" UMMA operands.  One 64-pixel
-// patch (KW x KH) of 64 channels is one TMA box = one 8 KB SWIZZLE_128B block
-// (64 rows of 128 B); M = 128 output channels = two such blocks LBO apart, N = BN
-// input channels = BN/64 blocks.  One CTA owns one (tap, co tile, ci tile, K split)
-// and reduces its share of pixel patches into one TMEM accumulator, then adds it
-// to the fp32 packed gradient with vector atomics (split-K).
+// Both operands are NHWC, i.e. the reduction index (pixel) is the strided one and the channel is
+// contiguous: both are "MN-major" UMMA operands.  A pixel chunk is a KW x KH patch of `rows` = KW*KH
+// pixels (any multiple of 16 up to 128, chosen per layer so that the patches tile the map with the
+// least padding); 64 channels of it are one TMA box = `rows` smem rows of 128 B (SWIZZLE_128B).
+// M = 128 rows of the gradient = two such blocks LBO apart, N = BN input channels = BN/64 blocks.
+//
+// Work unit = (item, K split): item = (tap, 128-row tile, BN-column tile) for the convolutions -- the
+// nine taps share dY, each reads X at its own offset -- and (128-row tile of the 4*Cout rows, column
+// tile) for the up-convolutions, where the four (a,b) phases are rows of M read through four stride-2
+// views of dY (Cout = 64: one tile holds two phases).  The kernel is PERSISTENT: CTA b runs units b,
+// b + grid, ... (item fastest, so the CTAs resident at one time walk the same pixel chunks and share
+// them in L2), with two TMEM accumulators so the read-out of unit i overlaps the MMAs of unit i+1.
+//
+// Deterministic split-K: every unit STORES its fp32 tile into its own slab, dw + split * slab_stride
+// (no atomics); the slabs are summed in fixed order by the unpack kernel that also converts the
+// packed layout to torch's (elementwise.cuh: unpack_all_kernel / unpack_grad_kernel).
 #pragma once
 #include "ptx.cuh"
 
 namespace ub {
 
 struct alignas(64) WgradParams {
-  CUtensorMap a_map[4];  // dY views (per tap for the up-convolution), box {64, KW, KH, 1}
+  CUtensorMap a_map[4];  // dY views (one per (a,b) phase for the up-convolution), box {64, KW, KH, 1}
   CUtensorMap b_map;     // X, box {64, KW, KH, 1}
-  int n_taps;
-  int tap_amap[9], tap_dx[9], tap_dy[9];
-  int m_tiles, n_tiles, splits;
-  int KW, KH;
-  int chunks_x, chunks_y, n_img;
+  int n_taps;            // conv: 9 (taps are items); up-conv: 1 (the phases are rows of M)
+  int tap_dx[9], tap_dy[9];
+  int upconv;            // 1: M rows = (ab, co), 64-row block -> a_map[ab]
+  int m_rows;            // Cout (conv) or 4 * Cout (up-conv)
+  int m_tiles, n_tiles, items, splits, per;  // per = pixel chunks per split (no split is empty)
+  int KW, KH, ksteps;    // ksteps = KW * KH / 16 MMAs per chunk
+  int chunks_x, chunks_y, total_chunks;
   int Cout, Cin;
-  int upconv_layout;  // 0: dw[(co*n_taps + tap)*Cin + ci]   1: dw[((tap*Cout) + co)*Cin + ci]
-  float* dw;
+  int nstage, stage_bytes, blk_bytes;  // pipeline geometry, chosen by the host: blk_bytes = KW*KH*128
+  float* dw;             // slabs [splits][packed layout]: conv [co][9][ci], up-conv [(ab,co)][ci]
+  long long slab_stride; // elements between slabs
 };
 
-template <int BN>
 struct WgradCfg {
-  static constexpr int A_BYTES = 2 * 8192;
-  static constexpr int B_BYTES = (BN / 64) * 8192;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MAX_STAGES = 8;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_LIMIT = 232448 - 1024;
-  static constexpr int NSTAGE_RAW = (SMEM_LIMIT - BAR_BYTES) / STAGE_BYTES;
-  static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_LIMIT = 232448 - 1024 - BAR_BYTES;
 };
+
+struct WgradUnit {
+  int split, tap, mt, nt;
+};
+__device__ __forceinline__ WgradUnit wgrad_unit(const WgradParams& p, int u) {
+  WgradUnit w;
+  w.split = u / p.items;
+  int r = u - w.split * p.items;
+  w.nt = r % p.n_tiles;
+  r /= p.n_tiles;
+  w.tap = r % p.n_taps;
+  w.mt = r / p.n_taps;
+  return w;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using C = WgradCfg<BN>;
+  using C = WgradCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
-  uint64_t* empty = full + C::NSTAGE;
-  uint64_t* tfull = empty + C::NSTAGE;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int NSTAGE = p.nstage, STAGE_BYTES = p.stage_bytes, BLK = p.blk_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+  uint64_t* empty = full + C::MAX_STAGES;
+  uint64_t* tfull = empty + C::MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // work item decode: split fastest so the CTAs of one (tap, tile) run together
-  int w = blockIdx.x;
-  const int split = w % p.splits;
-  w /= p.splits;
-  const int nt = w % p.n_tiles;
-  w /= p.n_tiles;
-  const int mt = w % p.m_tiles;
-  const int tap = w / p.m_tiles;
-
-  const int total_chunks = p.n_img * p.chunks_y * p.chunks_x;
-  const int per = (total_chunks + p.splits - 1) / p.splits;
-  const int c_begin = split * per;
-  const int c_end = min(total_chunks, c_begin + per);
-  const int n_iters = c_end - c_begin;  // may be <= 0 for a trailing split
-
-  const int m_valid_blocks = min(2, (p.Cout - mt * 128 + 63) / 64);
+  const int total_units = p.items * p.splits;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::NSTAGE; ++i) {
+    for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(tfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -92,78 +102,115 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (n_iters > 0) {
-    if (warp == 0) {
-      {
-        const CUtensorMap* am = &p.a_map[p.tap_amap[tap]];
-        const int dx = p.tap_dx[tap], dy = p.tap_dy[tap];
-        const uint32_t tx_bytes = (uint32_t)(m_valid_blocks + BN / 64) * 8192u;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int c = c_begin; c < c_end; ++c) {
-          const int cx = c % p.chunks_x;
-          int r = c / p.chunks_x;
-          const int cy = r % p.chunks_y;
-          const int img = r / p.chunks_y;
-          const int x0 = cx * p.KW, y0 = cy * p.KH;
-          mbar_wait(&empty[stage], phase ^ 1, 5);
-          if (elect_one()) {
-            uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            uint8_t* sb = sa + C::A_BYTES;
-            mbar_arrive_expect_tx(&full[stage], tx_bytes);
-            for (int b = 0; b < m_valid_blocks; ++b)
-              tma_load_4d(sa + b * 8192, am, &full[stage], mt * 128 + b * 64, x0, y0, img);
+  if (warp == 0) {
+    // ------------------------------------------------------- TMA producer (whole warp loops, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const WgradUnit w = wgrad_unit(p, u);
+      // the two 64-row blocks of this M tile: tensor map + channel coordinate
+      const int row_a = w.mt * 128, row_b = row_a + 64;
+      const int nblk = row_b < p.m_rows ? 2 : 1;
+      int map_a = 0, ch_a = row_a, map_b = 0, ch_b = row_b;
+      if (p.upconv) {
+        map_a = row_a / p.Cout;
+        ch_a = row_a - map_a * p.Cout;
+        map_b = (row_b / p.Cout) & 3;
+        ch_b = row_b - (row_b / p.Cout) * p.Cout;
+      }
+      const CUtensorMap* am_a = &p.a_map[map_a];
+      const CUtensorMap* am_b = &p.a_map[map_b];
+      const int dx = p.tap_dx[w.tap], dy = p.tap_dy[w.tap];
+      const uint32_t tx_bytes = (uint32_t)(nblk + BN / 64) * (uint32_t)BLK;
+      const int c_begin = w.split * p.per;
+      const int c_end = min(p.total_chunks, c_begin + p.per);
+      int cx = c_begin % p.chunks_x;
+      int r = c_begin / p.chunks_x;
+      int cy = r % p.chunks_y;
+      int img = r / p.chunks_y;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int x0 = cx * p.KW, y0 = cy * p.KH;
+        mbar_wait(&empty[stage], phase ^ 1, 5);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + 2 * BLK;
+          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          tma_load_4d(sa, am_a, &full[stage], ch_a, x0, y0, img);
+          if (nblk > 1) tma_load_4d(sa + BLK, am_b, &full[stage], ch_b, x0, y0, img);
 #pragma unroll
-            for (int b = 0; b < BN / 64; ++b)
-              tma_load_4d(sb + b * 8192, &p.b_map, &full[stage], nt * BN + b * 64, x0 + dx, y0 + dy, img);
-          }
-          __syncwarp();
-          if (++stage == C::NSTAGE) {
-            stage = 0;
-            phase ^= 1;
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(sb + b * BLK, &p.b_map, &full[stage], w.nt * BN + b * 64, x0 + dx, y0 + dy, img);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++cx == p.chunks_x) {
+          cx = 0;
+          if (++cy == p.chunks_y) {
+            cy = 0;
+            ++img;
           }
         }
       }
-    } else if (warp == 1) {
-      {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-        const uint32_t hiD = umma_desc_hi(1024);
-        const uint32_t loA0 = umma_desc_lo(smem_u32(smem), 8192), loB0 = umma_desc_lo(smem_u32(smem) + C::A_BYTES, 8192);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int i = 0; i < n_iters; ++i) {
-          mbar_wait(&full[stage], phase, 6);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t so = stage * (C::STAGE_BYTES >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // 16 pixels (K) per MMA = two 8-row groups = 2048 B (>>4 = 128)
-              umma_bf16(tmem_base, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + 128 * k), idesc,
-                        (i > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(&empty[stage]);
-            if (i == n_iters - 1) umma_commit(tfull);
-          }
-          __syncwarp();
-          if (++stage == C::NSTAGE) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    } else if (warp >= 4) {
-      const int q = warp - 4;
-      const int co = mt * 128 + q * 32 + lane;
-      mbar_wait(tfull, 0, 7);
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+    const uint32_t hiD = umma_desc_hi(1024);
+    // MN-major: LBO = distance between the 64-element M / N blocks, SBO = 1024 B between 8-row K groups
+    const uint32_t loA0 = umma_desc_lo(smem_u32(smem), (uint32_t)BLK);
+    const uint32_t loB0 = umma_desc_lo(smem_u32(smem) + 2 * BLK, (uint32_t)BLK);
+    const uint32_t stage16 = (uint32_t)STAGE_BYTES >> 4;
+    const int ksteps = p.ksteps;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const int split = u / p.items;
+      const int c_begin = split * p.per;
+      const int n_iters = min(p.total_chunks, c_begin + p.per) - c_begin;
+      const int acc = it & 1;
+      mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 8);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool valid = co < p.Cout;
-      float* drow = nullptr;
-      if (valid) {
-        const long long rowi = p.upconv_layout ? ((long long)tap * p.Cout + co) : ((long long)co * p.n_taps + tap);
-        drow = p.dw + rowi * p.Cin + nt * BN;
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int i = 0; i < n_iters; ++i) {
+        mbar_wait(&full[stage], phase, 6);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t so = stage * stage16;
+          // 16 pixels (K) per MMA = two 8-row groups = 2048 B (>>4 = 128)
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + 128 * k), idesc,
+                      (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (i == n_iters - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+    }
+  } else if (warp >= 4) {
+    // ----------------------------------------------------------- read-out: TMEM -> registers -> slab (plain stores)
+    const int q = warp - 4;
+    const int m = q * 32 + lane;  // accumulator row
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const WgradUnit w = wgrad_unit(p, u);
+      const int acc = it & 1;
+      const int row0 = (w.mt * 2 + (m >> 6)) * 64;  // first row of this thread's 64-row block
+      const bool valid = row0 < p.m_rows;
+      // conv: packed row = co * 9 + tap;  up-conv: packed row = (ab * Cout + co) = the M row itself
+      const long long prow = p.upconv ? (long long)(row0 + (m & 63)) : (long long)(row0 + (m & 63)) * p.n_taps + w.tap;
+      float* drow = p.dw + (long long)w.split * p.slab_stride + prow * p.Cin + w.nt * BN;
+      mbar_wait(&tfull[acc], (it >> 1) & 1, 7);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t v[32];
@@ -171,13 +218,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                   __uint_as_float(v[i + 3]));
-            atomicAdd(reinterpret_cast<float4*>(drow + j * 32 + i), a);
-          }
+          for (int i = 0; i < 32; i += 4)
+            __stcg(reinterpret_cast<float4*>(drow + j * 32 + i),
+                   make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                               __uint_as_float(v[i + 3])));
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -185,7 +233,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

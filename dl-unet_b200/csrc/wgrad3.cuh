@@ -32,7 +32,10 @@ struct alignas(64) Wgrad3Params {
   int Cout, Cin;
   int fuse_s;  // 1: one N=96 MMA per r (LBO = 64 B);  0: three N=32 MMAs per r (diagnostic fallback)
   int nstage, stage_bytes, g_bytes;  // pipeline geometry (depends on KH), chosen by the host
-  float* dw;   // [Cout][9][Cin] fp32, accumulated with vector atomics
+  int per;                // pixel chunks per split (no split is empty)
+  float* dw;              // slabs [splits][Cout][9][Cin] fp32: split s STORES its partial sums into slab s (deterministic;
+                          // the slabs are summed in fixed order by the unpack kernel)
+  long long slab_stride;  // elements between slabs
 };
 
 struct Wgrad3Cfg {
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3_kernel(const __grid_constant__ 
   const int split = w / p.m_tiles;
 
   const int total_chunks = p.n_img * p.chunks_y * p.chunks_x;
-  const int per = (total_chunks + p.splits - 1) / p.splits;
+  const int per = p.per;
   const int c_begin = split * per;
   const int c_end = min(total_chunks, c_begin + per);
   const int n_iters = c_end - c_begin;
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(256, 1) wgrad3_kernel(const __grid_constant__ 
         tmem_ld_32x32b_x32(t_addr + t * 32, v);   // columns (r*3+s)*32 .. +31
         tmem_ld_wait();
         if (valid) {
-          float* drow = p.dw + ((long long)co * 9 + t) * p.Cin + ct * 32;
+          float* drow = p.dw + (long long)split * p.slab_stride + ((long long)co * 9 + t) * p.Cin + ct * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
                                    __uint_as_float(v[i + 3]));
-            atomicAdd(reinterpret_cast<float4*>(drow + i), a);
+            __stcg(reinterpret_cast<float4*>(drow + i), a);
           }
         }
       }

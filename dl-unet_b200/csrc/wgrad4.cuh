@@ -27,7 +27,10 @@ struct alignas(64) Wgrad4Params {
   int ci_tiles, splits;
   int Cin;
   int nstage, stage_bytes, g_bytes;
-  float* dw;  // [64][9][Cin] fp32
+  int per;                // pixel chunks per split (no split is empty)
+  float* dw;              // slabs [splits][Cout][9][Cin] fp32: split s STORES its partial sums into slab s (deterministic;
+                          // the slabs are summed in fixed order by the unpack kernel)
+  long long slab_stride;  // elements between slabs
 };
 
 struct Wgrad4Cfg {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
   const int ct = blockIdx.x % p.ci_tiles;
   const int split = blockIdx.x / p.ci_tiles;
   const int total_chunks = p.n_img * p.chunks_y * p.chunks_x;
-  const int per = (total_chunks + p.splits - 1) / p.splits;
+  const int per = p.per;
   const int c_begin = split * per;
   const int c_end = min(total_chunks, c_begin + per);
   const int n_iters = c_end - c_begin;
@@ -160,12 +163,12 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
             tmem_ld_32x32b_x32(t_addr + r * 128 + sb * 64 + hh * 32, v);
             tmem_ld_wait();
             if (s < 3) {
-              float* drow = p.dw + ((long long)co * 9 + r * 3 + s) * p.Cin + ct * 64 + hh * 32;
+              float* drow = p.dw + (long long)split * p.slab_stride + ((long long)co * 9 + r * 3 + s) * p.Cin + ct * 64 + hh * 32;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
                                        __uint_as_float(v[i + 3]));
-                atomicAdd(reinterpret_cast<float4*>(drow + i), a);
+                __stcg(reinterpret_cast<float4*>(drow + i), a);
               }
             }
           }

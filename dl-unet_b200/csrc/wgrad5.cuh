@@ -26,7 +26,10 @@ struct alignas(64) Wgrad5Params {
   int m_tiles, ci_groups, splits;
   int Cout, Cin;
   int nstage, stage_bytes, g_bytes, x_block_bytes;
-  float* dw;  // [Cout][9][Cin] fp32
+  int per;                // pixel chunks per split (no split is empty)
+  float* dw;              // slabs [splits][Cout][9][Cin] fp32: split s STORES its partial sums into slab s (deterministic;
+                          // the slabs are summed in fixed order by the unpack kernel)
+  long long slab_stride;  // elements between slabs
 };
 
 struct Wgrad5Cfg {
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) wgrad5_kernel(const __grid_constant__ 
   const int split = w / p.m_tiles;
 
   const int total_chunks = p.n_img * p.chunks_y * p.chunks_x;
-  const int per = (total_chunks + p.splits - 1) / p.splits;
+  const int per = p.per;
   const int c_begin = split * per;
   const int c_end = min(total_chunks, c_begin + per);
   const int n_iters = c_end - c_begin;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256, 1) wgrad5_kernel(const __grid_constant__ 
       for (int b = 0; b < n_blocks; ++b) {
 #pragma unroll 1
         for (int s = 0; s < 3; ++s) {
-          float* drow = p.dw + ((long long)co * 9 + r * 3 + s) * p.Cin + cg * 128 + b * 64;
+          float* drow = p.dw + (long long)split * p.slab_stride + ((long long)co * 9 + r * 3 + s) * p.Cin + cg * 128 + b * 64;
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[32];
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(256, 1) wgrad5_kernel(const __grid_constant__ 
               for (int i = 0; i < 32; i += 4) {
                 float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
                                        __uint_as_float(v[i + 3]));
-                atomicAdd(reinterpret_cast<float4*>(drow + hh * 32 + i), a);
+                __stcg(reinterpret_cast<float4*>(drow + hh * 32 + i), a);
               }
             }
           }

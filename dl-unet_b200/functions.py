@@ -1,7 +1,8 @@
 """Drop-in for the reference's `functions.py` (same names, arguments, return types, and -- on
-purpose -- the same numerical quirks).  These are the CPU producers and
-consumers either side of the GPU hot path: weight maps feed the fused loss, the metrics read the
-masks back.  They are not kernels; GPU versions are the "next" rows f1 / f3 of SURVEY.md section 8.
+purpose -- the same numerical quirks).  Producers and consumers either side of
+the network: the weight maps that feed the fused loss run as device kernels (SURVEY.md 8 row f1,
+no host implementation here), the metrics reduce CUDA masks on the device (row f3) and keep the
+reference's two-line numpy formulas for CPU masks.
 
 Reference: functions.py:7-213.
 """
@@ -10,61 +11,33 @@ import torch
 
 from b200.geometry import input_size_compute as _input_size_compute
 
-try:  # OpenCV does the connected components / distance transform in the reference
-    import cv2 as _cv
-except Exception:  # pragma: no cover
-    _cv = None
+from b200 import weightmap as _wm
+
+
+def _on_device(gt_batch, fn):
+    """The weight maps are device kernels (csrc/weightmap.cuh); there is no host implementation.  A CPU label
+    batch -- what the reference's loaders yield (trainer.py:69,72) -- is uploaded to the current CUDA device, processed
+    there and returned on the CPU, so the call keeps the reference's signature and placement.
+    Size limit of the device kernels: H < 2048, W <= 2048 and H*W < 2^21 - 1 (RuntimeError otherwise)."""
+    if gt_batch.is_cuda:
+        return fn(gt_batch)
+    if not torch.cuda.is_available():
+        raise RuntimeError("functions.weighted_map / class_balance run on the B200 kernels: no CUDA device, no CPU path")
+    return fn(gt_batch.cuda()).cpu()
 
 
 def class_balance(gt_batch):
-    """functions.py:82-117: per-sample class-frequency weights, w[gt == v] = count(1) / count(v)
-    with `counts[1]` the SECOND unique value (IndexError on a single-class label, as upstream).
-    A CUDA label batch is processed on the device (b200.weightmap)."""
-    if gt_batch.is_cuda:
-        from b200 import weightmap as _wm
-        return _wm.class_balance(gt_batch)
-    w_batch = torch.empty(gt_batch.shape, dtype=torch.float32)
-    for b in range(gt_batch.shape[0]):
-        gt = gt_batch[b]
-        uval, counts = torch.unique(gt, return_counts=True)
-        w = torch.ones(gt.shape, dtype=torch.float32)
-        for pos in range(len(uval)):
-            w[gt == uval[pos]] = counts[1].float() / counts[pos].float()
-        w_batch[b] = w
-    return w_batch
+    """functions.py:82-117: per-sample class-frequency weights, w[gt == v] = count(1) / count(v) with `counts[1]` the
+    SECOND unique value (IndexError on a single-class label, as upstream).  Device kernels: b200.weightmap."""
+    return _on_device(gt_batch, _wm.class_balance)
 
 
 def weighted_map(gt_batch):
-    """functions.py:7-78: Ronneberger's w = w_c + w0 exp(-(d1+d2)^2 / (2 sigma^2)) on background
-    pixels, with the file's constants (w0 = 20, sigma^2 = 25), 4-connected components and exact L2
-    distance transforms.  w_c is held in the label's dtype, so an int64 label truncates the class
-    ratio exactly like the reference does (functions.py:37-40)."""
-    if gt_batch.is_cuda:   # device path: csrc/weightmap.cuh, same values (and quirks) without OpenCV or the host
-        from b200 import weightmap as _wm
-        return _wm.weighted_map(gt_batch)
-    if _cv is None:
-        raise RuntimeError("weighted_map needs OpenCV (cv2), as the reference does")
-    w0, sig2 = 20, 25
-    w_batch = torch.empty(gt_batch.shape, dtype=torch.float32)
-    for b in range(gt_batch.shape[0]):
-        gt = gt_batch[b]
-        uval, counts = torch.unique(gt.float(), return_counts=True)
-        w_c = torch.empty_like(gt)
-        for pos in range(len(uval)):
-            w_c[gt == uval[pos]] = counts[1].float() / counts[pos].float()
-        img = gt.reshape(gt.shape[0], -1).numpy()
-        n_obj, objects = _cv.connectedComponents(img.astype(np.uint8), connectivity=4)
-        maps = np.zeros([n_obj - 1, img.shape[0], img.shape[1]])
-        for i in range(n_obj - 1):
-            sep = (objects == i + 1).astype(np.float64)
-            # uint8(obj) - 1 wraps to 255 outside the object and is 0 inside it: distance to the object
-            maps[i] = _cv.distanceTransform(sep.astype(np.uint8) - 1, _cv.DIST_L2, maskSize=0)
-        maps = np.sort(maps, 0)
-        d1 = maps[0]
-        d2 = maps[1] if maps.shape[0] > 1 else 0
-        w_d = np.multiply(w0 * np.exp(-np.square(d1 + d2) / (2 * sig2)), -1 * (gt - 1))
-        w_batch[b] = (w_c + w_d).clone().detach()
-    return w_batch
+    """functions.py:7-78: Ronneberger's w = w_c + w0 exp(-(d1+d2)^2 / (2 sigma^2)) on background pixels, with the
+    file's constants (w0 = 20, sigma^2 = 25), 4-connected components and exact L2 distances to the two nearest
+    objects; w_c is truncated to an integer for integer labels, like the reference (functions.py:37-40).
+    Device kernels: b200.weightmap."""
+    return _on_device(gt_batch, _wm.weighted_map)
 
 
 def input_size_compute(image):

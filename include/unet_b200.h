@@ -47,12 +47,13 @@ int ub_device_error(unsigned int* out_code);
 void ub_set_prof_buffer(void* dev_ptr);
 /* Tuning overrides for experiments: <=0 restores the heuristic. */
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
-/* Experiment switches.  key 1: 3x3 wgrad kernel (0 = tap-per-CTA, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto [default], 4 = tap-row-per-CTA N=192, 5 = shifted-dY kernel for 64 output channels).
- * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default], 2 = wherever legal).
- * key 3: three-taps-per-instruction kernel for 64 -> 64 channel convs (0 = off, 1 = plain forward only [default], 2 = forward, dgrad and fused head).
- * key 4: igemm3 ablation bits (1 = no pixel shift-and-add, 2 = no staging / store, 4 = TMEM read-out only, 8 = a third of the MMAs, 16 = no patch loads after the first tile): timing experiments only, results are wrong.
+/* Experiment switches (A/B measurements; the defaults are the product configuration).
+ * key 1: 3x3 wgrad kernel (0 = persistent tap-per-unit kernel, 1 = haloed patch, 2 = haloed patch + fused s taps, 3 = auto
+ *        [default], 4 = tap-row-per-CTA N=192, 5 = shifted-dY kernel for 64 output channels).
+ * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default],
+ *        2 = wherever legal).
  * key 5: igemm ablation (1 = do not wait for earlier TMA stores): timing experiments only.
- * key 6: unused (was: TMA L2 prefetch of the ReLU-mask tiles, which now travel through shared memory). */
+ * key 7: host-side cache of encoded TMA tensor maps (1 = on [default], 0 = encode on every call). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------
@@ -61,17 +62,24 @@ void ub_set_option(int key, int value);
  * mode 2: ConvTranspose2d [Cin,Cout,2,2]  -> forward operand  [4*Cout][Cin]    bf16 (rows ordered a,b,co)
  * mode 3: ConvTranspose2d [Cin,Cout,2,2]  -> dgrad operand    [Cin][4*Cout]    bf16                      */
 int ub_pack_weight(const float* w, void* dst_bf16, int mode, int cout, int cin, void* stream);
-/* inverse of modes 0 / 2 for the fp32 packed gradient the wgrad kernels produce */
-int ub_unpack_grad(const float* packed, float* dw, int mode, int cout, int cin, int accumulate, void* stream);
+/* inverse of modes 0 / 2 for the fp32 gradient slabs the wgrad kernels produce: dw (torch layout) = (dw +) the sum,
+ * in slab order, of n_slabs packed partial gradients `slab_stride` elements apart (one layer, plain gather) */
+int ub_unpack_grad(const float* slabs, int n_slabs, long long slab_stride, float* dw, int mode, int cout, int cin,
+                   int accumulate, void* stream);
 
 /* All conv / up-conv layers in one launch.  A job table (ub_job_table_bytes(n) bytes) is filled on the host by
- * ub_job_table_fill (returns the total number of 32x32-channel tiles, or a negative error) from per-layer pointer
- * arrays and copied to the device by the caller; pass that tile count as `total`.  ub_pack_all writes both bf16 operands of every layer, ub_unpack_all the torch-layout gradients. */
+ * ub_job_table_fill from per-layer pointer arrays and copied to the device by the caller.  It returns the number of
+ * pack tiles (pass it as `total` to ub_pack_all; negative = error) and writes the n_jobs + 1 prefix sums of the
+ * UNPACK tiles to utile_begin_out.  `packed[i]` is layer i's slab workspace and slabs[i] = ub_wgrad_slabs(...) for the
+ * shape it is used with.  ub_pack_all writes both bf16 operands of every layer; ub_unpack_range(lo, hi) sums the
+ * slabs of the layers whose unpack tiles lie in [lo, hi) in fixed order and writes the torch-layout gradients
+ * (lo = utile_begin[i], hi = utile_begin[i + 1]: layer i alone; 0 .. utile_begin[n]: all layers). */
 int ub_job_table_bytes(int n_jobs);
 int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* const* dst_a, void* const* dst_b,
-                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin);
+                      const void* const* packed, void* const* dw, const int* kind, const int* cout, const int* cin,
+                      const int* slabs, int* utile_begin_out);
 int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream);
-int ub_unpack_all(const void* table_dev, int n_jobs, long long total, int accumulate, void* stream);
+int ub_unpack_range(const void* table_dev, int n_jobs, int tile_lo, int tile_hi, int accumulate, void* stream);
 
 /* ---- 3x3 valid convolution (nn.Conv2d(k=3) + F.relu; network.py:131-188) -------------
  * y[n,oy,ox,co] = act(bias[co] + sum_{r,s,ci} x[n,oy+r,ox+s,ci] * W[co,ci,r,s]);  y is (h-2)x(w-2). */
@@ -101,8 +109,14 @@ int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4
  * column-sum pass over dx otherwise. */
 int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                           float* dbias, int dbias_c0, void* stream);
-/* dw_packed[co][tap][ci] += sum_pixels dy * x   (fp32, caller zeroes it; split-K atomics) */
-int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream);
+/* Weight gradients are DETERMINISTIC: the reduction over pixels is split over CTAs (split-K), every split STORES
+ * its fp32 partial sums into its own slab and the slabs are added in fixed order by ub_unpack_range / ub_unpack_grad
+ * (no atomics anywhere; two runs give bit-identical gradients).
+ * ub_wgrad_slabs: number of slabs the wgrad of this shape writes (kind 0: 3x3 conv, x is h_x x w_x, dy two smaller;
+ * kind 2: 2x2 up-conv, dy twice as large); depends on the shape and the SM count only.  Negative = error.
+ * dw_slabs: fp32 [slabs][Cout][9][Cin] (conv) or [slabs][(a,b,co)][Cin] (up-conv), fully overwritten. */
+int ub_wgrad_slabs(int kind, int n, int h_x, int w_x, int cin, int cout);
+int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream);
 
 /* ---- 2x2 stride-2 up-convolution (nn.ConvTranspose2d(k=2,s=2); network.py:159,167,175,183) ----
  * y[n,2i+a,2j+b,co] = bias[co] + sum_ci x[n,i,j,ci] * W[ci,co,a,b]; y is normally the upper channel
@@ -110,7 +124,7 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed
 int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, void* stream);
 int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                        void* stream);
-int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_packed, void* stream);
+int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream);
 
 /* ---- first convolution, Cin = 1 (network.py:131), fp32 NCHW image in, bf16 NHWC out, bias+ReLU fused ---- */
 int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y_bf16, int n, int h, int w_,
@@ -198,12 +212,6 @@ int ub_colsum(const void* g_bf16, float* out, long long n_pix, int c, long long 
 /* ---- optim.SGD(lr, momentum=0.99).step() over a flat arena (trainer.py:30,78) ---- */
 int ub_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,
                     void* stream);
-
-/* ---- test-only comparators / probes (never on the product path) ---- */
-int ub_naive_conv3x3(const void* x_bf16, const void* w_fwd, const float* bias, float* y_f32, int n, int h, int w_,
-                     int cin, int cout, int relu, void* stream);
-/* Runs the descriptor-semantics probes; writes up to `cap` floats of results to host `out`. */
-int ub_probe_run(int which, float* out_host, int cap);
 
 #ifdef __cplusplus
 }

@@ -126,7 +126,7 @@ def sec_conv_wgrad():
         wt = torch.zeros(cout, cin, 3, 3, device=DEV, requires_grad=True)
         F.conv2d(xq, wt).backward(bf(dy).float())
         ref = wt.grad
-        dwp = torch.zeros(cout, 9 * cin, dtype=torch.float32, device=DEV)
+        dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout)
         ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp)
         dw = torch.empty_like(ref)
         ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
@@ -148,7 +148,7 @@ def sec_wgrad_modes():
         xh, dyh = nhwc(x), nhwc(dy)
         for mode in (0, 1, 2, 4, 5):
             ops.set_option(1, mode)
-            dwp = torch.zeros(cout, 9 * cin, dtype=torch.float32, device=DEV)
+            dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, xh, cout)
             ops.conv3x3_wgrad(xh, dyh, dwp)
             dw = torch.empty_like(ref)
             ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
@@ -245,7 +245,7 @@ def sec_upconv():
         # wgrad
         wz = torch.zeros(cin, cout, 2, 2, device=DEV, requires_grad=True)
         F.conv_transpose2d(bf(x).float(), wz, stride=2).backward(nchw(dyv))
-        dwp = torch.zeros(4 * cout, cin, dtype=torch.float32, device=DEV)
+        dwp = ops.wgrad_workspace(ops.PACK_UP_FWD, nhwc(x), cout)
         ops.upconv2x2_wgrad(nhwc(x), dyv, dwp)
         dw = torch.empty_like(wz)
         ops.unpack_grad(dwp, dw, ops.PACK_UP_FWD)

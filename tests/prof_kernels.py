@@ -9,7 +9,8 @@ import torch  # noqa: E402
 from b200 import ops  # noqa: E402
 
 DEV = "cuda:0"
-CASES = {"wg52": (16, 30, 1024, 1024), "wg12": (16, 570, 64, 64), "wg22": (16, 282, 128, 128),
+CASES = {"wg52": (16, 30, 1024, 1024), "wg42": (16, 66, 512, 512), "wg41": (16, 68, 256, 512), "wg41e": (16, 56, 1024, 512),
+         "fw52": (16, 30, 1024, 1024), "fw41e": (16, 56, 1024, 512), "wg12": (16, 570, 64, 64), "wg22": (16, 282, 128, 128),
          "fw12": (16, 570, 64, 64), "fw42": (16, 66, 512, 512), "fw22": (16, 282, 128, 128),
          "fwA": (16, 200, 64, 64), "fwB": (16, 200, 128, 128),
          "dg12": (16, 570, 64, 64), "dg11e": (16, 392, 128, 64), "up1": (16, 196, 128, 64), "up1d": (16, 196, 128, 64)}
@@ -47,8 +48,9 @@ elif case.startswith("up"):
     e1.record()
 elif case.startswith("wg"):
     dy = torch.randn(n, h - 2, h - 2, cout, device=DEV).to(torch.bfloat16)
-    dwp = torch.zeros(cout, 9 * cin, device=DEV)
     ops.set_option(1, mode)
+    dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, x, cout)
+    print("slabs", dwp.shape[0])
     ops.conv3x3_wgrad(x, dy, dwp)
     torch.cuda.synchronize()
     e0.record()

@@ -41,20 +41,24 @@ for (name, kind, cin, cout) in LAYERS:
         dy, dx = rnd(B, hout, hout, cout), torch.empty(B, hin, hin, cin, dtype=torch.bfloat16, device=DEV)
         wf, wd = rnd(cout, 9 * cin) / 30, rnd(cin, 9 * cout) / 30
         bias = torch.zeros(cout, device=DEV)
-        dwp = torch.zeros(cout, 9 * cin, device=DEV)
         fl = 2.0 * B * hout * hout * cin * cout * 9
+
+        def wg():   # the slab count depends on the kernel the current option selects
+            dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, x, cout)
+            return timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+
         t_f = timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y))
         t_d = timeit(lambda: ops.conv3x3_dgrad(dy, wd, dx, x))
         ops.set_option(1, 0)
-        t_w0 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        t_w0 = wg()
         ops.set_option(1, 2)
-        t_w2 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        t_w2 = wg()
         ops.set_option(1, 4)
-        t_w5 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        t_w5 = wg()
         ops.set_option(1, 5)
-        t_w4 = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp)) if cout == 64 else 0.0
+        t_w4 = wg() if cout == 64 else 0.0
         ops.set_option(1, 3)
-        t_auto = timeit(lambda: ops.conv3x3_wgrad(x, dy, dwp))
+        t_auto = wg()
     elif kind == "up":
         lvl = int(name[-1])
         hin = g.up[lvl] // 2
@@ -63,7 +67,7 @@ for (name, kind, cin, cout) in LAYERS:
         dx = torch.empty(B, hin, hin, cin, dtype=torch.bfloat16, device=DEV)
         wf, wd = rnd(4 * cout, cin) / 30, rnd(cin, 4 * cout) / 30
         bias = torch.zeros(cout, device=DEV)
-        dwp = torch.zeros(4 * cout, cin, device=DEV)
+        dwp = ops.wgrad_workspace(ops.PACK_UP_FWD, x, cout)
         fl = 2.0 * B * hin * hin * cin * cout * 4
         t_f = timeit(lambda: ops.upconv2x2_fwd(x, wf, bias, cat[..., cout:]))
         t_d = timeit(lambda: ops.upconv2x2_dgrad(dcat[..., cout:], wd, dx, x))
@@ -92,17 +96,3 @@ t_inf = timeit(lambda: ops.conv3x3_fwd_head(x, wf, bias, None, hw, hb, None, am)
 print(f"conv12e+head: conv {t_plain:.1f} us + head {t_head:.1f} us = {t_plain + t_head:.1f} us; fused (train) {t_fused:.1f} us; "
       f"fused, no activation store, argmax only (inference) {t_inf:.1f} us")
 
-# 64 -> 64 layers: three-taps-per-instruction kernel (igemm3, option 3 = 1) vs the haloed-patch kernel (igemm2, option 3 = 0)
-for name, hout in (("conv12c", 568), ("conv12e", 388)):
-    x, y = rnd(B, hout + 2, hout + 2, 64), torch.empty(B, hout, hout, 64, dtype=torch.bfloat16, device=DEV)
-    dy, dx = rnd(B, hout, hout, 64), torch.empty(B, hout + 2, hout + 2, 64, dtype=torch.bfloat16, device=DEV)
-    wf, wd = rnd(64, 9 * 64) / 30, rnd(64, 9 * 64) / 30
-    bias = torch.zeros(64, device=DEV)
-    fl = 2.0 * B * hout * hout * 64 * 64 * 9
-    res = {}
-    for mode in (0, 2):
-        ops.set_option(3, mode)
-        res[mode] = (timeit(lambda: ops.conv3x3_fwd(x, wf, bias, y)), timeit(lambda: ops.conv3x3_dgrad(dy, wd, dx, x)))
-    ops.set_option(3, 1)
-    print(f"{name}: fwd igemm2 {res[0][0]:.1f} us ({fl / res[0][0] / 1e6:.0f} TF/s) -> igemm3 {res[2][0]:.1f} us ({fl / res[2][0] / 1e6:.0f} TF/s); "
-          f"dgrad igemm2 {res[0][1]:.1f} us -> igemm3 {res[2][1]:.1f} us ({fl / res[2][1] / 1e6:.0f} TF/s)")

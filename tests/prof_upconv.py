@@ -22,7 +22,7 @@ dx = torch.empty(B, hin, hin, cin, dtype=torch.bfloat16, device=dev)
 wf = torch.randn(4 * cout, cin, device=dev).to(torch.bfloat16) / 30
 wd = torch.randn(cin, 4 * cout, device=dev).to(torch.bfloat16) / 30
 bias = torch.zeros(cout, device=dev)
-dwp = torch.zeros(4 * cout, cin, device=dev)
+dwp = ops.wgrad_workspace(ops.PACK_UP_FWD, x, cout)
 
 
 def timeit(fn, reps=10):

@@ -26,7 +26,7 @@ x = torch.randn(1, 20, 36, 128, device=dev).to(torch.bfloat16)
 dy = torch.randn(1, 18, 34, 64, device=dev).to(torch.bfloat16)
 for mode in (0, 1, 2, 4, 5):
     ops.set_option(1, mode)
-    ops.conv3x3_wgrad(x, dy, torch.zeros(64, 9 * 128, device=dev))
+    ops.conv3x3_wgrad(x, dy, ops.wgrad_workspace(ops.PACK_CONV_FWD, x, 64))
 ops.set_option(1, 3)
 for mode in (0, 2):
     ops.set_option(2, mode)

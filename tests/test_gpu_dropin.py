@@ -125,3 +125,32 @@ def test_async_checkpoint_equals_torch_save(tmp_path):
     assert not torch.equal(ref["conv12c.weight"], net.state_dict()["conv12c.weight"].cpu())   # weights did move on
     fresh = Unet()
     fresh.load_state_dict(got)
+
+
+def test_eval_after_graph_replay_uses_current_weights():
+    """A CUDA-graph replay updates the fp32 masters without running any Python: the bf16 operand caches must be
+    re-derived before the next forward outside the graph (trainer.py:95-121 validates after every epoch).  step, eval,
+    step, eval -- the second eval must equal a forward of a fresh module loaded with the current state_dict."""
+    import unet_oracle as O
+    from network import Unet
+    from b200 import train as T
+    torch.manual_seed(8)
+    net = Unet().to(DEV)
+    images, labels, weight = (t.to(DEV) for t in O.synthetic_batch(1, 220, seed=5))
+    step = T.TrainStep(net, T.FusedSGD(net), graph=True)
+    for _ in range(3):                       # eager first step, capture, first replay
+        step(images, labels, weight)
+    with torch.no_grad():
+        ev1 = net(images).clone()
+    step(images, labels, weight)             # replay: masters move, no Python between pack_all and sgd
+    with torch.no_grad():
+        ev2 = net(images).clone()
+        mask2 = net.predict(images)
+    fresh = Unet()
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in net.state_dict().items()})
+    fresh.to(DEV)
+    with torch.no_grad():
+        want = fresh(images)
+    assert torch.equal(ev2, want)
+    assert torch.equal(mask2, want.argmax(1))
+    assert not torch.equal(ev1, ev2)         # the step did change the weights

@@ -63,11 +63,46 @@ def test_conv3x3_fwd_dgrad_wgrad(ops, shape):
     assert rel_l2(nchw(dx), gx) < BF16_OUT_TOL
     ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))   # fused ReLU backward
     assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
-    dwp = torch.zeros(cout, 9 * cin, device=DEV)
+    # split-K slabs are stored, never accumulated: a NaN-filled workspace must come back fully overwritten, and two
+    # runs must agree bit for bit (no atomics)
+    dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
     ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp)
     dw = torch.empty_like(wt)
     ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
     assert rel_l2(dw, gw) < FP32_TOL
+    dwp2 = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
+    ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp2)
+    assert torch.equal(dwp, dwp2)
+    dw2 = dw.clone()
+    ops.unpack_grad(dwp2, dw2, ops.PACK_CONV_FWD, accumulate=True)
+    assert torch.equal(dw2, dw + dw)
+
+
+# shapes that reach every weight-gradient kernel and its edge cases: the persistent tap-per-unit kernel with several
+# units per CTA and both accumulators in use (items x splits > 148), a last M tile of one 64-row block (Cout = 320),
+# N tiles of 64 / 128 / 256, maps that no chunk shape tiles exactly; the tap-row kernel (Cin = 256, wide maps); the
+# haloed-patch kernel with two co blocks; the shifted-dY kernel (Cout = 64) with Cin = 128
+WGRAD_SHAPES = [(4, 30, 30, 512, 512), (2, 58, 58, 1024, 512), (3, 22, 38, 256, 256), (2, 20, 20, 192, 320),
+                (2, 68, 68, 256, 512), (1, 36, 164, 256, 128), (1, 40, 170, 256, 256), (2, 50, 66, 128, 256),
+                (2, 90, 90, 128, 64), (16, 30, 30, 1024, 1024)]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_conv3x3_wgrad_shapes(ops, shape):
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = bf(torch.randn(n, cin, h, w, device=DEV).clamp_min(0))
+    dy = bf(torch.randn(n, cout, h - 2, w - 2, device=DEV))
+    wt = torch.zeros(cout, cin, 3, 3, device=DEV, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv2d(x.float(), wt), wt, dy.float())
+    dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
+    ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp)
+    dw = torch.empty(cout, cin, 3, 3, device=DEV)
+    ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
+    assert rel_l2(dw, gw) < FP32_TOL
+    dwp2 = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
+    ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp2)
+    assert torch.equal(dwp, dwp2)
 
 
 @pytest.mark.parametrize("shape", [(1, 6, 6, 64), (2, 45, 37, 64), (1, 70, 70, 128), (3, 20, 26, 64)])
@@ -102,39 +137,6 @@ def test_conv3x3_fwd_fused_head(ops, shape):
     am2 = torch.full_like(am, 7)
     ops.conv3x3_fwd_head(nhwc(x), wp, b, None, hw, hb, None, am2)      # argmax only
     assert torch.equal(am2, am)
-
-
-@pytest.mark.parametrize("shape", [(1, 20, 20), (2, 70, 70), (1, 5, 3), (2, 33, 64), (1, 131, 47)])
-def test_igemm3_three_taps_per_instruction(ops, shape):
-    """igemm3.cuh (N = 192: the three taps of a kernel row in one tcgen05.mma, shift-and-add across pixels in the
-    epilogue) on every path it supports -- forward, dgrad with fused ReLU backward, fused head -- against the same
-    torch references as the default kernels; option 3 = 2 routes all 64 -> 64 convs through it."""
-    n, h, w = shape
-    ops.set_option(3, 2)
-    try:
-        torch.manual_seed(sum(shape))
-        x = torch.randn(n, 64, h, w, device=DEV).clamp_min(0)
-        wt = torch.randn(64, 64, 3, 3, device=DEV) / 24
-        b = torch.randn(64, device=DEV)
-        xq, wq = bf(x).float(), bf(wt).float()
-        act = F.relu(F.conv2d(xq, wq, b))
-        y = torch.full((n, h - 2, w - 2, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
-        wp = ops.pack_weight(wt, ops.PACK_CONV_FWD)
-        ops.conv3x3_fwd(nhwc(x), wp, b, y, relu=True)
-        assert rel_l2(nchw(y), act) < BF16_OUT_TOL
-        dy = torch.randn(n, 64, h - 2, w - 2, device=DEV)
-        gx = F.conv_transpose2d(bf(dy).float(), wq)
-        dx = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
-        ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))
-        assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
-        hw, hb = torch.randn(2, 64, 1, 1, device=DEV) / 8, torch.randn(2, device=DEV)
-        logits = torch.full((n, 2, h - 2, w - 2), float("nan"), device=DEV)
-        am = torch.full((n, h - 2, w - 2), 7, dtype=torch.uint8, device=DEV)
-        ops.conv3x3_fwd_head(nhwc(x), wp, b, None, hw, hb, logits, am)
-        assert rel_l2(logits, F.conv2d(act, hw, hb)) < FP32_TOL
-        assert torch.equal(am.long(), (logits[:, 1] > logits[:, 0]).long())
-    finally:
-        ops.set_option(3, 1)
 
 
 @pytest.mark.parametrize("case", [(2, 18, 18, 64, 64, 12), (1, 34, 26, 64, 128, 20), (1, 70, 70, 128, 128, 8), (2, 23, 31, 64, 64, 9),
@@ -213,7 +215,8 @@ def test_conv3x3_strided_views_write_in_place(ops):
     assert bool((out[..., :128] == 0).all()) and bool((out[..., 256:] == 0).all())   # neighbours untouched
 
 
-@pytest.mark.parametrize("shape", [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256)])
+@pytest.mark.parametrize("shape", [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256),
+                                   (6, 28, 28, 1024, 512), (2, 98, 98, 128, 64)])
 def test_upconv2x2(ops, shape):
     n, h, w, cin, cout = shape
     torch.manual_seed(sum(shape))
@@ -233,11 +236,14 @@ def test_upconv2x2(ops, shape):
     dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt, ops.PACK_UP_DGRAD), dx, nhwc(x))
     assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
-    dwp = torch.zeros(4 * cout, cin, device=DEV)
+    dwp = ops.wgrad_workspace(ops.PACK_UP_FWD, nhwc(x), cout, fill=float("nan"))
     ops.upconv2x2_wgrad(nhwc(x), dyv, dwp)
     dw = torch.empty_like(wt)
     ops.unpack_grad(dwp, dw, ops.PACK_UP_FWD)
     assert rel_l2(dw, gw) < FP32_TOL
+    dwp2 = ops.wgrad_workspace(ops.PACK_UP_FWD, nhwc(x), cout, fill=float("nan"))
+    ops.upconv2x2_wgrad(nhwc(x), dyv, dwp2)
+    assert torch.equal(dwp, dwp2)                                   # deterministic split-K
 
 
 def test_pack_modes_exact(ops):
@@ -432,3 +438,37 @@ def test_guard_bands_untouched(ops):
     ops.upconv2x2_fwd(x, bf(torch.randn(4 * cout, cin, device=DEV) / 12), torch.zeros(cout, device=DEV), cat[..., cout:])
     assert guards_ok(big, n, 2 * h, 2 * w, 2 * cout)
     assert bool((cat[..., :cout] == SENT).all()) and not bool((cat[..., cout:] == SENT).any())
+
+
+@pytest.mark.parametrize("n_slabs", [1, 3, 9, 20, 75])
+def test_unpack_range_sums_slabs_in_fixed_order(ops, n_slabs):
+    """ops.JobTable.unpack_* (unpack_all_kernel): the per-layer slabs the wgrad kernels leave are summed and transposed
+    to torch layout, one layer or all layers per launch, with 1 / 2 / 4 / 8 slab lanes per tile depending on the slab
+    count.  Against the plain gather kernel (ub_unpack_grad) on random slabs; bit-identical from run to run."""
+    torch.manual_seed(n_slabs)
+    layers = [(0, 128, 64), (2, 64, 128), (0, 64, 192)]            # (kind, cout, cin)
+    entries, refs = [], []
+    for kind, cout, cin in layers:
+        taps = 9 if kind == 0 else 4
+        shape = (cout, cin, 3, 3) if kind == 0 else (cin, cout, 2, 2)
+        slabs = torch.randn(n_slabs, cout * taps * cin, device=DEV)
+        dw = torch.full(shape, float("nan"), device=DEV)
+        w = torch.zeros(shape, device=DEV)
+        fa = torch.empty(cout * taps * cin, dtype=torch.bfloat16, device=DEV)
+        fb = torch.empty_like(fa)
+        entries.append((w, fa, fb, slabs, dw, kind, cout, cin, n_slabs))
+        ref = torch.empty(shape, device=DEV)
+        ops.unpack_grad(slabs, ref, kind)
+        refs.append(ref)
+    table = ops.JobTable(entries, DEV)
+    table.unpack_layer(1)
+    assert torch.isnan(entries[0][4]).all() and torch.isnan(entries[2][4]).all()       # only layer 1 was written
+    torch.testing.assert_close(entries[1][4], refs[1], rtol=1e-5, atol=1e-5)
+    table.unpack_all()
+    first = [e[4].clone() for e in entries]
+    for got, ref in zip(first, refs):
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    table.unpack_all()
+    assert all(torch.equal(e[4], f) for e, f in zip(entries, first))                    # deterministic
+    table.unpack_all(accumulate=True)
+    assert all(torch.equal(e[4], f + f) for e, f in zip(entries, first))

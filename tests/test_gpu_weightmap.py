@@ -163,3 +163,18 @@ def test_segment_image_equals_per_tile_forward():
     for idx, m in parts:
         full[idx] = m
     assert torch.equal(full, ref)
+
+
+def test_drop_in_functions_cpu_labels_go_through_the_device(golden_dir):
+    """dl-unet_b200/functions.py keeps the reference's call placement (trainer.py:69,72 pass CPU labels): a CPU label
+    batch is uploaded, processed by the kernels and returned on the CPU -- equal to the reference's golden outputs."""
+    import functions
+    import weightmap_oracle as W
+    g = np.load(os.path.join(golden_dir, "class_balance.npz"))
+    out = functions.class_balance(torch.from_numpy(g["lab"]))
+    assert not out.is_cuda and np.array_equal(out.numpy(), g["w"])
+    g = np.load(os.path.join(golden_dir, "weightmap_blobs_96.npz"))
+    lab = torch.from_numpy(W.synthetic_labels(int(g["batch"]), int(g["size"]), int(g["seed"]), str(g["kind"])))
+    w = functions.weighted_map(lab)
+    assert not w.is_cuda and float(np.abs(w.numpy() - g["w_i64"]).max()) <= 2.5e-6
+    assert functions.weighted_map(lab.to(DEV)).is_cuda
