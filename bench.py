@@ -231,6 +231,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cudnn"])
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="override the BASELINE batch (diagnostics only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock torch + cuDNN arm (N = 1)")
+    ap.add_argument("--no-inference", action="store_true", help="skip the overlap-tile inference measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -272,7 +274,8 @@ def main():
     # one-hot + weighted BCE, backward, SGD-momentum) as one call -- what dl-unet_b200/trainer.py::training runs per
     # batch.  On one GPU it replays a CUDA graph of the step; with the all-reducer attached (N > 1) it issues the
     # same kernel schedule eagerly so that the gradient buckets can be reduced while backward runs.
-    tstep = T.TrainStep(net, opt, kind="bce", graph=(world == 1), global_batch=gb)
+    dp_graph = world > 1 and os.environ.get("UB_DP_GRAPH", "0") == "1"     # experiment: capture the step incl. the all-reduces
+    tstep = T.TrainStep(net, opt, kind="bce", graph=(world == 1 or dp_graph), global_batch=gb, graph_with_allreduce=dp_graph)
     tstep_eager = T.TrainStep(net, opt, kind="bce", graph=False, global_batch=gb)
 
     def step(img, lab, wmap):
@@ -324,7 +327,45 @@ def main():
     barrier()
     ops.STATS.timing = False
     launches = ops.STATS.launches
-    fam = ops.STATS.summarize()
+    fam_all = ops.STATS.summarize()
+    fam_ig = ops.STATS.summarize("igemm").get("igemm", (0.0, 0.0, 1e-9, 0))
+    fam_wg = ops.STATS.summarize("wgrad").get("wgrad", (0.0, 0.0, 1e-9, 0))
+
+    # ---- where the time goes at N > 1: the same per-GPU batch without the exchange step (reducer detached: eager
+    # schedule, and as the CUDA-graph replay a single GPU would run), against the timed region above
+    breakdown = None
+    if world > 1:
+        def timed(fn, n):
+            for _ in range(2):
+                fn(d_img, d_lab, d_w)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn(d_img, d_lab, d_w)
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / n
+
+        reducer.detach()
+        kb = max(3, min(K, 10))
+        t_eager = timed(tstep_eager, kb)
+        tgraph = T.TrainStep(net, opt, kind="bce", graph=True, global_batch=gb)
+        t_graph = timed(tgraph, kb)
+        tgraph.graphs.clear()
+        reducer.attach()
+        reducer.broadcast_parameters(0)
+        t_total = ms / K
+        breakdown = {"ms_per_step": t_total, "compute_only_eager_ms": t_eager, "compute_only_graph_ms": t_graph,
+                     "exposed_allreduce_ms": t_total - t_eager, "exposed_allreduce_frac": (t_total - t_eager) / t_total,
+                     "eager_vs_graph_ms": t_eager - t_graph,
+                     "n1_equivalent_tiles_per_s": per_gpu / (t_graph * 1e-3),
+                     "allreduce_bytes_per_step": net.engine.store.total * 4,
+                     "reserve_sms": reducer.reserve_sms, "reserve_kernels": reducer.reserve_kernels,
+                     "schedule": "CUDA graph incl. all-reduces" if dp_graph else "eager schedule + bucketed all-reduce on a high-priority side stream",
+                     "what": "compute_only_*: the same per-GPU batch with the all-reducer detached (max over ranks): eager = "
+                             "the schedule the timed region uses minus the all-reduces, graph = what one GPU alone runs; "
+                             "exposed_allreduce = timed step - compute_only_eager"}
 
     # ---- end-to-end: pinned host inputs in, loss out, every step, through the public API.  Every step's inputs cross
     # PCIe inside the timed region; the copy of step i+1 is issued on a copy stream while step i computes (what an
@@ -363,16 +404,51 @@ def main():
     e2e_val = global_batch * ke / e2e_s
     h2d = h_img.numel() * 4 + h_lab.numel() + h_w.numel() * 4
 
+    # ---- inference half of the BASELINE metric (config 4: overlap-tile, 4096 x 4096, tiles sharded over the ranks)
+    inference = None
+    if not args.no_inference:
+        import bench_infer
+        torch.cuda.empty_cache()
+        inference = bench_infer.measure(net, dev, world, rank, steps=max(2, min(K, 5)), warmup=3)
+
+    # ---- the "existing Blackwell kernel" bar: stock torch + cuDNN on this same GPU (rank 0, N = 1 only)
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        torch.cuda.empty_cache()
+        try:
+            v, ms_c = cudnn_steps(per_gpu, 3, 3, dev, "bf16")
+            gpu_baseline = {"value": v, "unit": UNIT, "ms_per_step": ms_c, "kind": "torch %s + cuDNN %s, autocast(bf16) + "
+                            "channels_last, the reference's operator sequence (oracle/unet_oracle.py), same batch, "
+                            "device-resident inputs; `python bench.py --impl cudnn` also reports tf32 and fp32" %
+                            (torch.__version__, torch.backends.cudnn.version())}
+        except Exception as e:  # noqa: BLE001 -- a baseline failure must not lose the measurement
+            gpu_baseline = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         tf_peak, hbm_peak, peak_kind = load_peaks()
-        ig = fam.get("igemm", (0.0, 1e-9, 0))
-        wg = fam.get("wgrad", (0.0, 1e-9, 0))
-        ach = ig[0] / (ig[1] * 1e-3) / 1e12
-        traffic = None
+        ig, wg = fam_ig, fam_wg
+        ach = ig[0] / (ig[2] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("igemm_dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("igemm_dram_bytes_per_launch"), tj.get("source")
+        # every family on its own roof(s): tensor-pipe families by FLOPs, HBM families by algorithmic bytes; the
+        # up-convolutions carry both and are reported against the one that binds
+        fams = {}
+        for name, (fl, by, t_ms, n) in sorted(fam_all.items()):
+            e = {"ms_per_step": t_ms / K, "launches_per_step": n / K}
+            if fl > 0:
+                e["tflops"] = fl / (t_ms * 1e-3) / 1e12
+                e["tensor_frac"] = e["tflops"] / tf_peak
+            if by > 0:
+                e["gbs"] = by / (t_ms * 1e-3) / 1e9
+                e["hbm_frac"] = e["gbs"] / hbm_peak
+            if fl > 0 and by > 0:
+                e["bound"] = "hbm" if e["hbm_frac"] > e["tensor_frac"] else "tensor"
+            fams[name] = e
+        timed_ms = sum(v[2] for v in fam_all.values()) / K
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -385,15 +461,24 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": ke},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "igemm family: igemm_kernel / igemm2_kernel / igemm3_kernel (3x3 conv fwd + dgrad incl. the fused pool / head / bias-sum epilogues, up-conv fwd + dgrad)",
+            "roofline": {"bound": "tensor", "kernel": "igemm family: igemm_kernel / igemm2_kernel (3x3 conv fwd + dgrad incl. the fused pool / head / bias-sum epilogues, up-conv fwd + dgrad)",
                          "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                          "peak_kind": f"{peak_kind} sustained bf16 (MEASURED_PEAKS.json)", "traffic": traffic,
-                         "launches_timed": ig[2], "ms_per_step": ig[1] / K,
+                         "traffic_source": traffic_src,
+                         "launches_timed": ig[3], "ms_per_step": ig[2] / K,
                          "whole_step": {"achieved": FLOPS_PER_TRAIN_TILE * per_gpu * K / (ms * 1e-3) / 1e12,
                                         "frac": FLOPS_PER_TRAIN_TILE * per_gpu * K / (ms * 1e-3) / 1e12 / tf_peak},
-                         "wgrad_kernel": {"achieved": wg[0] / (wg[1] * 1e-3) / 1e12,
-                                          "frac": wg[0] / (wg[1] * 1e-3) / 1e12 / tf_peak, "ms_per_step": wg[1] / K}},
+                         "wgrad_kernel": {"achieved": wg[0] / (wg[2] * 1e-3) / 1e12,
+                                          "frac": wg[0] / (wg[2] * 1e-3) / 1e12 / tf_peak, "ms_per_step": wg[2] / K,
+                                          "deterministic": True},
+                         "hbm_peak": hbm_peak, "hbm_peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)",
+                         "families": fams,
+                         "timed_ms_per_step": timed_ms,
+                         "untimed_ms_per_step": ms / K - timed_ms},
             "loss": float(loss.item()),
+            "inference": inference,
+            "gpu_baseline": gpu_baseline,
+            "scaling_breakdown": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, dt = cpu_reference_steps(3, 1)
@@ -404,6 +489,8 @@ def main():
             out["cpu_baseline"] = None
         print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
+        tstep.graphs.clear()            # captured NCCL work must be gone before the communicator is
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

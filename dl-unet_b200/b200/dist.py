@@ -7,6 +7,8 @@ The reference has no multi-device code (main_main.py:157-167); this is SURVEY.md
 The loss must be normalised by the GLOBAL batch (b200.train.*(global_batch=...)) so that the summed
 gradients equal the single-GPU gradients of the concatenated batch.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -33,16 +35,30 @@ def bucket_bounds(total, ready_ends, bucket_elems):
 
 
 class GradAllReducer:
-    def __init__(self, unet, bucket_mb=32.0, group=None):
+    def __init__(self, unet, bucket_mb=32.0, group=None, reserve_sms=None, reserve_kernels=None):
+        """reserve_sms / reserve_kernels: after a bucket's all-reduce is enqueued, the next `reserve_kernels` compute
+        launches size their persistent grids for (SM count - reserve_sms) SMs, so the NCCL kernel starts at once on
+        free SMs instead of both kernels waiting for each other's CTAs (ops.reserve_sms).  Defaults from the
+        environment: UB_DP_RESERVE_SMS (0 = off), UB_DP_RESERVE_KERNELS (2)."""
         self.engine = unet.engine if hasattr(unet, "engine") else unet
         self.group = group
         self.world = dist.get_world_size(group)
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.reserve_sms = int(os.environ.get("UB_DP_RESERVE_SMS", "0")) if reserve_sms is None else reserve_sms
+        self.reserve_kernels = int(os.environ.get("UB_DP_RESERVE_KERNELS", "2")) if reserve_kernels is None else reserve_kernels
         self.comm_stream = None
         self.start = 0
         self.works = []
+        self.attach()
+
+    def attach(self):
         self.engine.grad_ready_hook = self._on_ready
         self.engine.grad_done_hook = self._on_done
+
+    def detach(self):
+        """Single-device schedule again (bench.py's compute-only leg of the scaling breakdown)."""
+        self.engine.grad_ready_hook = None
+        self.engine.grad_done_hook = None
 
     def broadcast_parameters(self, src=0):
         st = self.engine.store
@@ -59,13 +75,17 @@ class GradAllReducer:
             self.start = end
             return
         if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream(device=st.g_arena.device)
+            # high priority: at a kernel boundary the pending NCCL blocks are placed before the next compute kernel's
+            self.comm_stream = torch.cuda.Stream(device=st.g_arena.device, priority=-1)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
             self.works.append(dist.all_reduce(st.g_arena[self.start:end], group=self.group, async_op=True))
         self.start = end
+        if self.reserve_sms > 0:
+            from . import ops
+            ops.reserve_sms(self.reserve_sms, self.reserve_kernels)
 
     def _on_ready(self, s, e):
         if e - self.start >= self.bucket_elems:
@@ -73,6 +93,9 @@ class GradAllReducer:
 
     def _on_done(self):
         self._flush(self.engine.store.total)
+        if self.reserve_sms > 0 and self.engine.store.g_arena.is_cuda:
+            from . import ops
+            ops.reserve_sms(0, 0)
         for w in self.works:
             w.wait()  # the compute stream waits for the reduced buckets
         if self.comm_stream is not None:

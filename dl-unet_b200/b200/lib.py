@@ -31,6 +31,7 @@ SIGNATURES = {
     "ub_error_string": (C.c_char_p, [_i]),
     "ub_device_error": (_i, [C.POINTER(C.c_uint)]),
     "ub_set_tuning": (None, [_i, _i, _i, _i]),
+    "ub_set_sm_limit": (None, [_i]),
     "ub_set_prof_buffer": (None, [_P]),
     "ub_set_option": (None, [_i, _i]),
     "ub_pack_weight": (_i, [_P, _P, _i, _i, _i, _P]),
@@ -65,6 +66,8 @@ SIGNATURES = {
     "ub_augment_batch": (_i, [_P, _P, _i, _i, _i, _P, _P, _i, _i, _i, C.c_double, C.c_double, _P, _P, _P, _P]),
     "ub_mirror_pad": (_i, [_P, _P, _i, _i, _i, _P]),
     "ub_mask_metrics": (_i, [_P, _i, _P, _i, _ll, _P, _P]),
+    "ub_cut_tiles": (_i, [_P, _i, _i, _i, _i, _P, _i, _i, _i, _i, _P, _P]),
+    "ub_stitch_tiles": (_i, [_P, _P, _i, _i, _i, _P, _i, _i, _P]),
     "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),
     "ub_sgd_momentum": (_i, [_P, _P, _P, _ll, _f, _f, _i, _P]),
 }

@@ -15,9 +15,9 @@ def _stream():
 
 
 class _Stats:
-    """Launch accounting for bench.py: `launches` counts every kernel this library launched;
-    with `timing` on, each tensor-pipe launch is bracketed by CUDA events on the launching stream
-    and recorded as (family, algorithmic FLOPs, start, end)."""
+    """Launch accounting for bench.py: `launches` counts every kernel this library launched; with `timing` on, each
+    launch is bracketed by CUDA events on the launching stream and recorded as (family, algorithmic FLOPs, algorithmic
+    bytes, start, end).  Families: "igemm:<what>" / "wgrad:<what>" (tensor pipe), "hbm:<kernel>" (HBM-bound)."""
 
     def __init__(self):
         self.launches = 0
@@ -28,13 +28,18 @@ class _Stats:
         self.launches = 0
         self.records = []
 
-    def summarize(self):
-        """-> {family: (total_flops_or_bytes, total_ms, n_launches)}; call after a synchronize."""
+    def summarize(self, prefix=None):
+        """-> {family: (flops, bytes, total_ms, n_launches)}; call after a synchronize.  prefix: merge every family that
+        starts with it into one entry."""
         out = {}
-        for fam, work, e0, e1 in self.records:
+        for fam, fl, by, e0, e1 in self.records:
+            if prefix is not None:
+                if not fam.startswith(prefix):
+                    continue
+                fam = prefix
             t = e0.elapsed_time(e1)
-            w, ms, n = out.get(fam, (0.0, 0.0, 0))
-            out[fam] = (w + work, ms + t, n + 1)
+            f, b, ms, n = out.get(fam, (0.0, 0.0, 0.0, 0))
+            out[fam] = (f + fl, b + by, ms + t, n + 1)
         return out
 
 
@@ -42,8 +47,16 @@ STATS = _Stats()
 
 
 class _timed:
-    def __init__(self, family, work):
-        self.family, self.work = family, work
+    def __init__(self, family, work, flops=None):
+        """work: algorithmic bytes for "hbm:*" families, algorithmic FLOPs otherwise; flops / work may both be given for
+        kernels reported against either roof (up-convolutions): _timed(fam, bytes, flops)."""
+        self.family = family
+        if flops is not None:
+            self.flops, self.bytes = flops, work
+        elif family.startswith("hbm:"):
+            self.flops, self.bytes = 0.0, work
+        else:
+            self.flops, self.bytes = work, 0.0
 
     def __enter__(self):
         if STATS.timing:
@@ -55,14 +68,35 @@ class _timed:
         if STATS.timing:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            STATS.records.append((self.family, self.work, self.e0, e1))
+            STATS.records.append((self.family, self.flops, self.bytes, self.e0, e1))
         return False
+
+
+_RESERVE = {"left": 0}
+
+
+def reserve_sms(n_free, kernels):
+    """Size the persistent grids of the next `kernels` launches for (SM count - n_free) SMs: a collective that was just
+    enqueued on another stream finds free SMs at once instead of waiting for CTAs to drain (and our CTAs do not queue
+    behind it).  n_free = 0 restores full-size grids."""
+    lib = _lib.load()
+    if n_free <= 0 or kernels <= 0:
+        lib.ub_set_sm_limit(0)
+        _RESERVE["left"] = 0
+        return
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    lib.ub_set_sm_limit(max(1, sms - int(n_free)))
+    _RESERVE["left"] = int(kernels)
 
 
 def _chk(code, what=""):
     """check() + launch accounting (every successful call below is exactly one kernel launch)."""
     check(code, what)
     STATS.launches += 1
+    if _RESERVE["left"] > 0:
+        _RESERVE["left"] -= 1
+        if _RESERVE["left"] == 0:
+            _lib.load().ub_set_sm_limit(0)
 
 
 def _ptr(t):
@@ -202,7 +236,7 @@ class JobTable:
 def conv3x3_fwd(x, w_fwd, bias, y, relu=True):
     _need_cuda(x, w_fwd, y)
     n, h, w, co = y.shape
-    with _timed("igemm", 2.0 * n * h * w * co * 9 * x.shape[3]):
+    with _timed("igemm:conv_fwd", 2.0 * n * h * w * co * 9 * x.shape[3]):
         _chk(_lib.load().ub_conv3x3_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), int(relu), _stream()), "conv3x3_fwd")
     return y
 
@@ -212,7 +246,7 @@ def conv3x3_fwd_head(x, w_fwd, bias, y, head_w, head_b, logits=None, argmax=None
     (network.py:187-190).  y = None: the 64-channel activation is not stored (inference)."""
     _need_cuda(x, w_fwd, head_w, head_b, y, logits, argmax)
     n, h, w, ci = x.shape
-    with _timed("igemm", 2.0 * n * (h - 2) * (w - 2) * 64 * 9 * ci):
+    with _timed("igemm:conv_fwd_head", 2.0 * n * (h - 2) * (w - 2) * 64 * 9 * ci):
         _chk(_lib.load().ub_conv3x3_fwd_head(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _ptr(head_w), _ptr(head_b),
                                              _ptr(logits), _ptr(argmax), _stream()), "conv3x3_fwd_head")
 
@@ -222,7 +256,7 @@ def conv3x3_fwd_pool(x, w_fwd, bias, cout, y, pooled, idx, cat=None, c_off=0):
     (network.py:132-133).  y = None: the full-resolution activation is never stored."""
     _need_cuda(x, w_fwd, pooled, idx, y, cat)
     n, h, w, ci = x.shape
-    with _timed("igemm", 2.0 * n * (h - 2) * (w - 2) * cout * 9 * ci):
+    with _timed("igemm:conv_fwd_pool", 2.0 * n * (h - 2) * (w - 2) * cout * 9 * ci):
         _chk(_lib.load().ub_conv3x3_fwd_pool(_t4p(x), _ptr(w_fwd), _ptr(bias), int(cout), _t4p(y), _ptr(pooled), _ptr(idx),
                                              _t4p(cat), int(c_off), _stream()), "conv3x3_fwd_pool")
 
@@ -232,7 +266,7 @@ def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_c0=0):
     bias gradient of the layer that produced this layer's input (fused into the epilogue where supported)."""
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, co = dy.shape
-    with _timed("igemm", 2.0 * n * h * w * co * 9 * dx.shape[3]):
+    with _timed("igemm:conv_dgrad", 2.0 * n * h * w * co * 9 * dx.shape[3]):
         if dbias is None:
             _chk(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
         else:
@@ -246,7 +280,7 @@ def conv3x3_wgrad(x, dy, dw_packed):
     no atomics: the slabs are summed by unpack_grad / JobTable.unpack_*)."""
     _need_cuda(x, dy, dw_packed)
     n, h, w, co = dy.shape
-    with _timed("wgrad", 2.0 * n * h * w * co * 9 * x.shape[3]):
+    with _timed("wgrad:conv", 2.0 * n * h * w * co * 9 * x.shape[3]):
         _chk(_lib.load().ub_conv3x3_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "conv3x3_wgrad")
     return dw_packed
 
@@ -254,7 +288,8 @@ def conv3x3_wgrad(x, dy, dw_packed):
 def upconv2x2_fwd(x, w_fwd, bias, y):
     _need_cuda(x, w_fwd, y)
     n, h, w, ci = x.shape
-    with _timed("igemm", 2.0 * n * h * w * ci * 4 * y.shape[3]):
+    # bytes: x read, y written (bf16) -- the up-convolutions of levels 1-2 are HBM-bound
+    with _timed("igemm:up_fwd", n * h * w * 2.0 * (ci + 4 * y.shape[3]), 2.0 * n * h * w * ci * 4 * y.shape[3]):
         _chk(_lib.load().ub_upconv2x2_fwd(_t4p(x), _ptr(w_fwd), _ptr(bias), _t4p(y), _stream()), "upconv2x2_fwd")
     return y
 
@@ -262,7 +297,8 @@ def upconv2x2_fwd(x, w_fwd, bias, y):
 def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None):
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, ci = dx.shape
-    with _timed("igemm", 2.0 * n * h * w * ci * 4 * dy.shape[3]):
+    with _timed("igemm:up_dgrad", n * h * w * 2.0 * (4 * dy.shape[3] + ci * (2 if relu_src is not None else 1)),
+                2.0 * n * h * w * ci * 4 * dy.shape[3]):
         _chk(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
     return dx
 
@@ -270,7 +306,7 @@ def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None):
 def upconv2x2_wgrad(x, dy, dw_packed):
     _need_cuda(x, dy, dw_packed)
     n, h, w, ci = x.shape
-    with _timed("wgrad", 2.0 * n * h * w * ci * 4 * dy.shape[3]):
+    with _timed("wgrad:up", n * h * w * 2.0 * (ci + 4 * dy.shape[3]), 2.0 * n * h * w * ci * 4 * dy.shape[3]):
         _chk(_lib.load().ub_upconv2x2_wgrad(_t4p(x), _t4p(dy), _ptr(dw_packed), _stream()), "upconv2x2_wgrad")
     return dw_packed
 

@@ -59,7 +59,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int num_sms() {
+int g_sm_limit = 0;   // ub_set_sm_limit: persistent grids leave SMs free for a concurrently running collective
+int num_sms_physical() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -67,6 +68,10 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+int num_sms() {
+  const int n = num_sms_physical();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -419,7 +424,7 @@ struct SplitPlan {
   int splits, per;
 };
 SplitPlan plan_splits(long long items, long long chunks, int min_chunks, double overhead) {
-  const int sms = num_sms();
+  const int sms = num_sms_physical();   // the slab count of a shape must not change with ub_set_sm_limit
   long long max_splits = chunks / min_chunks;
   if (max_splits < 1) max_splits = 1;
   if (max_splits > 1024) max_splits = 1024;
@@ -716,6 +721,8 @@ void ub_set_option(int key, int value) {
   if (key == 7) g_map_cache_on = value;
 }
 
+void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }
+
 void ub_set_prof_buffer(void* dev_ptr) { g_prof_buffer = reinterpret_cast<unsigned long long*>(dev_ptr); }
 
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits) {
@@ -995,17 +1002,18 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
   return launch_wgrad(P, BN, smem_bytes, st);
 }
 
-// kernel choice measured per layer on B200 (profiles/r1_layer_table_batch16_v3.log ... r2_*):
-//   Cout == 64                           : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
-//   Cin <= 128                           : haloed patch, all nine taps, 32-channel tile (wgrad3)
-//   256-channel wide maps                : one tap row per CTA, N = 192 (wgrad5)
-//   everything deeper                    : one tap per unit, N = 256, persistent (wgrad_kernel)
+// kernel choice measured per layer on B200 at 16 tiles (profiles/r2_layer_table_batch16_v1_persistent_wgrad.log):
+//   Cout == 64                            : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
+//   Cin == 64                             : haloed patch, all nine taps, 32-channel tile (wgrad3)
+//   Cin 128 / 256 on maps >= 128 wide     : one tap row per CTA, three s taps per instruction, N = 192 (wgrad5)
+//   everything deeper / smaller           : one tap per unit, N = 256, persistent (wgrad_kernel)
 static int conv3x3_wgrad_impl(const ub_tensor4* x, const ub_tensor4* dy, float* slabs, cudaStream_t st, int* slabs_out) {
   int mode = g_wgrad_mode;
   if (mode == 3) {
     if (dy->c == 64) mode = 5;
+    else if (x->c < 128) mode = 2;
+    else if (x->c <= 256 && dy->w >= 128) mode = 4;
     else if (x->c <= 128) mode = 2;
-    else if (x->c <= 256 && dy->w >= 160) mode = 4;
     else mode = 0;
   }
   if (mode == 5 && dy->c == 64) return launch_wgrad4(x, dy, slabs, st, slabs_out);
@@ -1310,6 +1318,28 @@ int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* 
   if (b <= 0 || n <= 0 || size < n || ((size - n) & 1) || (size - n) / 2 >= n) return UB_E_SHAPE;
   const long long total = (long long)b * size * size;
   mirror_pad_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, out, n, size, (size - n) / 2, total);
+  return (int)cudaGetLastError();
+}
+
+int ub_cut_tiles(const float* image, int h, int w, int row0, int rows, const int* tile_ids, int n_tiles, int nx,
+                 int tile_in, int tile_out, float* tiles, void* stream) {
+  if (!image || !tile_ids || !tiles) return UB_E_ARG;
+  const int halo = (tile_in - tile_out) / 2;
+  if (h <= 0 || w <= 0 || n_tiles <= 0 || nx <= 0 || tile_out <= 0 || tile_in < tile_out || ((tile_in - tile_out) & 1) ||
+      halo >= h || halo >= w || row0 < 0 || rows <= 0 || row0 + rows > h)
+    return UB_E_SHAPE;
+  const long long total = (long long)n_tiles * tile_in * tile_in;
+  cut_tiles_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(image, h, w, row0, tile_ids, nx, tile_in, tile_out,
+                                                                     tiles, total);
+  return (int)cudaGetLastError();
+}
+
+int ub_stitch_tiles(const unsigned char* masks, const int* tile_ids, int n_tiles, int nx, int tile_out,
+                    unsigned char* out, int h, int w, void* stream) {
+  if (!masks || !tile_ids || !out) return UB_E_ARG;
+  if (h <= 0 || w <= 0 || n_tiles <= 0 || nx <= 0 || tile_out <= 0) return UB_E_SHAPE;
+  const long long total = (long long)n_tiles * tile_out * tile_out;
+  stitch_tiles_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(masks, tile_ids, nx, tile_out, out, h, w, total);
   return (int)cudaGetLastError();
 }
 

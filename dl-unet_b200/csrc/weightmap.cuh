@@ -355,4 +355,52 @@ __global__ void __launch_bounds__(256) mirror_pad_kernel(const float* __restrict
   }
 }
 
+// ---- overlap-tile inference (Ronneberger's tiling strategy): input tiles gathered straight from
+// the image and output mask tiles scattered straight into the stitched mask, so neither the reflect-padded image nor
+// the full tile stack ever exists.  Tile t = (ty, tx) of an nx-wide grid covers output pixels [ty*To, (ty+1)*To) x
+// [tx*To, ...) and reads input pixels shifted by -halo: coordinates below 0 reflect without repeating the edge
+// (F.pad "reflect"), coordinates beyond the reflect-padded extent H + halo repeat its last row / column (the
+// right / bottom fill up to a whole number of tiles), exactly as b200.tiling.cut_tiles' F.pad + unfold did.
+__device__ __forceinline__ int tile_src_index(int i, int n, int halo) {   // i: coordinate in the image frame
+  if (i > n - 1 + halo) i = n - 1 + halo;
+  if (i < 0) i = -i;
+  if (i > n - 1) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// image: rows [row0, row0 + rows) of an H x W fp32 image (a rank may hold only the band its tiles touch)
+__global__ void __launch_bounds__(256) cut_tiles_kernel(const float* __restrict__ image, int H, int W, int row0,
+                                                        const int* __restrict__ tile_ids, int nx, int tile_in,
+                                                        int tile_out, float* __restrict__ tiles, long long total) {
+  const int halo = (tile_in - tile_out) / 2;
+  const long long plane = (long long)tile_in * tile_in;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(g / plane);
+    const int r = (int)(g - (long long)k * plane);
+    const int py = r / tile_in, px = r - py * tile_in;
+    const int t = __ldg(tile_ids + k);
+    const int ty = t / nx, tx = t - ty * nx;
+    const int y = tile_src_index(ty * tile_out + py - halo, H, halo);
+    const int x = tile_src_index(tx * tile_out + px - halo, W, halo);
+    tiles[g] = __ldg(image + (long long)(y - row0) * W + x);
+  }
+}
+
+__global__ void __launch_bounds__(256) stitch_tiles_kernel(const unsigned char* __restrict__ masks,
+                                                           const int* __restrict__ tile_ids, int nx, int tile_out,
+                                                           unsigned char* __restrict__ out, int H, int W, long long total) {
+  const long long plane = (long long)tile_out * tile_out;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(g / plane);
+    const int r = (int)(g - (long long)k * plane);
+    const int py = r / tile_out, px = r - py * tile_out;
+    const int t = __ldg(tile_ids + k);
+    const int ty = t / nx, tx = t - ty * nx;
+    const int y = ty * tile_out + py, x = tx * tile_out + px;
+    if (y < H && x < W) out[(long long)y * W + x] = masks[g];
+  }
+}
+
 }  // namespace ub

@@ -45,6 +45,10 @@ int ub_device_error(unsigned int* out_code);
 /* experiment: device buffer of 148 x 8 uint64 that igemm2 launches fill with the clock sums of their epilogue phases
  * (wait for the MMAs, TMEM load + arithmetic + staging, store wait, chunk barrier, store issue, chunks, total); NULL = off */
 void ub_set_prof_buffer(void* dev_ptr);
+/* Size the persistent grids of the following launches for n_sms SMs instead of all of them (0 = all): leaves SMs free
+ * for a collective that runs concurrently on another stream (data-parallel gradient all-reduce), so that neither
+ * kernel waits for the other's CTAs to drain.  Host-side state, read at launch time. */
+void ub_set_sm_limit(int n_sms);
 /* Tuning overrides for experiments: <=0 restores the heuristic. */
 void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
 /* Experiment switches (A/B measurements; the defaults are the product configuration).
@@ -205,6 +209,19 @@ int ub_mirror_pad(const float* image, float* out, int b, int n, int size, void* 
  * |pred & label|, |pred | label| and sum |pred - label|:  IoU = counts[0]/counts[1], pixel error = counts[2]/n. */
 int ub_mask_metrics(const void* pred, int pred_bytes, const void* label, int label_bytes, long long n,
                     unsigned long long* counts, void* stream);
+
+/* ---- overlap-tile inference plumbing (the reference only has whole-image mirror padding,
+ * data.py:249-312).  Tile t = (t / nx, t % nx) produces tile_out x tile_out output pixels from a tile_in x tile_in
+ * input window shifted by -halo, halo = (tile_in - tile_out) / 2.
+ * ub_cut_tiles: tiles[k] (fp32 [tile_in][tile_in]) = window of tile tile_ids[k] gathered from `image`, which holds
+ *   rows [row0, row0 + rows) of an h x w fp32 image; outside the image the window reflects (edge not repeated) and
+ *   beyond the reflected extent repeats the last row / column.  The caller guarantees the band holds every row the
+ *   listed tiles touch.  tile_ids is a device array.
+ * ub_stitch_tiles: out[h][w] (uint8) receives masks[k] (uint8 [tile_out][tile_out]) at tile tile_ids[k], clipped. */
+int ub_cut_tiles(const float* image, int h, int w, int row0, int rows, const int* tile_ids, int n_tiles, int nx,
+                 int tile_in, int tile_out, float* tiles, void* stream);
+int ub_stitch_tiles(const unsigned char* masks, const int* tile_ids, int n_tiles, int nx, int tile_out,
+                    unsigned char* out, int h, int w, void* stream);
 
 /* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients); out += */
 int ub_colsum(const void* g_bf16, float* out, long long n_pix, int c, long long ld, void* stream);

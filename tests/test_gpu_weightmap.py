@@ -165,6 +165,54 @@ def test_segment_image_equals_per_tile_forward():
     assert torch.equal(full, ref)
 
 
+@pytest.mark.parametrize("shape", [(300, 420, 252), (389, 700, 572), (97, 130, 188)])
+def test_cut_and_stitch_kernels_equal_the_torch_route(shape):
+    """ub_cut_tiles / ub_stitch_tiles against b200.tiling.cut_tiles (F.pad reflect + replicate + unfold) / stitch:
+    bit-equal, also when a rank holds only the band of rows its tiles read."""
+    from b200 import tiling
+    from b200.dist import partition
+    h, w, tile_in = shape
+    torch.manual_seed(h)
+    image = torch.rand(h, w, device=DEV)
+    ref = tiling.cut_tiles(image, tile_in)
+    tile_out, halo, ny, nx, _, _ = tiling.plan(h, w, tile_in)
+    n = ny * nx
+    for world in (1, 3):
+        got = torch.full_like(ref, float("nan"))
+        for r in range(world):
+            ids = list(range(*partition(n, r, world)))
+            if not ids:
+                continue
+            row0, rows = tiling.needed_rows(h, ids, nx, tile_in, tile_out)
+            band = image[row0:row0 + rows].contiguous()
+            ids_dev = torch.tensor(ids, dtype=torch.int32, device=DEV)
+            out = torch.empty(len(ids), 1, tile_in, tile_in, device=DEV)
+            tiling.cut_tiles_device(band, h, w, row0, ids_dev, len(ids), nx, tile_in, tile_out, out)
+            got[ids] = out
+        assert torch.equal(got, ref)
+    masks = (torch.rand(n, tile_out, tile_out, device=DEV) > 0.5).to(torch.uint8)
+    full = torch.full((h, w), 9, dtype=torch.uint8, device=DEV)
+    tiling.stitch_device(masks, torch.arange(n, dtype=torch.int32, device=DEV), n, nx, tile_out, full)
+    assert torch.equal(full, tiling.stitch(masks, h, w, tile_in))
+
+
+def test_tile_segmenter_pipeline_equals_segment_image():
+    """TileSegmenter.segment_many (pinned host images in, pinned host masks out, upload / forward / download
+    overlapped over two slots) yields for every image the mask segment_image computes."""
+    from network import Unet
+    from b200 import tiling
+    torch.manual_seed(3)
+    net = Unet().to(DEV)
+    imgs = [torch.rand(300, 420).pin_memory() for _ in range(5)]
+    want = [tiling.segment_image(net, im.to(DEV), tile_in=252, batch=4).cpu() for im in imgs]
+    seg = tiling.TileSegmenter(net, 300, 420, tile_in=252, batch=4)
+    n = 0
+    for i, mask in seg.segment_many(imgs):
+        assert i == n and torch.equal(mask, want[i])
+        n += 1
+    assert n == len(imgs)
+
+
 def test_drop_in_functions_cpu_labels_go_through_the_device(golden_dir):
     """dl-unet_b200/functions.py keeps the reference's call placement (trainer.py:69,72 pass CPU labels): a CPU label
     batch is uploaded, processed by the kernels and returned on the CPU -- equal to the reference's golden outputs."""

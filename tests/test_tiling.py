@@ -27,3 +27,26 @@ def test_halo_is_mirror_without_edge_repeat():
     # first tile: the row above the image's first row is the image's SECOND row (reflect, data.py:249-277)
     assert torch.equal(t[0, 0, halo - 1, halo:halo + 388], img[1, :388])
     assert torch.equal(t[0, 0, halo:halo + 388, halo - 3], img[:388, 3])
+
+
+def test_src_index_and_band_match_the_pad_and_unfold_route():
+    """The index rule ub_cut_tiles implements (tiling._src_index) against the F.pad(reflect) + F.pad(replicate) +
+    unfold reference, and needed_rows: every source row of a rank's windows lies inside its band."""
+    from b200.dist import partition
+    for (h, w, tile_in) in ((300, 420, 252), (389, 1000, 572), (97, 130, 188)):
+        img = torch.rand(h, w)
+        ref = tiling.cut_tiles(img, tile_in)
+        tile_out, halo, ny, nx, _, _ = tiling.plan(h, w, tile_in)
+        for t in (0, nx - 1, ny * nx - 1, (ny // 2) * nx + nx // 2):
+            ty, tx = divmod(t, nx)
+            ys = torch.tensor([tiling._src_index(ty * tile_out + p - halo, h, halo) for p in range(tile_in)])
+            xs = torch.tensor([tiling._src_index(tx * tile_out + p - halo, w, halo) for p in range(tile_in)])
+            assert torch.equal(img[ys][:, xs], ref[t, 0])
+        for world in (1, 2, 3):
+            for r in range(world):
+                ids = list(range(*partition(ny * nx, r, world)))
+                if not ids:
+                    continue
+                row0, rows = tiling.needed_rows(h, ids, nx, tile_in, tile_out)
+                used = {tiling._src_index(ty * tile_out + p - halo, h, halo) for ty in {t // nx for t in ids} for p in range(tile_in)}
+                assert row0 <= min(used) and max(used) < row0 + rows <= h
