@@ -79,10 +79,10 @@ def main():
         run(f"pool_bwd+skip_grad_sum {h}x{h}x{c}", nout * (2 + 2 + 1 + 2 + 8),
             [lambda i=i: ops.pool2x2_bwd(dy, dcat[..., :c], coff, idx, y, dxs[i]) for i in range(2)],
             "dy + dcat window + idx + pooled read, 4 positions written: 15 B per pooled element")
-        dbias = torch.zeros(c, device=dev)
+        dbias = torch.empty(ops.partial_rows(ops.PROD_POOL, n, h, h, c), c, device=dev)
         run(f"pool_bwd+skip_grad_sum+bias_grad {h}x{h}x{c}", nout * (2 + 2 + 1 + 2 + 8),
-            [lambda i=i: ops.pool2x2_bwd(dy, dcat[..., :c], coff, idx, y, dxs[i], dbias) for i in range(2)],
-            "the variant the training step runs: also accumulates the bias gradient of the conv that fed the pool")
+            [lambda i=i: ops.pool2x2_bwd(dy, dcat[..., :c], coff, idx, y, dxs[i], dbias_part=dbias) for i in range(2)],
+            "the variant the training step runs: also leaves the partial rows of the bias gradient of the conv that fed the pool")
         del xs, dxs, cat, dcat
 
     # ---- conv11c, head, SGD
@@ -91,19 +91,19 @@ def main():
     w1, b1 = torch.randn(64, 1, 3, 3, device=dev), torch.randn(64, device=dev)
     ys = [torch.empty(n, s - 2, s - 2, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     run("conv11c_fwd (1->64, bias+ReLU)", n * (s * s * 4 + (s - 2) ** 2 * 128), [lambda i=i: ops.conv1_fwd(img, w1, b1, ys[i]) for i in range(2)])
-    dw, db = torch.zeros(64, 9, device=dev), torch.zeros(64, device=dev)
-    run("conv11c_wgrad", n * (s * s * 4 + (s - 2) ** 2 * 128), [lambda i=i: ops.conv1_wgrad(img, ys[i], dw, db) for i in range(2)])
+    c1part = torch.empty(ops.partial_rows(ops.PROD_CONV1, n, s, s), ops.CONV1_STRIDE, device=dev)
+    run("conv11c_wgrad", n * (s * s * 4 + (s - 2) ** 2 * 128), [lambda i=i: ops.conv1_wgrad(img, ys[i], part=c1part) for i in range(2)])
     x = torch.randn(n, 388, 388, 64, device=dev).clamp_min(0).to(torch.bfloat16)
     x2 = x.clone()
     wf, bf_ = torch.randn(2, 64, 1, 1, device=dev), torch.randn(2, device=dev)
     lg = torch.empty(n, 2, 388, 388, device=dev)
     run("head_fwd (64->2)", n * 388 * 388 * (128 + 8), [lambda: ops.head_fwd(x, wf, bf_, lg, None), lambda: ops.head_fwd(x2, wf, bf_, lg, None)])
     dxh = torch.empty_like(x)
-    dwh, dbh = torch.zeros(2, 64, device=dev), torch.zeros(2, device=dev)
-    run("head_bwd", n * 388 * 388 * (128 + 8 + 128), [lambda: ops.head_bwd(x, wf, lg, dxh, dwh, dbh), lambda: ops.head_bwd(x2, wf, lg, dxh, dwh, dbh)])
+    hpart = torch.empty(ops.partial_rows(ops.PROD_HEAD, n, 388, 388), ops.HEAD_STRIDE, device=dev)
+    run("head_bwd", n * 388 * 388 * (128 + 8 + 128), [lambda: ops.head_bwd(x, wf, lg, dxh, part=hpart), lambda: ops.head_bwd(x2, wf, lg, dxh, part=hpart)])
     g2 = torch.randn(n, 388, 388, 64, device=dev).to(torch.bfloat16)
-    cs = torch.zeros(64, device=dev)
-    run("colsum (bias grad)", n * 388 * 388 * 128, [lambda: ops.colsum(x, cs), lambda: ops.colsum(g2, cs)])
+    cs = torch.empty(ops.partial_rows(ops.PROD_COLSUM, n, 388, 388, 64), 64, device=dev)
+    run("colsum (bias grad)", n * 388 * 388 * 128, [lambda: ops.colsum(x, part=cs), lambda: ops.colsum(g2, part=cs)])
     nel = 31_030_658
     pa, ga, ma = (torch.randn(nel + 6, device=dev) for _ in range(3))
     run("sgd_momentum (31.03 M params)", nel * 20, [lambda: ops.sgd_momentum(pa, ga, ma, 1e-4, 0.99, False)],

@@ -22,9 +22,10 @@ from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
 # encoder levels whose 2x2 max pool runs inside the epilogue of conv{l}2c (the haloed-patch kernel: <= 256 channels);
 # UB_FUSED_POOL_LEVELS=0 restores the separate pool kernel everywhere (experiments)
 FUSED_POOL_LEVELS = int(__import__("os").environ.get("UB_FUSED_POOL_LEVELS", "2"))
-# bias gradients accumulated by the dgrad that produces the layer's output gradient (UB_FUSE_DGRAD_BIAS=0: separate
-# column-sum kernels, for A/B measurements)
-FUSE_DGRAD_BIAS = __import__("os").environ.get("UB_FUSE_DGRAD_BIAS", "1") != "0"
+
+# weight-gradient slabs -> torch-layout gradient right after each layer's wgrad (slabs still in L2) instead of one launch
+# over all layers at the end of backward (UB_UNPACK_PER_LAYER=0); the data-parallel schedule always unpacks per layer
+UNPACK_PER_LAYER = __import__("os").environ.get("UB_UNPACK_PER_LAYER", "0") != "0"
 
 PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
 # order in which backward finishes each layer's gradients
@@ -114,7 +115,7 @@ class ParamStore:
     def versions(self):
         return tuple(p._version for p in self.params().values())
 
-    def _layer_entries(self, slab_of=None):
+    def _layer_entries(self, slab_of=None, with_name=False):
         """Job-table rows of the 21 conv / up-conv layers (ops.JobTable).  slab_of(lname) -> (slab workspace, n_slabs);
         None: a pack-only table (the gradient columns are placeholders)."""
         entries = []
@@ -129,7 +130,7 @@ class ParamStore:
                                      torch.empty(dshape, dtype=torch.bfloat16, device=self.device))
             slab, n_slabs = slab_of(lname) if slab_of is not None else (self.g(lname + ".weight"), 1)
             entries.append((w, self.packs[lname][0], self.packs[lname][1], slab, self.g(lname + ".weight"),
-                            0 if kind == "conv" else 2, cout, cin, n_slabs))
+                            0 if kind == "conv" else 2, cout, cin, n_slabs) + ((lname,) if with_name else ()))
         return entries
 
     def _job_table(self):
@@ -146,10 +147,6 @@ class ParamStore:
         self._job_table().pack_all()
         self.pack_versions = v
         self.dirty = False
-
-
-# index of each conv / up-conv layer in the job tables
-JOB_INDEX = {l: i for i, l in enumerate(n for (n, k, _, _) in LAYERS if k in ("conv", "up"))}
 
 
 class Workspace:
@@ -196,10 +193,37 @@ class Workspace:
         out = ((g.enc1 if pos == 1 else g.enc2) if side == "c" else (g.dec1 if pos == 1 else g.dec2))[lvl]
         return out + 2
 
+    def bias_plan(self):
+        """Where every bias gradient (and the two small weight gradients) of the backward schedule comes from:
+        name -> (producer, ub_partial_rows arguments, row stride, column offset in the row, length, buffer key).
+        Mirrors Engine.backward."""
+        g, B = self.geom, self.B
+        plan = {}
+        head = ("head", (ops.PROD_HEAD, B, g.out, g.out), ops.HEAD_STRIDE)
+        plan["finalconv.weight"] = head + (0, 130, "head")          # weight [2][64] + bias [2]: contiguous in the arena
+        plan["conv12e.bias"] = head + (130, 64, "head")
+        for l in (1, 2, 3, 4):
+            C = LEVEL_C[l]
+            if l > 1:
+                plan[f"conv{l}2e.bias"] = ("colsum", (ops.PROD_COLSUM, B, g.dec2[l], g.dec2[l], C), C, 0, C, None)
+            # conv{l}2e's dgrad sums its dx = the output gradient of conv{l}1e; conv{l}1e's dgrad that of upconv{l}
+            plan[f"conv{l}1e.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.dec1[l], g.dec1[l], C, C, 0), C, 0, C, None)
+            plan[f"upconv{l}.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.up[l], g.up[l], 2 * C, C, C), C, 0, C, None)
+            plan[f"conv{l}2c.bias"] = ("pool", (ops.PROD_POOL, B, g.enc2[l], g.enc2[l], C), C, 0, C, None)
+            if l > 1:
+                plan[f"conv{l}1c.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.enc1[l], g.enc1[l], C, C, 0), C, 0, C, None)
+        plan["conv52c.bias"] = ("colsum", (ops.PROD_COLSUM, B, g.enc2[5], g.enc2[5], 1024), 1024, 0, 1024, None)
+        plan["conv51c.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.enc1[5], g.enc1[5], 1024, 1024, 0), 1024, 0, 1024, None)
+        plan["conv11c.weight"] = ("conv1", (ops.PROD_CONV1, B, self.S, self.S), ops.CONV1_STRIDE, 0, 640, None)
+        return plan
+
     def grad_slabs(self, store):
-        """Deterministic split-K: the wgrad kernel of every layer stores `n` partial gradients (slabs) side by side; the
-        slab counts depend on the layer shape at this batch, so the workspace and the unpack job table live here."""
+        """Deterministic reductions: the wgrad kernel of every layer stores `n` partial gradients (slabs) side by side,
+        every bias-gradient producer one row of partial sums per CTA; slab and row counts depend on the layer shape at
+        this batch, so the workspaces and the unpack job table (which sums them in fixed order) live here.
+        -> {"view": layer -> slab workspace, "part": parameter -> partial-row buffer, "table", "range": layer -> jobs}"""
         if self.slabs is None or self.slabs["arena_id"] != store.arena_id:
+            dev = store.device
             counts, off, total = {}, {}, 0
             for (lname, kind, cin, cout) in LAYERS:
                 if kind not in ("conv", "up"):
@@ -208,10 +232,33 @@ class Workspace:
                 counts[lname] = ops.wgrad_slabs(ops.PACK_CONV_FWD if kind == "conv" else ops.PACK_UP_FWD, self.B, h, h, cin, cout)
                 off[lname] = total
                 total += counts[lname] * store.numel[lname + ".weight"]
-            arena = torch.empty(total, dtype=torch.float32, device=store.device)
+            arena = torch.empty(total, dtype=torch.float32, device=dev)
             view = lambda l: arena[off[l]:off[l] + counts[l] * store.numel[l + ".weight"]]
-            table = ops.JobTable(store._layer_entries(lambda l: (view(l), counts[l])), store.device)
-            self.slabs = {"arena": arena, "view": view, "counts": counts, "table": table, "arena_id": store.arena_id}
+            # partial-row buffers of the bias producers
+            plan, bufs, part = self.bias_plan(), {}, {}
+            for name, (prod, qargs, stride, col, length, key) in plan.items():
+                key = key or name
+                if key not in bufs:
+                    bufs[key] = torch.empty(ops.partial_rows(*qargs), stride, dtype=torch.float32, device=dev)
+                part[name] = bufs[key]
+            weights = {e[-1]: e[:-1] for e in store._layer_entries(lambda l: (view(l), counts[l]), with_name=True)}
+            dummy = store.g_arena[:1]
+            entries, ranges = [], {}
+            for (lname, kind, cin, cout) in LAYERS:
+                first = len(entries)
+                if lname in weights:
+                    entries.append(weights[lname])
+                for pname in ("weight", "bias"):
+                    name = f"{lname}.{pname}"
+                    if name in plan:
+                        prod, qargs, stride, col, length, key = plan[name]
+                        buf = part[name]
+                        dst = store.g_arena[store.g_off[name]:store.g_off[name] + length]   # may span weight + bias
+                        entries.append((dummy, dummy, dummy, buf.view(-1)[col:], dst, 3, length, stride, buf.shape[0]))
+                ranges[lname] = (first, len(entries))
+            table = ops.JobTable(entries, dev)
+            self.slabs = {"arena": arena, "view": view, "counts": counts, "part": part, "bufs": bufs, "table": table,
+                          "range": ranges, "arena_id": store.arena_id}
         return self.slabs
 
 
@@ -291,48 +338,47 @@ class Engine:
             e = st.g_off[lname + ".bias"] + _align(st.numel[lname + ".bias"])
             self.grad_ready_hook(s, e)
 
-    @staticmethod
-    def _bias_from_dgrad(lname):
-        """Layers whose bias gradient is produced by the dgrad of the following conv (not by pool / head backward)."""
-        return lname.endswith("1e") or (lname.endswith("1c") and lname != "conv11c")
+    def _finish(self, lname):
+        """Every gradient of `lname` has been produced (slabs / partial rows): per-layer schedules reduce them now."""
+        if self.grad_ready_hook is not None or UNPACK_PER_LAYER:  # data parallel: the layer's gradient must be final now
+            i, j = self._slabs["range"][lname]
+            self._slabs["table"].unpack_layer(i, self._accumulate, j)
+        self._ready(lname)
 
     def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False, dx_bias=None, dx_bias_c0=0):
         """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer.  bias_done: the kernel that
-        produced dy (pool / head backward, or the dgrad of the layer after this one) already accumulated its column
-        sums into the bias gradient.  dx_bias: name of the parameter that receives the column sums of dx (channels
-        >= dx_bias_c0) -- the bias gradient of the layer that produced x, fused into this layer's dgrad."""
+        produced dy (pool / head backward, or the dgrad of the layer after this one) already left the partial rows of
+        its column sums (this layer's bias gradient).  dx_bias: name of the parameter that receives the column sums of
+        dx (channels >= dx_bias_c0) -- the bias gradient of the layer that produced x, fused into this layer's dgrad."""
         st = self.store
         ops.conv3x3_wgrad(x, dy, self._slabs["view"](lname))
-        if self.grad_ready_hook is not None:  # data parallel: the layer's gradient must be final now
-            self._slabs["table"].unpack_layer(JOB_INDEX[lname], self._accumulate)
-        if not bias_done or (not FUSE_DGRAD_BIAS and self._bias_from_dgrad(lname)):
-            ops.colsum(dy, st.g(lname + ".bias"))
-        self._ready(lname)
+        if not bias_done:
+            ops.colsum(dy, part=self._slabs["part"][lname + ".bias"])
+        self._finish(lname)
         if dx is not None:
-            fuse = dx_bias is not None and FUSE_DGRAD_BIAS
-            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src, st.g(dx_bias) if fuse else None, dx_bias_c0)
+            ops.conv3x3_dgrad(dy, st.packs[lname][1], dx, relu_src, dbias_c0=dx_bias_c0,
+                              dbias_part=self._slabs["part"][dx_bias] if dx_bias is not None else None)
 
     def backward(self, ws, dlogits):
         """dlogits: fp32 [B,2,So,So] (d loss / d logits).  Fills the gradient arena; if every
         param.grad still is its arena view (no zero_grad since the last backward) the new
-        gradients are accumulated on top, as autograd would."""
+        gradients are accumulated on top, as autograd would.  Nothing is zeroed and nothing is accumulated with
+        atomics: every kernel stores slabs / partial rows, the unpack job table sums them in fixed order."""
         st = self.store
         a, gr, g = ws.act, ws.grad, ws.geom
         self._accumulate = all(
             p.grad is not None and p.grad.data_ptr() == st.grad_view(n).data_ptr() for n, p in st.params().items())
-        if not self._accumulate:
-            st.g_arena.zero_()
-        self._slabs = ws.grad_slabs(st)      # every slab is fully overwritten by its wgrad kernel: nothing to zero
+        self._slabs = ws.grad_slabs(st)
+        part = self._slabs["part"]
         P, pk = st.p, st.packs
         dlogits = dlogits.contiguous().float()
 
-        ops.head_bwd(a["d12"], P("finalconv.weight"), dlogits, gr["d12"], st.g("finalconv.weight"),
-                     st.g("finalconv.bias"), st.g("conv12e.bias"))
-        self._ready("finalconv")
+        ops.head_bwd(a["d12"], P("finalconv.weight"), dlogits, gr["d12"], part=part["finalconv.weight"])
+        self._finish("finalconv")
         dy = gr["d12"]
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
-            # each dgrad also accumulates the bias gradient of the layer whose output gradient it produces
+            # each dgrad also produces the bias gradient of the layer whose output gradient it computes
             self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=(l == 1),
                            dx_bias=f"conv{l}1e.bias")
             self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None, bias_done=True,
@@ -343,11 +389,7 @@ class Engine:
             dsrc = gr[f"d{l + 1}2"] if l < 4 else gr["e52"]
             dyu = gr[f"cat{l}"][..., C:]
             ops.upconv2x2_wgrad(src, dyu, self._slabs["view"](up_name))
-            if self.grad_ready_hook is not None:
-                self._slabs["table"].unpack_layer(JOB_INDEX[up_name], self._accumulate)
-            if not FUSE_DGRAD_BIAS:
-                ops.colsum(dyu, st.g(up_name + ".bias"))
-            self._ready(up_name)                     # its bias gradient came with conv{l}1e's dgrad
+            self._finish(up_name)                    # its bias gradient came with conv{l}1e's dgrad
             ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
             dy = dsrc
         # bottleneck
@@ -359,16 +401,16 @@ class Engine:
             if H & 1:
                 gr[f"e{l}2"].zero_()  # floor-mode pool: the last row / column gets no gradient
             ops.pool2x2_bwd(gr[f"p{l}"], gr[f"cat{l}"][..., :C], g.coff[l], a[f"i{l}"], a[f"p{l}"], gr[f"e{l}2"],
-                            st.g(f"conv{l}2c.bias"))
+                            dbias_part=part[f"conv{l}2c.bias"])
             self._conv_bwd(f"conv{l}2c", a[f"e{l}1"], gr[f"e{l}2"], gr[f"e{l}1"], a[f"e{l}1"], bias_done=True,
                            dx_bias=f"conv{l}1c.bias" if l > 1 else None)     # conv11c: conv1_wgrad sums its own bias
             if l > 1:
                 self._conv_bwd(f"conv{l}1c", a[f"p{l - 1}"], gr[f"e{l}1"], gr[f"p{l - 1}"], None, bias_done=True)
             else:
-                ops.conv1_wgrad(ws.image, gr["e11"], st.g("conv11c.weight"), st.g("conv11c.bias"))
-                self._ready("conv11c")
-        if self.grad_ready_hook is None:
-            self._slabs["table"].unpack_all(self._accumulate)   # single device: all 21 layers in one launch
+                ops.conv1_wgrad(ws.image, gr["e11"], part=part["conv11c.weight"])
+                self._finish("conv11c")
+        if self.grad_ready_hook is None and not UNPACK_PER_LAYER:
+            self._slabs["table"].unpack_all(self._accumulate)   # single device: all 46 gradients in one launch
         if self.grad_done_hook is not None:
             self.grad_done_hook()
 

@@ -52,11 +52,11 @@ SIGNATURES = {
     "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
     "ub_upconv2x2_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_conv1_fwd": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
-    "ub_conv1_wgrad": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_conv1_wgrad": (_i, [_P, _P, _P, _i, _i, _i, _P]),
     "ub_pool2x2_fwd": (_i, [_P, _P, _P, _T4, _i, _i, _i, _i, _i, _P]),
     "ub_pool2x2_bwd": (_i, [_P, _T4, _i, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "ub_head_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _P]),
-    "ub_head_bwd": (_i, [_P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P]),
+    "ub_head_bwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "ub_loss_workspace_bytes": (_ll, []),
     "ub_loss_fwd_bwd": (_i, [_i, _P, _P, _i, _P, _P, _P, _P, _i, _i, _i, _i, _f, _P]),
     "ub_weight_map_workspace_bytes": (_ll, [_i, _i, _i]),
@@ -69,6 +69,8 @@ SIGNATURES = {
     "ub_cut_tiles": (_i, [_P, _i, _i, _i, _i, _P, _i, _i, _i, _i, _P, _P]),
     "ub_stitch_tiles": (_i, [_P, _P, _i, _i, _i, _P, _i, _i, _P]),
     "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),
+    "ub_partial_rows": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "ub_reduce_partials": (_i, [_P, _i, _ll, _i, _P, _i, _P]),
     "ub_sgd_momentum": (_i, [_P, _P, _P, _ll, _f, _f, _i, _P]),
 }
 # include/unet_b200_diag.h: only in libunet_b200_diag.so (make libunet_b200_diag.so), never in the product library

@@ -215,7 +215,7 @@ class JobTable:
         self.keep = entries  # keep the tensors alive
 
     def _numel(self):
-        return sum(e[0].numel() for e in self.keep)
+        return sum(e[0].numel() for e in self.keep if e[5] != 3)
 
     def pack_all(self):
         with _timed("hbm:pack_all", self._numel() * 8.0):                  # fp32 master in, two bf16 operands out
@@ -223,13 +223,16 @@ class JobTable:
 
     def unpack_all(self, accumulate=False):
         """Every layer: sum the gradient slabs in fixed order and write the torch-layout gradients."""
-        with _timed("hbm:unpack_all", sum(e[0].numel() * 4.0 * (e[8] + 1) for e in self.keep)):   # slabs in, gradient out
+        with _timed("hbm:unpack_all", sum(e[4].numel() * 4.0 * (e[8] + 1) for e in self.keep)):   # slabs in, gradient out
             _chk(_lib.load().ub_unpack_range(_ptr(self.table), self.n, 0, self.utile_begin[self.n], int(accumulate), _stream()),
                  "unpack_all")
 
-    def unpack_layer(self, i, accumulate=False):
-        _chk(_lib.load().ub_unpack_range(_ptr(self.table), self.n, self.utile_begin[i], self.utile_begin[i + 1],
-                                         int(accumulate), _stream()), "unpack_layer")
+    def unpack_layer(self, i, accumulate=False, j=None):
+        """Jobs i .. j-1 (default: job i alone)."""
+        j = i + 1 if j is None else j
+        with _timed("hbm:unpack_layer", sum(e[4].numel() * 4.0 * (e[8] + 1) for e in self.keep[i:j])):
+            _chk(_lib.load().ub_unpack_range(_ptr(self.table), self.n, self.utile_begin[i], self.utile_begin[j],
+                                             int(accumulate), _stream()), "unpack_layer")
 
 
 # ---------------------------------------------------------------- tensor-pipe ops
@@ -261,17 +264,24 @@ def conv3x3_fwd_pool(x, w_fwd, bias, cout, y, pooled, idx, cat=None, c_off=0):
                                              _t4p(cat), int(c_off), _stream()), "conv3x3_fwd_pool")
 
 
-def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_c0=0):
-    """dbias (fp32 [C - c0], zeroed by the caller): also receives the column sums of dx over the channels >= c0 -- the
-    bias gradient of the layer that produced this layer's input (fused into the epilogue where supported)."""
+def conv3x3_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_c0=0, dbias_part=None):
+    """dbias_part: [partial_rows(PROD_DGRAD, n, h, w, C, Cdy, c0), C - c0] also receives partial rows of the column sums of
+    dx over the channels >= c0 -- the bias gradient of the layer that produced this layer's input (fused into the
+    epilogue where supported); dbias (fp32 [C - c0]): the same, reduced here and ADDED to it."""
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, co = dy.shape
+    own = dbias is not None and dbias_part is None
+    length = dx.shape[3] - dbias_c0
+    if own:
+        dbias_part = _part(partial_rows(PROD_DGRAD, n, dx.shape[1], dx.shape[2], dx.shape[3], co, dbias_c0), length, dx)
     with _timed("igemm:conv_dgrad", 2.0 * n * h * w * co * 9 * dx.shape[3]):
-        if dbias is None:
+        if dbias_part is None:
             _chk(_lib.load().ub_conv3x3_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "conv3x3_dgrad")
         else:
-            _chk(_lib.load().ub_conv3x3_dgrad_bias(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _ptr(dbias), int(dbias_c0),
-                                                   _stream()), "conv3x3_dgrad_bias")
+            _chk(_lib.load().ub_conv3x3_dgrad_bias(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _ptr(dbias_part),
+                                                   int(dbias_c0), _stream()), "conv3x3_dgrad_bias")
+    if own:
+        reduce_partials(dbias_part, dbias_part.shape[0], length, length, dbias, True)
     return dx
 
 
@@ -311,6 +321,33 @@ def upconv2x2_wgrad(x, dy, dw_packed):
     return dw_packed
 
 
+# ---------------------------------------------------------------- partial sums (bias gradients)
+# Kernels that reduce over pixels into a short vector store one row of partial sums per CTA (no atomics); the rows are
+# summed in order by the unpack job table (engine) or by reduce_partials (the `dbias=` / `out=` forms below, which keep
+# the old "accumulate into a [C] tensor" semantics for tests and tools).
+PROD_POOL, PROD_COLSUM, PROD_DGRAD, PROD_HEAD, PROD_CONV1 = 0, 1, 2, 3, 4
+HEAD_STRIDE, CONV1_STRIDE = 194, 640
+
+
+def partial_rows(producer, n, h, w, c=0, c_dy=0, c0=0):
+    r = _lib.load().ub_partial_rows(int(producer), int(n), int(h), int(w), int(c), int(c_dy), int(c0))
+    if r < 0:
+        check(r, "partial_rows")
+    return r
+
+
+def reduce_partials(part, rows, stride, length, dst, accumulate=True, col=0):
+    """dst[e] (+)= sum over the first `rows` rows of part[:, col + e], in row order."""
+    base = C.c_void_p(part.data_ptr() + 4 * col)
+    _chk(_lib.load().ub_reduce_partials(base, int(rows), int(stride), int(length), _ptr(dst), int(accumulate), _stream()),
+         "reduce_partials")
+    return dst
+
+
+def _part(rows, stride, like):
+    return torch.empty(rows, stride, dtype=torch.float32, device=like.device)
+
+
 # ---------------------------------------------------------------- HBM-bound ops
 def conv1_fwd(image, w, bias, y):
     """image fp32 [N,1,H,W] -> y bf16 [N,H-2,W-2,64], bias + ReLU fused (network.py:131)."""
@@ -321,10 +358,18 @@ def conv1_fwd(image, w, bias, y):
     return y
 
 
-def conv1_wgrad(image, dy, dw, db):
+def conv1_wgrad(image, dy, dw=None, db=None, part=None):
+    """conv11c weight + bias gradient.  part: [partial_rows(PROD_CONV1, n, h, w), 640] receives the partial rows
+    (dW[64][9] then db[64]); otherwise they are reduced here and ADDED to dw / db."""
     n, _, h, wd = image.shape
+    own = part is None
+    if own:
+        part = _part(partial_rows(PROD_CONV1, n, h, wd), CONV1_STRIDE, image)
     with _timed("hbm:conv1_wgrad", n * (h * wd * 4.0 + (h - 2) * (wd - 2) * 128.0)):
-        _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(dw), _ptr(db), n, h, wd, _stream()), "conv1_wgrad")
+        _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(part), n, h, wd, _stream()), "conv1_wgrad")
+    if own:
+        reduce_partials(part, part.shape[0], CONV1_STRIDE, 576, dw, True)
+        reduce_partials(part, part.shape[0], CONV1_STRIDE, 64, db, True, col=576)
 
 
 def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
@@ -336,15 +381,20 @@ def pool2x2_fwd(x, y, idx, cat=None, c_off=0):
     return y, idx
 
 
-def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx, dbias=None):
-    """dbias (fp32 [C], zeroed by the caller): also receives the column sums of dx (bias gradient of the conv
-    that fed the pool)."""
+def pool2x2_bwd(dy, dcat, c_off, idx, pooled, dx, dbias=None, dbias_part=None):
+    """dbias_part: [partial_rows(PROD_POOL, n, h, w, c), c] receives partial rows of the column sums of dx (bias gradient
+    of the conv that fed the pool); dbias (fp32 [C]): the same, reduced here and ADDED to it."""
     n, h, w, c = dx.shape
+    own = dbias is not None and dbias_part is None
+    if own:
+        dbias_part = _part(partial_rows(PROD_POOL, n, h, w, c), c, dx)
     # SURVEY.md 8(d): 2 B dY + 1 B index read + 4 x 2 B dX written per pooled element (the second gradient producer
     # and the ReLU mask this kernel also reads are not counted)
     with _timed("hbm:pool_bwd", n * (h // 2) * (w // 2) * c * 11.0):
-        _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), _ptr(dbias),
+        _chk(_lib.load().ub_pool2x2_bwd(_ptr(dy), _t4p(dcat), int(c_off), _ptr(idx), _ptr(pooled), _ptr(dx), _ptr(dbias_part),
                                          n, h, w, c, _stream()), "pool2x2_bwd")
+    if own:
+        reduce_partials(dbias_part, dbias_part.shape[0], c, c, dbias, True)
     return dx
 
 
@@ -353,12 +403,22 @@ def head_fwd(x, w, bias, logits=None, argmax=None):
     _chk(_lib.load().ub_head_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(logits), _ptr(argmax), n, h, wd, _stream()), "head_fwd")
 
 
-def head_bwd(x, w, dlogits, dx, dw, db, dbias_x=None):
-    """dbias_x (fp32 [64], zeroed by the caller): also receives the column sums of dx (bias gradient of conv12e)."""
+def head_bwd(x, w, dlogits, dx, dw=None, db=None, dbias_x=None, part=None, with_dx_sums=True):
+    """part: [partial_rows(PROD_HEAD, n, h, w), 194] receives the partial rows (dW[2][64], db[2], column sums of dx[64] =
+    bias gradient of conv12e); otherwise they are reduced here and ADDED to dw / db / dbias_x."""
     n, h, wd, _ = x.shape
+    own = part is None
+    if own:
+        part = _part(partial_rows(PROD_HEAD, n, h, wd), HEAD_STRIDE, x)
+        with_dx_sums = dbias_x is not None
     with _timed("hbm:head_bwd", n * h * wd * (128.0 + 8.0 + 128.0)):      # x, dlogits in; dx out
-        _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(dw), _ptr(db), _ptr(dbias_x), n, h, wd,
+        _chk(_lib.load().ub_head_bwd(_ptr(x), _ptr(w), _ptr(dlogits), _ptr(dx), _ptr(part), int(with_dx_sums), n, h, wd,
                                       _stream()), "head_bwd")
+    if own:
+        reduce_partials(part, part.shape[0], HEAD_STRIDE, 128, dw, True)
+        reduce_partials(part, part.shape[0], HEAD_STRIDE, 2, db, True, col=128)
+        if dbias_x is not None:
+            reduce_partials(part, part.shape[0], HEAD_STRIDE, 64, dbias_x, True, col=130)
 
 
 LOSS_BCE, LOSS_SOFTMAX_CE = 0, 1
@@ -381,14 +441,20 @@ def loss_fwd_bwd(kind, logits, label, weight, dlogits, loss_out, workspace, grad
                                           _ptr(workspace), b, hp, wp, l, float(grad_scale), _stream()), "loss_fwd_bwd")
 
 
-def colsum(g, out):
-    """out[c] += sum over pixels of the bf16 NHWC view g (dense in n,y,x up to the pixel stride)."""
+def colsum(g, out=None, part=None):
+    """Column sums over pixels of the bf16 NHWC view g (dense in n,y,x up to the pixel stride).  part:
+    [partial_rows(PROD_COLSUM, n, h, w, c), c] receives the partial rows; out (fp32 [C]): reduced here, out += sums."""
     n, h, w, c = g.shape
     ld = g.stride(2)
     if g.stride(1) != w * ld or (n > 1 and g.stride(0) != h * w * ld):
         raise RuntimeError("colsum needs a view that is dense over pixels")
+    own = part is None
+    if own:
+        part = _part(partial_rows(PROD_COLSUM, n, h, w, c), c, g)
     with _timed("hbm:colsum", n * h * w * c * 2.0):
-        _chk(_lib.load().ub_colsum(_ptr(g), _ptr(out), n * h * w, c, ld, _stream()), "colsum")
+        _chk(_lib.load().ub_colsum(_ptr(g), _ptr(part), n * h * w, c, ld, _stream()), "colsum")
+    if own:
+        reduce_partials(part, part.shape[0], c, c, out, True)
 
 
 def sgd_momentum(p, g, buf, lr, momentum, first_step):

@@ -276,6 +276,32 @@ int ew_grid(long long work_items, int tpb = 256) {
   return (int)b;
 }
 
+// Grids of the kernels that leave per-CTA partial sums (bias gradients etc.): functions of the shape and the PHYSICAL SM
+// count only, because the number of partial rows is baked into the unpack job table (ub_partial_rows).
+int pool_bwd_bias_blocks(int n, int h, int w, int c) {
+  // one resident wave (6 CTAs per SM): a larger grid only adds rows to reduce
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 6ll * num_sms_physical()) blocks = 6ll * num_sms_physical();
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+int colsum_blocks(long long n_pix, int c) {
+  const int slots = 256 / (c / 8);
+  long long blocks = (n_pix + slots * 8 - 1) / (slots * 8);
+  if (blocks > 4ll * num_sms_physical()) blocks = 4ll * num_sms_physical();
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+int head_bwd_blocks(long long npix_total) {
+  long long blocks = (npix_total * 8 + 256ll * 8 - 1) / (256ll * 8);
+  if (blocks > 8ll * num_sms_physical()) blocks = 8ll * num_sms_physical();
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+int conv1_wgrad_rpb(int n, int h) {
+  // ~10 blocks per SM (5 resident, two waves)
+  int rpb = (int)(((long long)(h - 2) * n + 10ll * num_sms_physical() - 1) / (10ll * num_sms_physical()));
+  return rpb < 1 ? 1 : rpb;
+}
+
 void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) {
   pick_patch(W, H, P.BW, P.BH);
   P.tiles_x = (W + P.BW - 1) / P.BW;
@@ -402,6 +428,7 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   P.aux_bytes = 2048 + head_smem + col_smem;
   P.dbias = dbias;
   P.dbias_c0 = dbias_c0;
+  P.dbias_rows = num_sms_physical();
   const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem + mask_smem + col_smem;
   if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
   if (pool) {
@@ -758,16 +785,24 @@ int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* 
     t[i].cout = cout[i];
     t[i].cin = cin[i];
     t[i].elem_begin = begin;
-    const long long numel = (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
-    begin += numel;
-    if ((cout[i] % 32) || (cin[i] % 32) || slabs[i] < 1) return UB_E_SHAPE;
     t[i].tile_begin = tiles;
-    tiles += (cout[i] / 32) * (cin[i] / 32);
     t[i].slabs = slabs[i];
-    t[i].slab_stride = numel;
-    t[i].lanes = slabs[i] >= 32 ? 8 : slabs[i] >= 16 ? 4 : slabs[i] >= 8 ? 2 : 1;
     t[i].utile_begin = utiles;
     utile_begin_out[i] = utiles;
+    if (slabs[i] < 1) return UB_E_SHAPE;
+    if (kind[i] == 3) {   // vector job: cout elements, partial rows cin elements apart; not part of pack_all
+      if (cout[i] < 1 || cin[i] < cout[i]) return UB_E_SHAPE;
+      t[i].slab_stride = cin[i];
+      t[i].lanes = 8;
+      utiles += (cout[i] + 31) / 32;
+      continue;
+    }
+    const long long numel = (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
+    begin += numel;
+    if ((cout[i] % 32) || (cin[i] % 32)) return UB_E_SHAPE;
+    tiles += (cout[i] / 32) * (cin[i] / 32);
+    t[i].slab_stride = numel;
+    t[i].lanes = slabs[i] >= 32 ? 8 : slabs[i] >= 16 ? 4 : slabs[i] >= 8 ? 2 : 1;
     utiles += (cout[i] / (8 / t[i].lanes)) * (cin[i] / 32);
   }
   utile_begin_out[n_jobs] = utiles;
@@ -917,7 +952,7 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   return launch_igemm(P, BN, (cudaStream_t)stream);
 }
 
-int ub_colsum(const void* g, float* out, long long n_pix, int c, long long ld, void* stream);
+int ub_colsum(const void* g, float* part, long long n_pix, int c, long long ld, void* stream);
 
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                      void* stream) {
@@ -926,14 +961,14 @@ int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4
 }
 
 int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
-                          float* dbias, int dbias_c0, void* stream) {
-  if (!dbias || dbias_c0 < 0 || (dbias_c0 % 8)) return UB_E_ARG;
+                          float* dbias_part, int dbias_c0, void* stream) {
+  if (!dbias_part || dbias_c0 < 0 || (dbias_c0 % 8)) return UB_E_ARG;
   bool fused;
-  int e = conv3x3_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, dbias, dbias_c0, &fused);
+  int e = conv3x3_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, dbias_part, dbias_c0, &fused);
   if (e || fused) return e;
   // the kernel chosen for this shape has no fused column sums: one pass over the channels [c0, C) of dx
   if (dx->c <= dbias_c0 || dx->sy != (long long)dx->w * dx->sx || dx->sn != (long long)dx->h * dx->sy) return UB_E_SHAPE;
-  return ub_colsum(reinterpret_cast<const __nv_bfloat16*>(dx->ptr) + dbias_c0, dbias, (long long)dx->n * dx->h * dx->w,
+  return ub_colsum(reinterpret_cast<const __nv_bfloat16*>(dx->ptr) + dbias_c0, dbias_part, (long long)dx->n * dx->h * dx->w,
                    dx->c - dbias_c0, dx->sx, stream);
 }
 
@@ -1124,16 +1159,14 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   return (int)cudaGetLastError();
 }
 
-int ub_conv1_wgrad(const float* image, const void* dy, float* dw, float* db, int n, int h, int w_, void* stream) {
-  if (!image || !dy || !dw || !db) return UB_E_ARG;
+int ub_conv1_wgrad(const float* image, const void* dy, float* part, int n, int h, int w_, void* stream) {
+  if (!image || !dy || !part) return UB_E_ARG;
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
   if (n > 65535) return UB_E_SHAPE;
-  // ~10 blocks per SM (5 resident, two waves)
-  int rpb = (int)(((long long)(h - 2) * n + 10ll * num_sms() - 1) / (10ll * num_sms()));
-  if (rpb < 1) rpb = 1;
+  const int rpb = conv1_wgrad_rpb(n, h);
   const dim3 grid((h - 2 + rpb - 1) / rpb, n);
-  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, dw, db, n, h, w_, rpb);
+  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, part, n, h, w_, rpb);
   return (int)cudaGetLastError();
 }
 
@@ -1178,10 +1211,8 @@ int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsi
   }
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
   if (dbias) {
-    // one resident wave (6 CTAs per SM): every CTA ends with c atomics into dbias, a larger grid only adds contention
-    long long blocks = (total + 255) / 256;
-    if (blocks > 6ll * num_sms()) blocks = 6ll * num_sms();
-    pool_bwd_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+    const int blocks = pool_bwd_bias_blocks(n, h, w, c);   // = rows of the partial sums written to dbias
+    pool_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, catp, idx, (const __nv_bfloat16*)pooled, (__nv_bfloat16*)dx, n, h, w, c, ch, cw, cc, c_off, dbias);
   } else
     pool_bwd_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
@@ -1200,17 +1231,14 @@ int ub_head_fwd(const void* x, const float* w, const float* bias, float* logits,
   return (int)cudaGetLastError();
 }
 
-int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db, float* dbias_x,
-                int n, int h, int w_, void* stream) {
-  if (!x || !w || !dlogits || !dx || !dw || !db) return UB_E_ARG;
+int ub_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* part, int with_dx_sums, int n,
+                int h, int w_, void* stream) {
+  if (!x || !w || !dlogits || !dx || !part) return UB_E_ARG;
   if (!aligned16(x) || !aligned16(dx)) return UB_E_ALIGN;
   const long long npix = (long long)h * w_;
   if (npix * n * 8 >= (1ll << 31)) return UB_E_SHAPE;
-  long long blocks = (npix * n * 8 + 256ll * 8 - 1) / (256ll * 8);
-  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
-  if (blocks < 1) blocks = 1;
-  head_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, dlogits,
-                                                                (__nv_bfloat16*)dx, dw, db, dbias_x, npix, n);
+  head_bwd_kernel<<<head_bwd_blocks(npix * n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, dlogits,
+                                                                              (__nv_bfloat16*)dx, part, with_dx_sums, npix, n);
   return (int)cudaGetLastError();
 }
 
@@ -1423,15 +1451,37 @@ int ub_augment_batch(const unsigned char* images, const unsigned char* targets, 
   return (int)cudaGetLastError();
 }
 
-int ub_colsum(const void* g, float* out, long long n_pix, int c, long long ld, void* stream) {
-  if (!g || !out) return UB_E_ARG;
+int ub_colsum(const void* g, float* part, long long n_pix, int c, long long ld, void* stream) {
+  if (!g || !part) return UB_E_ARG;
   if (c % 8 || c > 2048 || (256 % (c / 8)) || (ld % 8)) return UB_E_SHAPE;
   if (!aligned16(g)) return UB_E_ALIGN;
-  const int slots = 256 / (c / 8);
-  long long blocks = (n_pix + slots * 8 - 1) / (slots * 8);
-  if (blocks > 4ll * num_sms()) blocks = 4ll * num_sms();
-  if (blocks < 1) blocks = 1;
-  colsum_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, out, n_pix, c, ld);
+  colsum_kernel<<<colsum_blocks(n_pix, c), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, part, n_pix, c, ld);
+  return (int)cudaGetLastError();
+}
+
+int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) {
+  if (n <= 0 || h <= 0 || w <= 0) return UB_E_SHAPE;
+  switch (producer) {
+    case 0: return (c > 0 && c % 8 == 0) ? pool_bwd_bias_blocks(n, h, w, c) : UB_E_SHAPE;
+    case 1: return (c > 0 && c % 8 == 0 && 256 % (c / 8) == 0) ? colsum_blocks((long long)n * h * w, c) : UB_E_SHAPE;
+    case 2: {
+      if (c <= c0 || c_dy <= 0) return UB_E_SHAPE;
+      ub_tensor4 dx{nullptr, n, h, w, c, 0, 0, 0}, dy{nullptr, n, h - 2, w - 2, c_dy, 0, 0, 0};
+      if (igemm2_eligible(&dy, &dx)) return num_sms_physical();
+      return colsum_blocks((long long)n * h * w, c - c0);
+    }
+    case 3: return head_bwd_blocks((long long)n * h * w);
+    case 4: {
+      const int rpb = conv1_wgrad_rpb(n, h);
+      return ((h - 2 + rpb - 1) / rpb) * n;
+    }
+  }
+  return UB_E_ARG;
+}
+
+int ub_reduce_partials(const float* part, int rows, long long stride, int length, float* dst, int accumulate, void* stream) {
+  if (!part || !dst || rows < 1 || length < 1) return UB_E_ARG;
+  reduce_partials_kernel<<<(length + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, rows, stride, length, dst, accumulate);
   return (int)cudaGetLastError();
 }
 

@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 // dY is bf16 NHWC (already ReLU-masked), 8 KB per 64-pixel tile, streamed through a 3-stage cp.async ring together
 // with the tile's 3 x 66 image window, so ~16 KB per block (5 blocks per SM) are in flight whatever the compute
 // does.  Thread = (pixel slot, channel octet, tap half): half 0 accumulates taps 0..4, half 1 taps 5..8 and the
-// bias (x = 1): 40 accumulators.  Block-level reduction in shared memory, one atomicAdd per (co, tap) per block.
+// bias (x = 1): 40 accumulators.  Block-level reduction in shared memory (fixed order); every block STORES its 576 + 64
+// partial sums as one row of `part` ([blocks][640]: dW[co][tap] then db[co]) -- no atomics; the rows are summed in
+// order by the unpack kernel (deterministic gradients).
 constexpr int C1W_TILE = 64, C1W_STAGES = 3;
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ dy,
-                                                          float* __restrict__ dw, float* __restrict__ db, int n_img,
+                                                          float* __restrict__ part, int n_img,
                                                           int H, int W, int rows_per_block) {
   __shared__ __align__(16) uint8_t sdy[C1W_STAGES][C1W_TILE * 128];
   __shared__ float sxw[C1W_STAGES][3][C1W_TILE + 2];
@@ -202,10 +204,11 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
     const int ch = i / 10, t = i % 10;
     float v = 0.0f;
     for (int wv = 0; wv < 8; ++wv) v += sred[wv][(t / 5) * 8 + (ch >> 3)][(ch & 7) * 5 + (t % 5)];
+    float* row = part + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * 640;
     if (t < 9)
-      atomicAdd(dw + ch * 9 + t, v);
+      row[ch * 9 + t] = v;
     else
-      atomicAdd(db + ch, v);
+      row[576 + ch] = v;
   }
 }
 
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(256, BIAS ? 6 : 7) pool_bwd_kernel(const __nv_
       const int cc8 = i >> 3, c = i & 7;
       float v = 0.0f;
       for (int sl = 0; sl < slots; ++sl) v += sred[sl * C8 + cc8][c];
-      atomicAdd(dbias + i, v);
+      dbias[(long long)blockIdx.x * C + i] = v;   // row blockIdx.x of the partial sums [gridDim.x][C] (no atomics)
     }
   }
 }
@@ -395,10 +398,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                        const float* __restrict__ w,
                                                        const float* __restrict__ dlogits,
-                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
-                                                       float* __restrict__ db, float* __restrict__ dbias_x,
-                                                       long long n_pix_per_img, int n_img) {
-  // dbias_x != nullptr: also the column sums of dX = the bias gradient of conv12e (network.py:188)
+                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
+                                                       int with_dx_sums, long long n_pix_per_img, int n_img) {
+  // part: partial sums [gridDim.x][194] = dW[2][64], db[2] and (with_dx_sums) the column sums of dX = the bias
+  // gradient of conv12e (network.py:188); summed in row order by the unpack kernel
   const int oct = threadIdx.x & 7;
   float w0[8], w1[8];
 #pragma unroll
@@ -458,15 +461,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const __nv_bfloat16* __re
     sred[warp][129] = sb1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (dbias_x != nullptr ? 194 : 130); i += blockDim.x) {
+  for (int i = threadIdx.x; i < (with_dx_sums ? 194 : 130); i += blockDim.x) {
     float v = 0.0f;
     for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sred[wv][i];
-    if (i < 128)
-      atomicAdd(dw + i, v);
-    else if (i < 130)
-      atomicAdd(db + (i - 128), v);
-    else
-      atomicAdd(dbias_x + (i - 130), v);
+    part[(long long)blockIdx.x * 194 + i] = v;   // row of partial sums: dW[2][64], db[2], column sums of dx [64]
   }
 }
 
@@ -768,7 +766,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
       const int cc8 = i >> 3, c = i & 7;
       float v = 0.0f;
       for (int s = 0; s < slots; ++s) v += sred[s * C8 + cc8][c];
-      atomicAdd(out + i, v);
+      out[(long long)blockIdx.x * C + i] = v;     // row blockIdx.x of the partial sums [gridDim.x][C] (no atomics)
     }
   } else {
     // C8 > 256 never happens for this network (C <= 1024 -> C8 <= 128)
@@ -824,7 +822,7 @@ struct PackJob {
   __nv_bfloat16* dst_b;    // dgrad operand     (pack)
   const float* packed;     // packed fp32 gradient (unpack source)
   float* dw;               // torch-layout gradient (unpack destination)
-  int kind;                // 0 = 3x3 conv, 2 = 2x2 up-conv
+  int kind;                // 0 = 3x3 conv, 2 = 2x2 up-conv, 3 = vector of `cout` elements (partial rows -> bias gradient)
   int cout, cin;
   long long elem_begin;    // prefix sum of element counts over the jobs
   int tile_begin;          // prefix sum of 32x32-channel tile counts (pack_all)
@@ -915,19 +913,56 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restri
     const PackJob jb = jobs[lo];
     const int lt = tile - jb.utile_begin;
     const int Cin = jb.cin, Cout = jb.cout;
+    if (jb.kind == 3) {
+      // vector job (bias gradients, finalconv / conv11c weights): dw[e] = sum over the `slabs` partial rows the
+      // producing kernel's CTAs stored; 32 elements per tile, 8 row lanes added in order
+      __syncthreads();
+      const int e = lt * 32 + ci;
+      float v = 0.0f;
+      if (e < Cout) {
+#pragma unroll 4
+        for (int s = y; s < jb.slabs; s += 8) v += __ldcg(jb.packed + (long long)s * jb.slab_stride + e);
+      }
+      P[y * 32 + ci] = v;
+      __syncthreads();
+      if (y == 0 && e < Cout) {
+        float t = P[ci];
+#pragma unroll
+        for (int l = 1; l < 8; ++l) t += P[l * 32 + ci];
+        jb.dw[e] = accumulate ? jb.dw[e] + t : t;
+      }
+      continue;
+    }
     const int lanes = jb.lanes, co_t = 8 / lanes;
     const int ci_tiles = Cin >> 5;
     const int co0 = (lt / ci_tiles) * co_t, ci0 = (lt % ci_tiles) * 32;
     const int co = co0 + y / lanes, lane = y % lanes;
     const int T = jb.kind == 0 ? 9 : 4;
     __syncthreads();
-    for (int t = 0; t < T; ++t) {
-      const float* src = jb.packed + (jb.kind == 0 ? ((long long)co * 9 + t) * Cin : ((long long)t * Cout + co) * Cin) + ci0 + ci;
-      float v = 0.0f;
-#pragma unroll 8
-      for (int s = lane; s < jb.slabs; s += lanes) v += __ldcg(src + (long long)s * jb.slab_stride);
-      P[(y * 9 + t) * 32 + ci] = v;
+    // all taps of one (co, ci) at once: T independent running sums, so every pass over the slabs keeps T loads in flight
+    const long long tap_stride = jb.kind == 0 ? (long long)Cin : (long long)Cout * Cin;
+    const float* src0 = jb.packed + (jb.kind == 0 ? (long long)co * 9 * Cin : (long long)co * Cin) + ci0 + ci;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = 0.0f;
+    if (jb.kind == 0) {
+#pragma unroll 2
+      for (int s = lane; s < jb.slabs; s += lanes) {
+        const float* sp = src0 + (long long)s * jb.slab_stride;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] += __ldcg(sp + t * tap_stride);
+      }
+    } else {
+#pragma unroll 4
+      for (int s = lane; s < jb.slabs; s += lanes) {
+        const float* sp = src0 + (long long)s * jb.slab_stride;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] += __ldcg(sp + t * tap_stride);
+      }
     }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      if (t < T) P[(y * 9 + t) * 32 + ci] = v[t];
     __syncthreads();
     if (jb.kind == 0) {
       for (int e = threadIdx.x; e < co_t * 288; e += 256) {     // torch [co][ci][t]: 288 contiguous floats per co
@@ -979,6 +1014,17 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restric
     for (int k = 0; k < slabs; ++k) v += __ldg(src + (long long)k * slab_stride + s);
     dw[i] = accumulate ? dw[i] + v : v;
   }
+}
+
+// Partial rows -> vector, one producer, in row order (tests / stand-alone use of the bias-gradient producers):
+// dst[e] (+)= sum_r part[r * stride + e], e < length.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int rows, long long stride,
+                                                              int length, float* __restrict__ dst, int accumulate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= length) return;
+  float v = 0.0f;
+  for (int r = 0; r < rows; ++r) v += __ldg(part + (long long)r * stride + e);
+  dst[e] = accumulate ? dst[e] + v : v;
 }
 
 // ---------------------------------------------------------------------------

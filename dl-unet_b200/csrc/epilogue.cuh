@@ -22,7 +22,7 @@ __device__ __forceinline__ void load_mask(const __nv_bfloat16* mcols, uint4 (&m4
 __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, int relu, bool mask_on, bool mask_valid,
                                            const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                            const float* shead = nullptr, float2* head_part = nullptr,
-                                           bool stage = true, float* scol = nullptr) {
+                                           bool stage = true, float* col_acc = nullptr) {
   if (sbias != nullptr) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -69,18 +69,19 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
     }
     const int chunk = (h * 4 + c) ^ (row & 7);
     sts_u4(ebuf + row * 128 + chunk * 16, o);
-    if (scol != nullptr) {   // keep the stored (masked, bf16-rounded) values for the column sums below
+    if (col_acc != nullptr) {   // keep the stored (masked, bf16-rounded) values for the column sums below
       f[c * 8 + 0] = __uint_as_float(o.x << 16); f[c * 8 + 1] = __uint_as_float(o.x & 0xffff0000u);
       f[c * 8 + 2] = __uint_as_float(o.y << 16); f[c * 8 + 3] = __uint_as_float(o.y & 0xffff0000u);
       f[c * 8 + 4] = __uint_as_float(o.z << 16); f[c * 8 + 5] = __uint_as_float(o.z & 0xffff0000u);
       f[c * 8 + 6] = __uint_as_float(o.w << 16); f[c * 8 + 7] = __uint_as_float(o.w & 0xffff0000u);
     }
   }
-  if (scol != nullptr) {
+  if (col_acc != nullptr) {
     // Column sums over the warp's 32 pixel rows (the bias gradient of the layer that consumes this gradient):
     // recursive halving -- each step a lane keeps one half of its columns and receives the partner's sums of that
-    // half -- 31 shuffles instead of 160, and lane l ends up with the total of column l.  scol: this thread's
-    // 32-column slice of the CTA's shared accumulators.
+    // half -- 31 shuffles instead of 160, and lane l ends up with the total of column l of this warp's 32-column
+    // slice, returned in *col_acc (the caller keeps per-thread running sums in registers: a fixed summation order,
+    // so the bias gradients are bit-reproducible).
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
@@ -92,7 +93,7 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
         f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
       }
     }
-    reds_add_f32(scol + lane, f[0]);
+    *col_acc = f[0];
   }
 }
 
@@ -103,14 +104,14 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
                                           const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                           const float* shead = nullptr, float2* head_part = nullptr,
-                                          bool stage = true, float* scol = nullptr) {
+                                          bool stage = true, float* col_acc = nullptr) {
   uint32_t v[32];
   tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage, scol);
+  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage, col_acc);
 }
 
 }  // namespace ub

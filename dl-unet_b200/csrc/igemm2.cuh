@@ -48,6 +48,7 @@ struct alignas(64) Igemm2Params {
   __nv_bfloat16* pool_cat; // concat buffer view (dense in n, y, x) or nullptr
   int pool_C, cat_H, cat_W, cat_C, c_off;
   int l2_prefetch;            // (unused since the mask tiles travel through shared memory)
+  int dbias_rows;             // rows of the partial-sum buffer p.dbias (>= gridDim.x)
   int aux_bytes;              // bytes between the staging buffers and the mask tile buffers (2048, or 5120 with a head)
   float* dbias;               // fused column sums of the output (bias gradient of the consuming layer) or nullptr
   int dbias_c0;               // channels >= dbias_c0 are summed, into dbias[channel - dbias_c0]
@@ -331,11 +332,10 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
       named_bar_sync(1, 256);
     }
+    // fused bias gradient: per-thread running column sums in registers (static indices only), one per 64-column chunk
+    // of the N <= 256 outputs; combined across the four row quarters in fixed order at the end (deterministic)
     const bool colsum_on = p.dbias != nullptr;
-    if (colsum_on) {
-      scol[et] = 0.0f;
-      named_bar_sync(1, 256);
-    }
+    float cacc0 = 0.0f, cacc1 = 0.0f, cacc2 = 0.0f, cacc3 = 0.0f;
     int it = 0;
     uint32_t chunk_ctr = 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -382,9 +382,17 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
           }
           float2 hp = make_float2(0.0f, 0.0f);
           const long long c1 = (p.prof && et == 0) ? clock64() : 0;
+          float csum = 0.0f;
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
                     true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL,
-                    colsum_on ? scol + n0 + j * 64 + h * 32 : nullptr);
+                    colsum_on ? &csum : nullptr);
+          if (colsum_on) {
+            const int cidx = nt * (BN / 64) + j;   // 64-column chunk of the output channels
+            cacc0 += cidx == 0 ? csum : 0.0f;
+            cacc1 += cidx == 1 ? csum : 0.0f;
+            cacc2 += cidx == 2 ? csum : 0.0f;
+            cacc3 += cidx == 3 ? csum : 0.0f;
+          }
           const long long c2 = (p.prof && et == 0) ? clock64() : 0;
           if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
@@ -475,10 +483,26 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       mbar_arrive(&tempty[acc]);
     }
     if (et == 0 && (HEAD || POOL)) tma_store_wait_all<0>();
-    if (colsum_on) {   // one flush per CTA: 148 x N global atomics in all
-      named_bar_sync(1, 256);
-      const int ch = et;
-      if (ch < p.n_tiles_n * BN && ch >= p.dbias_c0) atomicAdd(p.dbias + ch - p.dbias_c0, scol[ch]);
+    if (colsum_on) {
+      // one flush per CTA, no atomics: the row quarters q = 0..3 add their register sums into scol one after the
+      // other, then the CTA stores its row of the partial sums [dbias_rows][N - c0]; CTAs beyond the grid the host
+      // planned for (ub_set_sm_limit) do not exist, so their rows are zero-filled here
+      const int N = p.n_tiles_n * BN;
+      for (int qq = 0; qq < 4; ++qq) {
+        if (q == qq) {
+          const int col = h * 32 + lane;
+          if (col < N) scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc0;
+          if (64 + col < N) scol[64 + col] = (qq == 0 ? 0.0f : scol[64 + col]) + cacc1;
+          if (128 + col < N) scol[128 + col] = (qq == 0 ? 0.0f : scol[128 + col]) + cacc2;
+          if (192 + col < N) scol[192 + col] = (qq == 0 ? 0.0f : scol[192 + col]) + cacc3;
+        }
+        named_bar_sync(1, 256);
+      }
+      const int ch = et, len = N - p.dbias_c0;
+      if (ch < N && ch >= p.dbias_c0) {
+        p.dbias[(long long)blockIdx.x * len + ch - p.dbias_c0] = scol[ch];
+        for (int r = gridDim.x + blockIdx.x; r < p.dbias_rows; r += gridDim.x) p.dbias[(long long)r * len + ch - p.dbias_c0] = 0.0f;
+      }
     }
     if (p.prof && et == 0) {
       for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 8 + i] = (unsigned long long)prof_acc[i];

@@ -107,12 +107,26 @@ int ub_conv3x3_fwd_pool(const ub_tensor4* x, const void* w_fwd, const float* bia
  * layer that produced x is fused: dx *= (relu_src > 0).  (autograd of network.py:131-188) */
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                      void* stream);
-/* the same, and dbias[c - c0] += sum over pixels of dx[.., c] for the channels c >= c0 (fp32, caller zeroes): the bias
- * gradient of the layer whose output gradient dx is (c0 > 0: the up-conv half of a concat buffer).  Fused into the
- * epilogue where the chosen kernel supports it (shared-memory accumulators, one flush per CTA), one extra
- * column-sum pass over dx otherwise. */
+/* ---- partial sums (bias gradients and the two small weight gradients) ----------------------------------------
+ * Every kernel that reduces over pixels into a short vector leaves PARTIAL ROWS instead of accumulating with atomics:
+ * CTA r stores row r of part[rows][stride]; the rows are summed in row order by ub_unpack_range (vector jobs, kind 3,
+ * of the job table) or ub_reduce_partials -- fixed summation order, bit-reproducible gradients, nothing to zero.
+ * rows = ub_partial_rows(producer, ...): a function of the shape and the SM count only.
+ *   producer 0: ub_pool2x2_bwd with dbias     (n, h, w, c of dx; c_dy, c0 unused)             stride = c
+ *   producer 1: ub_colsum                     (n*h*w pixels, c channels)                       stride = c
+ *   producer 2: ub_conv3x3_dgrad_bias         (n, h, w, c of dx; c_dy channels of dy; c0)      stride = c - c0
+ *   producer 3: ub_head_bwd                   (n, h, w)                                        stride = 194
+ *   producer 4: ub_conv1_wgrad                (n, h, w of the image)                           stride = 640 */
+int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0);
+/* dst[e] (+)= sum_r part[r * stride + e], e < length (one producer; the job table does all of them in one launch) */
+int ub_reduce_partials(const float* part, int rows, long long stride, int length, float* dst, int accumulate, void* stream);
+
+/* ub_conv3x3_dgrad, and partial rows of sum over pixels of dx[.., c] for the channels c >= c0 (row length c - c0): the
+ * bias gradient of the layer whose output gradient dx is (c0 > 0: the up-conv half of a concat buffer).  Fused into
+ * the epilogue where the chosen kernel supports it (register accumulators, one row per CTA), one extra column-sum
+ * pass over dx otherwise. */
 int ub_conv3x3_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
-                          float* dbias, int dbias_c0, void* stream);
+                          float* dbias_part, int dbias_c0, void* stream);
 /* Weight gradients are DETERMINISTIC: the reduction over pixels is split over CTAs (split-K), every split STORES
  * its fp32 partial sums into its own slab and the slabs are added in fixed order by ub_unpack_range / ub_unpack_grad
  * (no atomics anywhere; two runs give bit-identical gradients).
@@ -133,8 +147,8 @@ int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slab
 /* ---- first convolution, Cin = 1 (network.py:131), fp32 NCHW image in, bf16 NHWC out, bias+ReLU fused ---- */
 int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y_bf16, int n, int h, int w_,
                  void* stream);
-/* dw[64*9] += , db[64] += (fp32, caller zeroes) */
-int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* dw, float* db, int n, int h, int w_, void* stream);
+/* partial rows [rows][640]: dW[64][9] then db[64] (producer 4) */
+int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* part, int n, int h, int w_, void* stream);
 
 /* ---- 2x2 max pool (F.max_pool2d(t,2,2); network.py:133,139,145,151) + skip write (network.py:108-127) ----
  * x: dense [n,h,w,c] bf16.  y: dense [n,h/2,w/2,c].  idx: 1 byte per output element, code = dy*2+dx of the
@@ -144,17 +158,18 @@ int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* dw, float* db
 int ub_pool2x2_fwd(const void* x, void* y, unsigned char* idx, const ub_tensor4* cat, int c_off, int n, int h, int w,
                    int c, void* stream);
 /* dx[n,h,w,c] = scatter((dy + window(dcat)) * (pooled > 0)) by idx; dy / dcat may be NULL.
- * dbias (fp32 [c], may be NULL, caller zeroes): += column sums of dx = the bias gradient of the conv that fed the
- * pool (saves the separate ub_colsum pass over dx); needs 256 % (c/8) == 0. */
+ * dbias (may be NULL): partial rows [rows][c] (producer 0) of the column sums of dx = the bias gradient of the conv
+ * that fed the pool (saves the separate ub_colsum pass over dx); needs 256 % (c/8) == 0. */
 int ub_pool2x2_bwd(const void* dy, const ub_tensor4* dcat, int c_off, const unsigned char* idx, const void* pooled,
                    void* dx, float* dbias, int n, int h, int w, int c, void* stream);
 
 /* ---- 1x1 head, 64 -> 2 (network.py:190) and argmax (tester.py:30; trainer.py:82) ---- */
 int ub_head_fwd(const void* x_bf16, const float* w, const float* bias, float* logits_nchw, unsigned char* argmax,
                 int n, int h, int w_, void* stream);
-/* dbias_x (fp32 [64], may be NULL, caller zeroes): += column sums of dx = the bias gradient of conv12e */
-int ub_head_bwd(const void* x_bf16, const float* w, const float* dlogits_nchw, void* dx_bf16, float* dw, float* db,
-                float* dbias_x, int n, int h, int w_, void* stream);
+/* part: partial rows [rows][194] (producer 3) = dW[2][64], db[2] and, if with_dx_sums, the column sums of dx[64] = the
+ * bias gradient of conv12e */
+int ub_head_bwd(const void* x_bf16, const float* w, const float* dlogits_nchw, void* dx_bf16, float* part, int with_dx_sums,
+                int n, int h, int w_, void* stream);
 
 /* ---- pixel-wise weighted loss, forward + dlogits fused (trainer.py:60-75) ----
  * kind 0: BCE-with-logits vs the one-hot target, mean over B*2*L*L (nn.BCEWithLogitsLoss(weight));
@@ -223,8 +238,8 @@ int ub_cut_tiles(const float* image, int h, int w, int row0, int rows, const int
 int ub_stitch_tiles(const unsigned char* masks, const int* tile_ids, int n_tiles, int nx, int tile_out,
                     unsigned char* out, int h, int w, void* stream);
 
-/* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients); out += */
-int ub_colsum(const void* g_bf16, float* out, long long n_pix, int c, long long ld, void* stream);
+/* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients): partial rows [rows][c] (producer 1) */
+int ub_colsum(const void* g_bf16, float* part, long long n_pix, int c, long long ld, void* stream);
 
 /* ---- optim.SGD(lr, momentum=0.99).step() over a flat arena (trainer.py:30,78) ---- */
 int ub_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,

@@ -154,3 +154,28 @@ def test_eval_after_graph_replay_uses_current_weights():
     assert torch.equal(ev2, want)
     assert torch.equal(mask2, want.argmax(1))
     assert not torch.equal(ev1, ev2)         # the step did change the weights
+
+
+def test_testing_tile_route_equals_per_tile_predict(tmp_path):
+    """testing(..., tile_in=...) -- the overlap-tile route of the drop-in (b200.tiling.TileSegmenter behind the
+    reference's signature): the written prediction equals the per-tile predict() masks stitched together."""
+    import numpy as np
+    import tester
+    from network import Unet
+    from b200 import tiling
+    torch.manual_seed(11)
+    net = Unet().to(DEV)
+    size, S = 300, 508                      # label / mirror-padded input size, as ImageDataset_test would deliver
+    raw = torch.rand(size, size)
+    pad = (S - size) // 2
+    image = torch.nn.functional.pad(raw[None, None], (pad,) * 4, mode="reflect")
+    label = (torch.rand(1, 1, size, size) > 0.5).long()
+    tester.testing(net, [(image, label)], 1, DEV, str(tmp_path), tile_in=252)
+    tiles = tiling.cut_tiles(raw.to(DEV), 252)
+    ref = torch.cat([net.predict(tiles[i:i + 1]) for i in range(tiles.shape[0])]).to(torch.uint8)
+    want = tiling.stitch(ref, size, size, 252).cpu().numpy()
+    from PIL import Image
+    got = np.array(Image.open(tmp_path / "preds" / "pred0.tif"))
+    got = got[..., 0] if got.ndim == 3 else got
+    assert np.array_equal(got > 0, want > 0)
+    assert os.path.exists(tmp_path / "test_iou.out")

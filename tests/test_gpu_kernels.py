@@ -460,6 +460,14 @@ def test_unpack_range_sums_slabs_in_fixed_order(ops, n_slabs):
         ref = torch.empty(shape, device=DEV)
         ops.unpack_grad(slabs, ref, kind)
         refs.append(ref)
+    # a vector job (kind 3): 130 elements from column 5 of partial rows 200 elements apart (the bias-gradient producers)
+    part = torch.randn(4 * n_slabs + 1, 200, device=DEV)
+    vec = torch.full((130,), float("nan"), device=DEV)
+    entries.append((vec, vec, vec, part.view(-1)[5:], vec, 3, 130, 200, part.shape[0]))
+    vref = torch.empty(130, device=DEV)
+    ops.reduce_partials(part, part.shape[0], 200, 130, vref, accumulate=False, col=5)
+    torch.testing.assert_close(vref, part[:, 5:135].double().sum(0).float(), rtol=1e-5, atol=1e-5)
+    refs.append(vref)
     table = ops.JobTable(entries, DEV)
     table.unpack_layer(1)
     assert torch.isnan(entries[0][4]).all() and torch.isnan(entries[2][4]).all()       # only layer 1 was written
