@@ -274,7 +274,8 @@ def main():
     # one-hot + weighted BCE, backward, SGD-momentum) as one call -- what dl-unet_b200/trainer.py::training runs per
     # batch.  On one GPU it replays a CUDA graph of the step; with the all-reducer attached (N > 1) it issues the
     # same kernel schedule eagerly so that the gradient buckets can be reduced while backward runs.
-    dp_graph = world > 1 and os.environ.get("UB_DP_GRAPH", "0") == "1"     # experiment: capture the step incl. the all-reduces
+    # N > 1: the step incl. its bucketed all-reduces is captured into one CUDA graph (UB_DP_GRAPH=0: eager schedule)
+    dp_graph = world > 1 and os.environ.get("UB_DP_GRAPH", "1") == "1"
     tstep = T.TrainStep(net, opt, kind="bce", graph=(world == 1 or dp_graph), global_batch=gb, graph_with_allreduce=dp_graph)
     tstep_eager = T.TrainStep(net, opt, kind="bce", graph=False, global_batch=gb)
 
@@ -283,7 +284,7 @@ def main():
 
     step(d_img, d_lab, d_w)  # builds the arenas
     if world > 1:
-        reducer = GradAllReducer(net)
+        reducer = GradAllReducer(net, bucket_mb=float(os.environ.get("UB_DP_BUCKET_MB", "32")))
         reducer.broadcast_parameters(0)
 
     def barrier():
@@ -362,6 +363,7 @@ def main():
                      "n1_equivalent_tiles_per_s": per_gpu / (t_graph * 1e-3),
                      "allreduce_bytes_per_step": net.engine.store.total * 4,
                      "reserve_sms": reducer.reserve_sms, "reserve_kernels": reducer.reserve_kernels,
+                     "bucket_mb": reducer.bucket_elems * 4 / (1 << 20),
                      "schedule": "CUDA graph incl. all-reduces" if dp_graph else "eager schedule + bucketed all-reduce on a high-priority side stream",
                      "what": "compute_only_*: the same per-GPU batch with the all-reducer detached (max over ranks): eager = "
                              "the schedule the timed region uses minus the all-reduces, graph = what one GPU alone runs; "

@@ -70,6 +70,8 @@ class GradAllReducer:
         st = self.engine.store
         if end <= self.start:
             return
+        if hasattr(self.engine, "flush_pending_unpack"):
+            self.engine.flush_pending_unpack()     # slabs / partial rows of the bucket's layers -> gradients, one launch
         if not st.g_arena.is_cuda:  # host-side logic tests (gloo): same bucketing, no streams
             self.works.append(dist.all_reduce(st.g_arena[self.start:end], group=self.group, async_op=True))
             self.start = end

@@ -23,10 +23,6 @@ from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
 # UB_FUSED_POOL_LEVELS=0 restores the separate pool kernel everywhere (experiments)
 FUSED_POOL_LEVELS = int(__import__("os").environ.get("UB_FUSED_POOL_LEVELS", "2"))
 
-# weight-gradient slabs -> torch-layout gradient right after each layer's wgrad (slabs still in L2) instead of one launch
-# over all layers at the end of backward (UB_UNPACK_PER_LAYER=0); the data-parallel schedule always unpacks per layer
-UNPACK_PER_LAYER = __import__("os").environ.get("UB_UNPACK_PER_LAYER", "0") != "0"
-
 PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
 # order in which backward finishes each layer's gradients
 BACKWARD_LAYER_ORDER = [n for (n, _, _, _) in reversed(LAYERS)]
@@ -339,11 +335,22 @@ class Engine:
             self.grad_ready_hook(s, e)
 
     def _finish(self, lname):
-        """Every gradient of `lname` has been produced (slabs / partial rows): per-layer schedules reduce them now."""
-        if self.grad_ready_hook is not None or UNPACK_PER_LAYER:  # data parallel: the layer's gradient must be final now
-            i, j = self._slabs["range"][lname]
-            self._slabs["table"].unpack_layer(i, self._accumulate, j)
+        """Every gradient of `lname` has been produced as slabs / partial rows.  Single device: they are all reduced by
+        one launch at the end of backward.  Data parallel: the layer joins the pending set, which the all-reducer has
+        reduced (flush_pending_unpack, one launch per bucket) right before it sends the bucket."""
+        if self.grad_ready_hook is not None:
+            self._pending.append(lname)
         self._ready(lname)
+
+    def flush_pending_unpack(self):
+        """Slabs / partial rows of the layers finished since the last flush -> final gradients, one launch.  Backward
+        finishes layers in reverse definition order, so their jobs are one contiguous range of the table."""
+        if self._pending:
+            r = self._slabs["range"]
+            i = min(r[l][0] for l in self._pending)
+            j = max(r[l][1] for l in self._pending)
+            self._slabs["table"].unpack_layer(i, self._accumulate, j)
+            self._pending = []
 
     def _conv_bwd(self, lname, x, dy, dx, relu_src, bias_done=False, dx_bias=None, dx_bias_c0=0):
         """wgrad + bias grad (+ dgrad when dx is not None) of one 3x3 conv layer.  bias_done: the kernel that
@@ -369,6 +376,7 @@ class Engine:
         self._accumulate = all(
             p.grad is not None and p.grad.data_ptr() == st.grad_view(n).data_ptr() for n, p in st.params().items())
         self._slabs = ws.grad_slabs(st)
+        self._pending = []
         part = self._slabs["part"]
         P, pk = st.p, st.packs
         dlogits = dlogits.contiguous().float()
@@ -409,7 +417,7 @@ class Engine:
             else:
                 ops.conv1_wgrad(ws.image, gr["e11"], part=part["conv11c.weight"])
                 self._finish("conv11c")
-        if self.grad_ready_hook is None and not UNPACK_PER_LAYER:
+        if self.grad_ready_hook is None:
             self._slabs["table"].unpack_all(self._accumulate)   # single device: all 46 gradients in one launch
         if self.grad_done_hook is not None:
             self.grad_done_hook()

@@ -52,7 +52,8 @@ SIGNATURES = {
     "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
     "ub_upconv2x2_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_conv1_fwd": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
-    "ub_conv1_wgrad": (_i, [_P, _P, _P, _i, _i, _i, _P]),
+    "ub_conv1_wgrad_workspace_bytes": (_ll, [_i, _i, _i]),
+    "ub_conv1_wgrad": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
     "ub_pool2x2_fwd": (_i, [_P, _P, _P, _T4, _i, _i, _i, _i, _i, _P]),
     "ub_pool2x2_bwd": (_i, [_P, _T4, _i, _P, _P, _P, _P, _i, _i, _i, _i, _P]),
     "ub_head_fwd": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _P]),

@@ -358,15 +358,25 @@ def conv1_fwd(image, w, bias, y):
     return y
 
 
-def conv1_wgrad(image, dy, dw=None, db=None, part=None):
+_CONV1_WS = {}
+
+
+def conv1_wgrad(image, dy, dw=None, db=None, part=None, ws=None):
     """conv11c weight + bias gradient.  part: [partial_rows(PROD_CONV1, n, h, w), 640] receives the partial rows
     (dW[64][9] then db[64]); otherwise they are reduced here and ADDED to dw / db."""
     n, _, h, wd = image.shape
     own = part is None
     if own:
         part = _part(partial_rows(PROD_CONV1, n, h, wd), CONV1_STRIDE, image)
+    if ws is None:      # scratch for the bf16 image copy (tensor-pipe path)
+        key = (n, h, wd, str(image.device))
+        ws = _CONV1_WS.get(key)
+        if ws is None:
+            ws = _CONV1_WS[key] = torch.empty(_lib.load().ub_conv1_wgrad_workspace_bytes(n, h, wd), dtype=torch.uint8,
+                                              device=image.device)
     with _timed("hbm:conv1_wgrad", n * (h * wd * 4.0 + (h - 2) * (wd - 2) * 128.0)):
-        _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(part), n, h, wd, _stream()), "conv1_wgrad")
+        _chk(_lib.load().ub_conv1_wgrad(_ptr(image), _ptr(dy), _ptr(part), _ptr(ws), n, h, wd, _stream()), "conv1_wgrad")
+        STATS.launches += 1   # the image conversion kernel
     if own:
         reduce_partials(part, part.shape[0], CONV1_STRIDE, 576, dw, True)
         reduce_partials(part, part.shape[0], CONV1_STRIDE, 64, db, True, col=576)

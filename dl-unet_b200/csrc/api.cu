@@ -39,6 +39,8 @@ int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_mask_l2_prefetch = 1;
 int g_igemm_dbg = 0;
+int g_conv1_dbg = 0;
+int g_conv1_wgrad_tc = 1;   // conv11c weight gradient on the tensor pipe (0: CUDA-core kernel)
 int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -257,6 +259,18 @@ int launch_wgrad_t(const WgradParams& P, int smem_bytes, cudaStream_t st) {
   const long long units = (long long)P.items * P.splits;
   const int grid = (int)(units < num_sms() ? units : num_sms());
   wgrad_kernel<BN><<<grid, 256, smem_bytes, st>>>(P);
+  return (int)cudaGetLastError();
+}
+int launch_wgrad_conv1(const WgradParams& P, int smem_bytes, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long units = (long long)P.items * P.splits;
+  const int grid = (int)(units < num_sms() ? units : num_sms());
+  wgrad_kernel<32, true><<<grid, 256, smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
 }
 int launch_wgrad(const WgradParams& P, int BN, int smem_bytes, cudaStream_t st) {
@@ -746,6 +760,8 @@ void ub_set_option(int key, int value) {
   if (key == 2) g_igemm2_mode = value;
   if (key == 5) g_igemm_dbg = value;
   if (key == 7) g_map_cache_on = value;
+  if (key == 8) g_conv1_wgrad_tc = value;
+  if (key == 9) g_conv1_dbg = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }
@@ -1159,14 +1175,64 @@ int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y,
   return (int)cudaGetLastError();
 }
 
-int ub_conv1_wgrad(const float* image, const void* dy, float* part, int n, int h, int w_, void* stream) {
+// conv11c weight + bias gradient on the tensor pipe (wgrad.cuh, CONV1): geometry shared by the launch, the workspace
+// query and ub_partial_rows.
+static void conv1_wgrad_plan(int n, int h, int w_, WgradParams& P) {
+  memset(&P, 0, sizeof(P));
+  P.KW = 64;
+  P.KH = 1;
+  P.ksteps = 4;
+  P.blk_bytes = 64 * 128;
+  P.stage_bytes = 2 * P.blk_bytes + 4096;   // dY block (+ the unused second M block) + four 8-row groups of the tap tile
+  P.nstage = WgradCfg::SMEM_LIMIT / P.stage_bytes;
+  if (P.nstage > WgradCfg::MAX_STAGES) P.nstage = WgradCfg::MAX_STAGES;
+  P.chunks_x = (w_ - 2 + 63) / 64;
+  P.chunks_y = h - 2;
+  P.total_chunks = n * P.chunks_x * P.chunks_y;
+  P.Cout = 64;
+  P.Cin = 16;
+  P.m_rows = 64;
+  P.n_taps = 1;
+  P.m_tiles = P.n_tiles = P.items = 1;
+  const SplitPlan sp = plan_splits(1, P.total_chunks, 8, 2.0);
+  P.splits = sp.splits;
+  P.per = sp.per;
+  P.img_H = h;
+}
+static int conv1_pitch(int w_) { return (w_ + 7) / 8 * 8; }
+
+long long ub_conv1_wgrad_workspace_bytes(int n, int h, int w_) {
+  if (n <= 0 || h < 3 || w_ < 3) return 0;
+  return 3ll * n * h * conv1_pitch(w_) * 2;   // three shifted bf16 copies of the image
+}
+
+int ub_conv1_wgrad(const float* image, const void* dy, float* part, void* ws_bf16, int n, int h, int w_, void* stream) {
   if (!image || !dy || !part) return UB_E_ARG;
   if (h < 3 || w_ < 3 || n <= 0) return UB_E_SHAPE;
   if (!aligned16(dy)) return UB_E_ALIGN;
   if (n > 65535) return UB_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_conv1_wgrad_tc && ws_bf16) {
+    if (!aligned16(ws_bf16)) return UB_E_ALIGN;
+    WgradParams P;
+    conv1_wgrad_plan(n, h, w_, P);
+    const int pitch = conv1_pitch(w_);
+    const long long rows = (long long)n * h;
+    image_to_bf16_kernel<<<ew_grid(rows * pitch), 256, 0, st>>>(image, (__nv_bfloat16*)ws_bf16, w_, pitch, rows);
+    ub_tensor4 dyv{const_cast<void*>(dy), n, h - 2, w_ - 2, 64, (long long)(h - 2) * (w_ - 2) * 64, (long long)(w_ - 2) * 64, 64};
+    int e;
+    if ((e = make_map4(&P.a_map[0], &dyv, 64, 1))) return e;
+    for (int sft = 0; sft < 3; ++sft)
+      if ((e = make_map2(&P.a_map[1 + sft], reinterpret_cast<const __nv_bfloat16*>(ws_bf16) + sft * rows * pitch, pitch, rows, 3)))
+        return e;
+    P.b_map = P.a_map[1];
+    P.dw = part;
+    P.dbg = g_conv1_dbg;
+    return launch_wgrad_conv1(P, P.nstage * P.stage_bytes + WgradCfg::BAR_BYTES + 1024, st);
+  }
   const int rpb = conv1_wgrad_rpb(n, h);
   const dim3 grid((h - 2 + rpb - 1) / rpb, n);
-  conv1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image, (const __nv_bfloat16*)dy, part, n, h, w_, rpb);
+  conv1_wgrad_kernel<<<grid, 256, 0, st>>>(image, (const __nv_bfloat16*)dy, part, n, h, w_, rpb);
   return (int)cudaGetLastError();
 }
 
@@ -1472,6 +1538,11 @@ int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) 
     }
     case 3: return head_bwd_blocks((long long)n * h * w);
     case 4: {
+      if (g_conv1_wgrad_tc) {
+        WgradParams P;
+        conv1_wgrad_plan(n, h, w, P);
+        return P.splits;
+      }
       const int rpb = conv1_wgrad_rpb(n, h);
       return ((h - 2 + rpb - 1) / rpb) * n;
     }

@@ -113,7 +113,23 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   }
 }
 
-// conv11c weight + bias gradient: dW[co, tap] = sum_p dY[p, co] * x[p + tap], db[co] = sum_p dY[p, co].
+// fp32 image [n][H][W] -> three bf16 copies [3][n*H][pitch], copy s shifted left by s pixels (copy_s[x] = image[x + s],
+// zero beyond the row; pitch = W rounded up to 8 elements): the B operand source of the tensor-pipe conv11c weight
+// gradient (wgrad.cuh, CONV1), whose TMA boxes need 16-byte aligned starts and row strides.
+__global__ void __launch_bounds__(256) image_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            int W, int pitch, long long rows) {
+  const long long plane = rows * pitch;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < plane; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / pitch;
+    const int c = (int)(g - r * pitch);
+    const float* xr = x + r * W;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) y[s * plane + g] = __float2bfloat16_rn(c + s < W ? __ldg(xr + c + s) : 0.0f);
+  }
+}
+
+// conv11c weight + bias gradient, CUDA-core version (kept as the comparator of the tensor-pipe one; ub_set_option(8, 0)):
+// dW[co, tap] = sum_p dY[p, co] * x[p + tap], db[co] = sum_p dY[p, co].
 // dY is bf16 NHWC (already ReLU-masked), 8 KB per 64-pixel tile, streamed through a 3-stage cp.async ring together
 // with the tile's 3 x 66 image window, so ~16 KB per block (5 blocks per SM) are in flight whatever the compute
 // does.  Thread = (pixel slot, channel octet, tap half): half 0 accumulates taps 0..4, half 1 taps 5..8 and the

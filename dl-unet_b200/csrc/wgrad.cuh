@@ -37,6 +37,8 @@ struct alignas(64) WgradParams {
   int chunks_x, chunks_y, total_chunks;
   int Cout, Cin;
   int nstage, stage_bytes, blk_bytes;  // pipeline geometry, chosen by the host: blk_bytes = KW*KH*128
+  int img_H;             // CONV1: rows per image of the 2-D bf16 image map in b_map
+  int dbg;               // bring-up switches (ub_set_option 9): 1 no B loads, 2 no MMAs, 4 no TMEM read-out, 8 no init of constant rows
   float* dw;             // slabs [splits][packed layout]: conv [co][9][ci], up-conv [(ab,co)][ci]
   long long slab_stride; // elements between slabs
 };
@@ -61,7 +63,17 @@ __device__ __forceinline__ WgradUnit wgrad_unit(const WgradParams& p, int u) {
   return w;
 }
 
-template <int BN>
+// CONV1 (BN = 32): the weight + bias gradient of conv11c (Cin = 1, network.py:131) on the same pipeline.
+//   dW[co, tap] = sum_p dY[p, co] * x[p + tap],  db[co] = sum_p dY[p, co]
+// is a GEMM with M = 64 channels, N = 32 columns (9 taps, a column of ones for the bias, the rest unused), K = pixels.
+// A = dY as everywhere else (MN-major, one 64-channel block).  B is K-MAJOR, four 8-row SWIZZLE_128B groups of 64
+// pixels (128 B) per row: group s = 0..2 receives ONE TMA box {64 pixels, 3 rows} of the bf16 image copy SHIFTED by s
+// pixels (p.a_map[1 + s]: 2-D maps over three copies [n*H][pitch], copy_s[x] = image[x + s] -- a TMA box must start on
+// a 16-byte boundary of global memory, which a one-pixel shift of a one-channel image is not), i.e. its rows 0..2 are
+// the taps (r, s), r = 0..2; every box lands on a 1024-byte boundary of shared memory; row 0 of group 3 holds ones,
+// written once per stage at kernel start.  Column of tap (r, s) = 8 s + r, bias = column 24.  A chunk is 64 pixels of one output row.
+// Every unit stores one row of partial sums [640] = dW[64][9], db[64] into p.dw (summed in order by the unpack kernel).
+template <int BN, bool CONV1 = false>
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   using C = WgradCfg;
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +84,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   uint64_t* tfull = empty + C::MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int ACC_COLS = CONV1 ? 32 : BN;        // TMEM columns between the two accumulators
+  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +109,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
+  }
+  if (CONV1 && !(p.dbg & 8)) {
+    // the rows of every stage's B tile that no TMA box writes: rows 3..7 of the tap groups and rows 1..7 of group 3 =
+    // zeros (unused columns), row 0 of group 3 = ones (bias column).  All 64 values of a row are equal, so the 128-byte
+    // swizzle is immaterial.
+    for (int i = threadIdx.x; i < NSTAGE * 32 * 32; i += blockDim.x) {
+      const int st = i / (32 * 32), r = (i / 32) % 32, c = i % 32;
+      if (r >= 24 || (r & 7) >= 3)
+        *reinterpret_cast<uint32_t*>(smem + st * STAGE_BYTES + 2 * BLK + r * 128 + c * 4) = r == 24 ? 0x3F803F80u : 0u;
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -121,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const CUtensorMap* am_a = &p.a_map[map_a];
       const CUtensorMap* am_b = &p.a_map[map_b];
       const int dx = p.tap_dx[w.tap], dy = p.tap_dy[w.tap];
-      const uint32_t tx_bytes = (uint32_t)(nblk + BN / 64) * (uint32_t)BLK;
+      const uint32_t tx_bytes = CONV1 ? (uint32_t)BLK + ((p.dbg & 1) ? 0u : 3u * 384u) : (uint32_t)(nblk + BN / 64) * (uint32_t)BLK;
       const int c_begin = w.split * p.per;
       const int c_end = min(p.total_chunks, c_begin + p.per);
       int cx = c_begin % p.chunks_x;
@@ -136,10 +160,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           uint8_t* sb = sa + 2 * BLK;
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, am_a, &full[stage], ch_a, x0, y0, img);
-          if (nblk > 1) tma_load_4d(sa + BLK, am_b, &full[stage], ch_b, x0, y0, img);
+          if (CONV1) {
+            if (!(p.dbg & 1))
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b)
-            tma_load_4d(sb + b * BLK, &p.b_map, &full[stage], w.nt * BN + b * 64, x0 + dx, y0 + dy, img);
+            for (int sft = 0; sft < 3; ++sft)   // box {64 pixels, 3 rows} of the image copy shifted by sft: taps (0..2, sft)
+              tma_load_2d(sb + sft * 1024, &p.a_map[1 + sft], &full[stage], x0 + ((p.dbg & 16) ? sft : 0), img * p.img_H + y0);
+          } else {
+            if (nblk > 1) tma_load_4d(sa + BLK, am_b, &full[stage], ch_b, x0, y0, img);
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_4d(sb + b * BLK, &p.b_map, &full[stage], w.nt * BN + b * 64, x0 + dx, y0 + dy, img);
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) {
@@ -157,11 +188,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, CONV1 ? 0 : 1);
     const uint32_t hiD = umma_desc_hi(1024);
-    // MN-major: LBO = distance between the 64-element M / N blocks, SBO = 1024 B between 8-row K groups
+    // MN-major: LBO = distance between the 64-element M / N blocks, SBO = 1024 B between 8-row K groups;
+    // CONV1: B is K-major (rows = taps, 128 B = 64 pixels of K per row): SBO = 1024 B between 8-row groups, 32 B per K step
     const uint32_t loA0 = umma_desc_lo(smem_u32(smem), (uint32_t)BLK);
-    const uint32_t loB0 = umma_desc_lo(smem_u32(smem) + 2 * BLK, (uint32_t)BLK);
+    const uint32_t loB0 = umma_desc_lo(smem_u32(smem) + 2 * BLK, CONV1 ? 16u : (uint32_t)BLK);
+    constexpr uint32_t kstepB = CONV1 ? 2u : 128u;
     const uint32_t stage16 = (uint32_t)STAGE_BYTES >> 4;
     const int ksteps = p.ksteps;
     int stage = 0;
@@ -174,7 +207,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 8);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int i = 0; i < n_iters; ++i) {
         mbar_wait(&full[stage], phase, 6);
         tc_fence_after();
@@ -182,8 +215,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           const uint32_t so = stage * stage16;
           // 16 pixels (K) per MMA = two 8-row groups = 2048 B (>>4 = 128)
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + 128 * k), idesc,
+          for (int k = 0; k < ((CONV1 && (p.dbg & 2)) ? 0 : ksteps); ++k)
+            umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + kstepB * k), idesc,
                       (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (i == n_iters - 1) umma_commit(&tfull[acc]);
@@ -210,9 +243,20 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       float* drow = p.dw + (long long)w.split * p.slab_stride + prow * p.Cin + w.nt * BN;
       mbar_wait(&tfull[acc], (it >> 1) & 1, 7);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      if (CONV1 && !(p.dbg & 4)) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_addr, v);   // column 8 s + r = tap (r, s), column 24 = bias
+        tmem_ld_wait();
+        if (m < 64) {
+          float* prow_ = p.dw + (long long)u * 640;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) prow_[m * 9 + t] = __uint_as_float(v[(t % 3) * 8 + t / 3]);
+          prow_[576 + m] = __uint_as_float(v[24]);
+        }
+      }
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = 0; j < (CONV1 ? 0 : BN / 32); ++j) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_addr + j * 32, v);
         tmem_ld_wait();

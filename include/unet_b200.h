@@ -57,7 +57,8 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  * key 2: 3x3 fwd/dgrad kernel (0 = tap-per-load igemm only, 1 = haloed-patch kernel on wide shallow layers [default],
  *        2 = wherever legal).
  * key 5: igemm ablation (1 = do not wait for earlier TMA stores): timing experiments only.
- * key 7: host-side cache of encoded TMA tensor maps (1 = on [default], 0 = encode on every call). */
+ * key 7: host-side cache of encoded TMA tensor maps (1 = on [default], 0 = encode on every call).
+ * key 8: conv11c weight gradient on the tensor pipe (1 = on [default], 0 = CUDA-core kernel). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------
@@ -147,8 +148,12 @@ int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slab
 /* ---- first convolution, Cin = 1 (network.py:131), fp32 NCHW image in, bf16 NHWC out, bias+ReLU fused ---- */
 int ub_conv1_fwd(const float* image, const float* w, const float* bias, void* y_bf16, int n, int h, int w_,
                  void* stream);
-/* partial rows [rows][640]: dW[64][9] then db[64] (producer 4) */
-int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* part, int n, int h, int w_, void* stream);
+/* partial rows [rows][640]: dW[64][9] then db[64] (producer 4).  ws_bf16 (ub_conv1_wgrad_workspace_bytes, 16-byte
+ * aligned): scratch for a bf16 copy of the image -- with it the gradient runs on the tensor pipe (the image enters the
+ * products rounded to bf16; exact for bf16-representable images); NULL or ub_set_option(8, 0): CUDA-core kernel on the
+ * fp32 image.  The row count depends on which of the two runs (ub_partial_rows reports it for the current option). */
+long long ub_conv1_wgrad_workspace_bytes(int n, int h, int w_);
+int ub_conv1_wgrad(const float* image, const void* dy_bf16, float* part, void* ws_bf16, int n, int h, int w_, void* stream);
 
 /* ---- 2x2 max pool (F.max_pool2d(t,2,2); network.py:133,139,145,151) + skip write (network.py:108-127) ----
  * x: dense [n,h,w,c] bf16.  y: dense [n,h/2,w/2,c].  idx: 1 byte per output element, code = dy*2+dx of the

@@ -17,10 +17,8 @@ net = Unet().to(dev)
 opt = T.FusedSGD(net)
 images, labels, weight = synth.synthetic_batch(batch, 572, seed=1)
 x, y, w = images.to(dev), labels[:, 0].to(torch.uint8).to(dev), weight.to(dev)
+step = T.TrainStep(net, opt, graph=False)      # the schedule bench.py times (there replayed as one CUDA graph), issued eagerly
 for i in range(steps):
-    opt.zero_grad()
-    loss = T.weighted_bce_with_logits(net(x), y, w)
-    loss.backward()
-    opt.step()
+    loss = step(x, y, w)
 torch.cuda.synchronize()
 print("loss", loss.item())

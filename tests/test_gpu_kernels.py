@@ -267,9 +267,37 @@ def test_conv1(ops):
     assert rel_l2(nchw(y), F.relu(pre)) < BF16_OUT_TOL
     dy = bf(torch.randn(n, h - 2, w - 2, 64, device=DEV))
     gw, gb = torch.autograd.grad(pre, (w1, b1), nchw(dy))
-    dw, db = torch.zeros(64, 9, device=DEV), torch.zeros(64, device=DEV)
-    ops.conv1_wgrad(img, dy, dw, db)
-    assert rel_l2(dw.view(64, 1, 3, 3), gw) < FP32_TOL and rel_l2(db, gb) < FP32_TOL
+    # CUDA-core comparator kernel (option 8 = 0): fp32 image, fp32 products
+    ops.set_option(8, 0)
+    try:
+        dw, db = torch.zeros(64, 9, device=DEV), torch.zeros(64, device=DEV)
+        ops.conv1_wgrad(img, dy, dw, db)
+        assert rel_l2(dw.view(64, 1, 3, 3), gw) < FP32_TOL and rel_l2(db, gb) < FP32_TOL
+    finally:
+        ops.set_option(8, 1)
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 44), (3, 100, 200), (1, 67, 131), (16, 190, 190), (1, 3, 3)])
+def test_conv1_wgrad_tensor_pipe(ops, shape):
+    """conv11c weight + bias gradient as a K-major-B tcgen05 GEMM (wgrad.cuh, CONV1): exact products for a
+    bf16-representable image (what the parity tests and the benchmark feed), image rounded to bf16 otherwise;
+    deterministic partial rows."""
+    n, h, w = shape
+    torch.manual_seed(sum(shape))
+    img = torch.rand(n, 1, h, w, device=DEV)
+    dy = bf(torch.randn(n, h - 2, w - 2, 64, device=DEV))
+    for image, tol in ((bf(img).float(), FP32_TOL), (img, 4e-3)):
+        w1 = torch.zeros(64, 1, 3, 3, device=DEV, requires_grad=True)
+        b1 = torch.zeros(64, device=DEV, requires_grad=True)
+        gw, gb = torch.autograd.grad(F.conv2d(image, w1, b1), (w1, b1), nchw(dy).float())
+        dw, db = torch.zeros(64, 9, device=DEV), torch.zeros(64, device=DEV)
+        ops.conv1_wgrad(image, dy, dw, db)
+        assert rel_l2(dw.view(64, 1, 3, 3), gw) < tol and rel_l2(db, gb) < FP32_TOL
+    rows = ops.partial_rows(ops.PROD_CONV1, n, h, w)
+    parts = [torch.full((rows, ops.CONV1_STRIDE), float("nan"), device=DEV) for _ in range(2)]
+    for part in parts:
+        ops.conv1_wgrad(img, dy, part=part)
+    assert torch.equal(parts[0], parts[1]) and not torch.isnan(parts[0]).any()
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 12), (1, 8, 8, 128, 8), (2, 20, 20, 64, 8), (1, 24, 24, 256, 20), (1, 11, 11, 64, 7)])
