@@ -284,7 +284,18 @@ def main():
 
     step(d_img, d_lab, d_w)  # builds the arenas
     if world > 1:
-        reducer = GradAllReducer(net, bucket_mb=float(os.environ.get("UB_DP_BUCKET_MB", "32")))
+        # gradient exchange: our own NVLS / peer-memory all-reduce on the compute stream (default), or the bucketed NCCL
+        # all-reduce on a side stream (UB_DP_ALLREDUCE=nccl, also the fallback where symmetric memory is unavailable)
+        mode = os.environ.get("UB_DP_ALLREDUCE", "symm")
+        if mode != "nccl":
+            try:
+                from b200.symm import SymmAllReducer
+                reducer = SymmAllReducer(net, use_multicast=(mode != "peer"))
+            except Exception as e:  # noqa: BLE001
+                print(f"rank {rank}: symmetric-memory all-reduce unavailable ({e!r}); using NCCL", file=sys.stderr)
+                mode = "nccl"
+        if mode == "nccl":
+            reducer = GradAllReducer(net, bucket_mb=float(os.environ.get("UB_DP_BUCKET_MB", "32")))
         reducer.broadcast_parameters(0)
 
     def barrier():
@@ -362,9 +373,10 @@ def main():
                      "eager_vs_graph_ms": t_eager - t_graph,
                      "n1_equivalent_tiles_per_s": per_gpu / (t_graph * 1e-3),
                      "allreduce_bytes_per_step": net.engine.store.total * 4,
-                     "reserve_sms": reducer.reserve_sms, "reserve_kernels": reducer.reserve_kernels,
-                     "bucket_mb": reducer.bucket_elems * 4 / (1 << 20),
-                     "schedule": "CUDA graph incl. all-reduces" if dp_graph else "eager schedule + bucketed all-reduce on a high-priority side stream",
+                     "allreduce": ("own kernels over symmetric memory, " + ("NVLS multimem.ld_reduce / multimem.st" if reducer.multicast else "peer loads / stores")
+                                   + ", on the compute stream after backward") if hasattr(reducer, "multicast") else
+                                  f"NCCL, buckets of {reducer.bucket_elems * 4 / (1 << 20):.0f} MB on a high-priority side stream",
+                     "schedule": "one CUDA graph incl. the exchange" if dp_graph else "eager kernel schedule",
                      "what": "compute_only_*: the same per-GPU batch with the all-reducer detached (max over ranks): eager = "
                              "the schedule the timed region uses minus the all-reduces, graph = what one GPU alone runs; "
                              "exposed_allreduce = timed step - compute_only_eager"}

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ub_colsum": (_i, [_P, _P, _ll, _i, _ll, _P]),
     "ub_partial_rows": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "ub_reduce_partials": (_i, [_P, _i, _ll, _i, _P, _i, _P]),
+    "ub_allreduce_sym": (_i, [C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _i, _i, _ll, _ll, _i, _i, _i, _P]),
     "ub_sgd_momentum": (_i, [_P, _P, _P, _ll, _f, _f, _i, _P]),
 }
 # include/unet_b200_diag.h: only in libunet_b200_diag.so (make libunet_b200_diag.so), never in the product library

@@ -25,6 +25,7 @@
 #ifdef UB_DIAGNOSTICS
 #include "probe.cuh"
 #endif
+#include "allreduce.cuh"
 #include "wgrad.cuh"
 #include "wgrad3.cuh"
 #include "wgrad4.cuh"
@@ -1553,6 +1554,44 @@ int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) 
 int ub_reduce_partials(const float* part, int rows, long long stride, int length, float* dst, int accumulate, void* stream) {
   if (!part || !dst || rows < 1 || length < 1) return UB_E_ARG;
   reduce_partials_kernel<<<(length + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, rows, stride, length, dst, accumulate);
+  return (int)cudaGetLastError();
+}
+
+int ub_allreduce_sym(void* const* peer_ptrs, void* const* flag_ptrs, void* mc_ptr, unsigned int* step_ctr,
+                     unsigned int* done_ctr, int rank, int world, long long begin, long long end, int bucket, int n_buckets,
+                     int phases, void* stream) {
+  if (!peer_ptrs || !flag_ptrs || !step_ctr || !done_ctr) return UB_E_ARG;
+  if (world < 1 || world > AR_MAX_RANKS || rank < 0 || rank >= world || bucket < 0 || bucket >= AR_MAX_BUCKETS ||
+      n_buckets < 1 || n_buckets > AR_MAX_BUCKETS || begin < 0 || end <= begin || (begin % 4) || (end % 4))
+    return UB_E_SHAPE;
+  ArParams P;
+  memset(&P, 0, sizeof(P));
+  for (int k = 0; k < world; ++k) {
+    if (!peer_ptrs[k] || !flag_ptrs[k] || !aligned16(peer_ptrs[k])) return UB_E_ARG;
+    P.peer[k] = (float*)peer_ptrs[k];
+    P.flags[k] = (unsigned int*)flag_ptrs[k];
+  }
+  P.mc = (float*)mc_ptr;
+  P.step = step_ctr;
+  P.done_ctr = done_ctr;
+  P.rank = rank;
+  P.world = world;
+  P.bucket = bucket;
+  P.begin = begin;
+  P.end = end;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (phases & 1) ar_bump_kernel<<<1, 1, 0, st>>>(step_ctr);
+  if (phases & 2) ar_signal_kernel<<<1, 32, 0, st>>>(P);
+  if (phases & 4) {
+    // this rank's part: (end - begin) / world elements; every thread keeps two 16-byte round trips in flight
+    const long long part4 = ((end - begin) / 4 + world - 1) / world;
+    long long blocks = (part4 + 2 * 512 - 1) / (2 * 512);
+    if (blocks > 4ll * num_sms_physical()) blocks = 4ll * num_sms_physical();
+    if (blocks < 1) blocks = 1;
+    if (P.mc) ar_reduce_kernel<true><<<(int)blocks, 512, 0, st>>>(P);
+    else ar_reduce_kernel<false><<<(int)blocks, 512, 0, st>>>(P);
+  }
+  if (phases & 8) ar_gate_kernel<<<1, 256, 0, st>>>(P, n_buckets);
   return (int)cudaGetLastError();
 }
 

@@ -246,6 +246,19 @@ int ub_stitch_tiles(const unsigned char* masks, const int* tile_ids, int n_tiles
 /* column sums of a bf16 [n_pix, c] view with pixel stride ld (bias gradients): partial rows [rows][c] (producer 1) */
 int ub_colsum(const void* g_bf16, float* part, long long n_pix, int c, long long ld, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink / NVSwitch peer memory (SURVEY.md 8 row e-train; csrc/allreduce.cuh) ----
+ * Sum all-reduce, in place, of elements [begin, end) of an fp32 arena that every rank holds in SYMMETRIC memory:
+ * peer_ptrs[k] = the arena of rank k as mapped into this process, flag_ptrs[k] = its flag pad (>= 2 * 32 * 16 uint32,
+ * zeroed once), mc_ptr = the multicast address of the arenas (NVLS: in-switch reduction and broadcast through
+ * multimem.ld_reduce / multimem.st) or NULL (peer loads added in rank order, one store per peer).  step_ctr / done_ctr:
+ * local device uint32, zeroed once.  phases (bit mask, launched in this order on `stream`): 1 = ++step (once per
+ * training step), 2 = signal "my gradients of `bucket` are final" to every peer, 4 = reduce this rank's 1/world part
+ * once every rank has signalled and broadcast it, 8 = wait until all parts of buckets [0, n_buckets) have arrived.
+ * Every rank must issue the same sequence; all waits are bounded. */
+int ub_allreduce_sym(void* const* peer_ptrs, void* const* flag_ptrs, void* mc_ptr, unsigned int* step_ctr,
+                     unsigned int* done_ctr, int rank, int world, long long begin, long long end, int bucket, int n_buckets,
+                     int phases, void* stream);
+
 /* ---- optim.SGD(lr, momentum=0.99).step() over a flat arena (trainer.py:30,78) ---- */
 int ub_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, int first_step,
                     void* stream);

@@ -28,7 +28,13 @@ opt = T.FusedSGD(net)
 # prime the arenas, then attach the reducer (small buckets so that several all-reduces overlap backward)
 opt.zero_grad()
 T.weighted_bce_with_logits(net(images[lo:hi].to(dev)), labels[lo:hi].to(dev), weight[lo:hi].to(dev), global_batch=G).backward()
-red = GradAllReducer(net, bucket_mb=8.0)
+if os.environ.get("UB_DP_ALLREDUCE", "symm") == "nccl":
+    red = GradAllReducer(net, bucket_mb=8.0)          # bucketed NCCL all-reduce on a side stream
+else:
+    from b200.symm import SymmAllReducer
+    red = SymmAllReducer(net, use_multicast=os.environ.get("UB_DP_ALLREDUCE", "symm") != "peer")   # own NVLS / peer kernels
+    if rank == 0:
+        print("symmetric-memory all-reduce, multicast:", red.multicast, flush=True)
 torch.manual_seed(0)
 ref_sd = Unet().state_dict()
 net.load_state_dict(ref_sd)

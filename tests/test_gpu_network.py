@@ -300,9 +300,11 @@ def test_gradients_are_bit_reproducible():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_data_parallel_gradients_equal_single_gpu():
+@pytest.mark.parametrize("mode", ["symm", "peer", "nccl"])
+def test_data_parallel_gradients_equal_single_gpu(mode):
     """tests/gpu_dp_check.py under torchrun on 2 GPUs: all-reduced DP gradients == single-GPU gradients of the
-    concatenated batch, weights bit-identical across ranks after 3 steps (SURVEY.md 8 e-train)."""
+    concatenated batch, weights bit-identical across ranks after 3 steps (SURVEY.md 8 e-train) -- with our own
+    all-reduce over symmetric memory (NVLS multicast, peer loads / stores) and with the bucketed NCCL all-reduce."""
     import socket
     import subprocess
     import sys
@@ -312,6 +314,6 @@ def test_data_parallel_gradients_equal_single_gpu():
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "gpu_dp_check.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, UB_DP_ALLREDUCE=mode))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("PASS") == 2, r.stdout[-2000:]
