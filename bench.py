@@ -244,7 +244,6 @@ def main():
     from network import Unet
     from b200 import ops, synth
     from b200 import train as T
-    from b200.dist import GradAllReducer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -286,16 +285,8 @@ def main():
     if world > 1:
         # gradient exchange: our own NVLS / peer-memory all-reduce on the compute stream (default), or the bucketed NCCL
         # all-reduce on a side stream (UB_DP_ALLREDUCE=nccl, also the fallback where symmetric memory is unavailable)
-        mode = os.environ.get("UB_DP_ALLREDUCE", "symm")
-        if mode != "nccl":
-            try:
-                from b200.symm import SymmAllReducer
-                reducer = SymmAllReducer(net, use_multicast=(mode != "peer"))
-            except Exception as e:  # noqa: BLE001
-                print(f"rank {rank}: symmetric-memory all-reduce unavailable ({e!r}); using NCCL", file=sys.stderr)
-                mode = "nccl"
-        if mode == "nccl":
-            reducer = GradAllReducer(net, bucket_mb=float(os.environ.get("UB_DP_BUCKET_MB", "32")))
+        from b200.dist import make_reducer
+        reducer = make_reducer(net)
         reducer.broadcast_parameters(0)
 
     def barrier():

@@ -3,6 +3,7 @@ path)` as trainer.py:152-233 writes them -- the same 46 keys, shapes and fp32 dt
 stream.  The flat parameter arena is copied to a pinned host buffer on a side stream (one 124 MB D2H instead of 46
 small ones) and a worker thread serialises it; `wait()` joins the writers (called at the end of training and before a
 file is overwritten)."""
+import os
 import threading
 
 import torch
@@ -36,22 +37,34 @@ class AsyncCheckpointer:
         layout = [(name, st.p_off[name], st.numel[name], tuple(p.shape)) for name, p in st.params().items()]
 
         def work():
-            done.synchronize()
-            sd = {name: host[off:off + n].view(shape).clone() for name, off, n, shape in layout}
-            torch.save(sd, path)
-            self.pinned.append(host)
+            # a failure (disk full, bad path) is kept and re-raised by wait(): the reference's synchronous torch.save
+            # would have raised at this point of the training loop
+            try:
+                done.synchronize()
+                sd = {name: host[off:off + n].view(shape).clone() for name, off, n, shape in layout}
+                tmp = path + ".tmp"
+                torch.save(sd, tmp)
+                os.replace(tmp, path)                     # the file appears atomically, complete
+            except BaseException as e:  # noqa: BLE001
+                t.error = e
+            finally:
+                self.pinned.append(host)
 
         t = threading.Thread(target=work, name=f"ckpt:{path}", daemon=False)
         t.path = path
+        t.error = None
         t.start()
         self.threads.append(t)
 
     def wait(self, path=None):
         """Join the writers (of `path` only, if given)."""
-        keep = []
+        keep, failed = [], None
         for t in self.threads:
             if path is None or t.path == path:
                 t.join()
+                failed = failed or t.error
             else:
                 keep.append(t)
         self.threads = keep
+        if failed is not None:
+            raise RuntimeError(f"asynchronous checkpoint failed: {failed!r}") from failed

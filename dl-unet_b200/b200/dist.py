@@ -106,3 +106,24 @@ class GradAllReducer:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self.works = []
         self.start = 0
+
+
+def make_reducer(unet, group=None, mode=None, bucket_mb=None):
+    """The gradient exchange of a data-parallel run.  mode (default: environment UB_DP_ALLREDUCE, else "symm"):
+      "symm"  our own all-reduce over torch symmetric memory on the compute stream (b200.symm.SymmAllReducer):
+              NVLS multicast (multimem.ld_reduce / multimem.st) where the fabric offers it, peer loads / stores else;
+      "peer"  the same without multicast;
+      "nccl"  bucketed NCCL all-reduce on a side stream (GradAllReducer) -- also the fallback when symmetric memory
+              cannot be set up (no peer access, CPU / gloo groups).
+    The engine's arenas must exist (one forward, or unet.engine.store.adopt(device))."""
+    mode = mode or os.environ.get("UB_DP_ALLREDUCE", "symm")
+    st = (unet.engine if hasattr(unet, "engine") else unet).store
+    if mode != "nccl" and st.g_arena is not None and st.g_arena.is_cuda:
+        try:
+            from .symm import SymmAllReducer
+            return SymmAllReducer(unet, group=group, use_multicast=(mode != "peer"))
+        except Exception as e:  # noqa: BLE001 -- any failure of the symmetric-memory set-up: use NCCL
+            import sys
+            print(f"symmetric-memory all-reduce unavailable ({e!r}); using the NCCL all-reducer", file=sys.stderr)
+    mb = bucket_mb if bucket_mb is not None else float(os.environ.get("UB_DP_BUCKET_MB", "32"))
+    return GradAllReducer(unet, bucket_mb=mb, group=group)

@@ -74,15 +74,27 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
     prog_dir, model_dir = os.path.join(fold_dir, 'progress'), os.path.join(fold_dir, 'models')
     os.makedirs(prog_dir, exist_ok=True)
     os.makedirs(model_dir, exist_ok=True)
+    # Data parallel (not in the reference; SURVEY.md 8 row e-train): under torchrun, one process per GPU, every rank
+    # iterates its own shard of the data; the loss is normalised by the global batch and the gradients are summed over
+    # the ranks after backward (b200.dist.make_reducer), so the update equals the single-GPU update of the joint batch.
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank0 = world == 1 or dist.get_rank() == 0
+    say = print if rank0 else (lambda *a, **k: None)        # files and prints: rank 0 only
+    if world > 1:
+        from b200.dist import make_reducer
+        unet.engine.store.adopt(torch.device(device))      # the flat arenas exist before the first step
+        make_reducer(unet).broadcast_parameters(0)
     # the whole hot-loop body (trainer.py:54-78) as one replayed CUDA graph per batch shape / learning rate
-    train_step = TrainStep(unet, optimizer, kind="bce", graph=True)
+    train_step = TrainStep(unet, optimizer, kind="bce", graph=True, global_batch=batch_size * world if world > 1 else None,
+                           graph_with_allreduce=True)
     loss_best_epoch = 100000.0
     history = {k: [] for k in ('train_eval_iou', 'train_eval_pe', 'val_eval_iou', 'val_eval_pe', 'loss', 'loss_val')}
     epoch = 0
 
     for epoch in range(epochs + 1):
-        print(' ')
-        print('Epoch:', epoch)
+        say(' ')
+        say('Epoch:', epoch)
         start = time()
         total_loss = torch.zeros((), device=device)
         total_loss_val = torch.zeros((), device=device)
@@ -115,6 +127,12 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
                     val_eval = _first_sample_metrics(logits, labels)
         val_eval_epoch = np.mean(val_eval, axis=1)
 
+        if world > 1:
+            # every rank must take the same scheduler / checkpoint decisions: epoch losses over all ranks' shards (the
+            # training losses already are shares of the global-batch mean, the validation losses are local means)
+            dist.all_reduce(total_loss)
+            dist.all_reduce(total_loss_val)
+            total_loss_val /= world
         # ---- epoch bookkeeping (trainer.py:132-233)
         scheduler.step(total_loss_val / (len(val_loader) * batch_size))
         l_rate = optimizer.param_groups[-1]['lr']
@@ -123,56 +141,56 @@ def training(unet, train_loader, val_loader, epochs, batch_size, device, fold_di
 
         if loss_epoch_val < (loss_best_epoch * (1.0 - scheduler.threshold)):
             loss_best_epoch = loss_epoch_val
-            print('New best epoch!')
+            say('New best epoch!')
             my_patience = 0
-            _save(unet, os.path.join(model_dir, 'unet_weight_save_best.pth'))
+            rank0 and _save(unet, os.path.join(model_dir, 'unet_weight_save_best.pth'))
         else:
             my_patience += 1
 
         best = loss_best_epoch.item() if torch.is_tensor(loss_best_epoch) else loss_best_epoch
-        print('Current lr is:             ', l_rate)
-        print('Patience is:                {}/{}'.format(my_patience, scheduler.patience))
-        print('Mean IoU training:         ', "{:.6f}".format(train_eval_epoch[0]))
-        print('Mean PE training:          ', "{:.6f}".format(train_eval_epoch[1]))
-        print('Mean IoU validation:       ', "{:.6f}".format(val_eval_epoch[0]))
-        print('Mean PE validation:        ', "{:.6f}".format(val_eval_epoch[1]))
-        print('Total training loss:       ', "{:.6f}".format(loss_epoch.item()))
-        print('Total validation loss:     ', "{:.6f}".format(loss_epoch_val.item()))
-        print('Best epoch validation loss:', "{:.6f}".format(best))
-        print('Epoch duration:            ', "{:.6f}".format(time() - start), 's')
-        print('                                                                         ')
+        say('Current lr is:             ', l_rate)
+        say('Patience is:                {}/{}'.format(my_patience, scheduler.patience))
+        say('Mean IoU training:         ', "{:.6f}".format(train_eval_epoch[0]))
+        say('Mean PE training:          ', "{:.6f}".format(train_eval_epoch[1]))
+        say('Mean IoU validation:       ', "{:.6f}".format(val_eval_epoch[0]))
+        say('Mean PE validation:        ', "{:.6f}".format(val_eval_epoch[1]))
+        say('Total training loss:       ', "{:.6f}".format(loss_epoch.item()))
+        say('Total validation loss:     ', "{:.6f}".format(loss_epoch_val.item()))
+        say('Best epoch validation loss:', "{:.6f}".format(best))
+        say('Epoch duration:            ', "{:.6f}".format(time() - start), 's')
+        say('                                                                         ')
 
         for key, val in (('train_eval_iou', train_eval_epoch[0]), ('train_eval_pe', train_eval_epoch[1]),
                          ('val_eval_iou', val_eval_epoch[0]), ('val_eval_pe', val_eval_epoch[1]),
                          ('loss', loss_epoch.item()), ('loss_val', loss_epoch_val.item())):
             history[key].append(val)
-            np.savetxt(os.path.join(prog_dir, key + '.out'), np.asarray(history[key]))
+            rank0 and np.savetxt(os.path.join(prog_dir, key + '.out'), np.asarray(history[key]))
 
         if goal is not None:
             # trainer.py:185-214: all three branches test the IoU slot, save once, and `continue`
             # (so the periodic checkpoint and the low-lr stop below are skipped until the goal is met)
             if val_eval_epoch[0] > goal:
                 path = os.path.join(model_dir, 'unet_weight_save_{}.pth'.format(DATASET))
-                _CKPT.save(unet, path)
-                print('The goal was reached in epoch {}!'.format(epoch))
-                print('Model has been saved:')
-                print(path)
+                rank0 and _CKPT.save(unet, path)
+                say('The goal was reached in epoch {}!'.format(epoch))
+                say('Model has been saved:')
+                say(path)
                 goal = None
             continue
 
         if epoch % 25 == 0:  # trainer.py:216-221 ("every 50 epochs" in its comment)
-            _save(unet, os.path.join(model_dir, 'unet_weight_save_latest.pth'))
+            rank0 and _save(unet, os.path.join(model_dir, 'unet_weight_save_latest.pth'))
 
         if l_rate < 10 * scheduler.eps and my_patience == scheduler.patience:
-            print(f'LR dropped below {10 * scheduler.eps}!')
-            print('Stopping training')
-            print(' ')
-            _save(unet, os.path.join(model_dir, 'unet_weight_save_latest.pth'))
+            say(f'LR dropped below {10 * scheduler.eps}!')
+            say('Stopping training')
+            say(' ')
+            rank0 and _save(unet, os.path.join(model_dir, 'unet_weight_save_latest.pth'))
             break
 
         if my_patience == scheduler.patience:
             my_patience = -1
 
     _CKPT.wait()                      # every checkpoint file is complete when training() returns
-    print('Training is finished as epoch {} has been reached'.format(epoch))
-    print('                                                               ')
+    say('Training is finished as epoch {} has been reached'.format(epoch))
+    say('                                                               ')
