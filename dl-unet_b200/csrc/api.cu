@@ -1006,7 +1006,7 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
   P.blk_bytes = P.KW * P.KH * 128;
   P.stage_bytes = (2 + BN / 64) * P.blk_bytes;
   P.nstage = WgradCfg::SMEM_LIMIT / P.stage_bytes;
-  if (P.nstage > WgradCfg::MAX_STAGES) P.nstage = WgradCfg::MAX_STAGES;
+  if (P.nstage > 8) P.nstage = 8;
   if (P.nstage < 2) return UB_E_SHAPE;
   P.chunks_x = (W + P.KW - 1) / P.KW;
   P.chunks_y = (H + P.KH - 1) / P.KH;
@@ -1184,7 +1184,7 @@ static void conv1_wgrad_plan(int n, int h, int w_, WgradParams& P) {
   P.KH = 1;
   P.ksteps = 4;
   P.blk_bytes = 64 * 128;
-  P.stage_bytes = 2 * P.blk_bytes + 4096;   // dY block (+ the unused second M block) + four 8-row groups of the tap tile
+  P.stage_bytes = P.blk_bytes + 4096;       // one dY block (the second M block aliases it) + four 8-row groups of taps
   P.nstage = WgradCfg::SMEM_LIMIT / P.stage_bytes;
   if (P.nstage > WgradCfg::MAX_STAGES) P.nstage = WgradCfg::MAX_STAGES;
   P.chunks_x = (w_ - 2 + 63) / 64;

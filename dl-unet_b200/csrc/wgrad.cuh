@@ -44,7 +44,7 @@ struct alignas(64) WgradParams {
 };
 
 struct WgradCfg {
-  static constexpr int MAX_STAGES = 8;
+  static constexpr int MAX_STAGES = 20;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_LIMIT = 232448 - 1024 - BAR_BYTES;
 };
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     for (int i = threadIdx.x; i < NSTAGE * 32 * 32; i += blockDim.x) {
       const int st = i / (32 * 32), r = (i / 32) % 32, c = i % 32;
       if (r >= 24 || (r & 7) >= 3)
-        *reinterpret_cast<uint32_t*>(smem + st * STAGE_BYTES + 2 * BLK + r * 128 + c * 4) = r == 24 ? 0x3F803F80u : 0u;
+        *reinterpret_cast<uint32_t*>(smem + st * STAGE_BYTES + BLK + r * 128 + c * 4) = r == 24 ? 0x3F803F80u : 0u;
     }
     fence_proxy_async_smem();
   }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         mbar_wait(&empty[stage], phase ^ 1, 5);
         if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + 2 * BLK;
+          uint8_t* sb = sa + (CONV1 ? BLK : 2 * BLK);
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, am_a, &full[stage], ch_a, x0, y0, img);
           if (CONV1) {
@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const uint32_t hiD = umma_desc_hi(1024);
     // MN-major: LBO = distance between the 64-element M / N blocks, SBO = 1024 B between 8-row K groups;
     // CONV1: B is K-major (rows = taps, 128 B = 64 pixels of K per row): SBO = 1024 B between 8-row groups, 32 B per K step
-    const uint32_t loA0 = umma_desc_lo(smem_u32(smem), (uint32_t)BLK);
-    const uint32_t loB0 = umma_desc_lo(smem_u32(smem) + 2 * BLK, CONV1 ? 16u : (uint32_t)BLK);
+    // CONV1: only 64 rows of M exist; LBO = 0 makes the second 64-row block an alias of the first (its accumulator rows
+    // are never read), so a stage is 8 KB of dY + 4 KB of taps and 18 stages (144 KB of dY per SM) are in flight
+    const uint32_t loA0 = umma_desc_lo(smem_u32(smem), CONV1 ? 0u : (uint32_t)BLK);
+    const uint32_t loB0 = umma_desc_lo(smem_u32(smem) + (CONV1 ? BLK : 2 * BLK), CONV1 ? 16u : (uint32_t)BLK);
     constexpr uint32_t kstepB = CONV1 ? 2u : 128u;
     const uint32_t stage16 = (uint32_t)STAGE_BYTES >> 4;
     const int ksteps = p.ksteps;
