@@ -22,6 +22,7 @@
 #include "augment.cuh"
 #include "igemm.cuh"
 #include "igemm2.cuh"
+#include "igemm_pair.cuh"
 #ifdef UB_DIAGNOSTICS
 #include "probe.cuh"
 #endif
@@ -40,6 +41,7 @@ int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_mask_l2_prefetch = 1;
 int g_igemm_dbg = 0;
+int g_pair_mode = 1;        // N = 256 tiles of the tap-per-load conv kernel on CTA pairs (cta_group::2); 0: one CTA per tile
 int g_conv1_dbg = 0;
 int g_conv1_wgrad_tc = 1;   // conv11c weight gradient on the tensor pipe (0: CUDA-core kernel)
 int g_wgrad_mode = 3;  // 0: tap-per-CTA wgrad_kernel, 1: wgrad3 with per-s MMAs, 2: wgrad3 with fused s taps, 3: auto
@@ -238,9 +240,29 @@ int launch_igemm_t(const IgemmParams& P, cudaStream_t st) {
   igemm_kernel<BN><<<grid, 384, C::SMEM_BYTES, st>>>(P);
   return (int)cudaGetLastError();
 }
+bool pair_mode(int BN) { return BN == 256 && g_pair_mode != 0; }
+int b_box_rows(int BN) { return pair_mode(BN) ? 128 : BN; }   // a CTA of a pair loads half of the N = 256 weight rows
+
+int launch_igemm_pair(const IgemmParams& P, cudaStream_t st) {
+  using C = IgemmPairCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long m_tiles = (long long)P.n_img * P.tiles_y * P.tiles_x;
+  const long long units = ((m_tiles + 1) / 2) * P.n_tiles_n;
+  long long pairs = num_sms() / 2;
+  if (units < pairs) pairs = units;
+  igemm_pair_kernel<<<(int)(2 * pairs), 384, C::SMEM_BYTES, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
 int launch_igemm(const IgemmParams& P0, int BN, cudaStream_t st) {
   IgemmParams P = P0;
   P.dbg = g_igemm_dbg;
+  if (pair_mode(BN)) return launch_igemm_pair(P, st);
   switch (BN) {
     case 64: return launch_igemm_t<64>(P, st);
     case 128: return launch_igemm_t<128>(P, st);
@@ -465,8 +487,9 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
 struct SplitPlan {
   int splits, per;
 };
-SplitPlan plan_splits(long long items, long long chunks, int min_chunks, double overhead) {
-  const int sms = num_sms_physical();   // the slab count of a shape must not change with ub_set_sm_limit
+SplitPlan plan_splits(long long items, long long chunks, int min_chunks, double overhead, int workers = 0) {
+  // workers: CTAs (or CTA pairs) that run side by side; the slab count of a shape must not change with ub_set_sm_limit
+  const int sms = workers > 0 ? workers : num_sms_physical();
   long long max_splits = chunks / min_chunks;
   if (max_splits < 1) max_splits = 1;
   if (max_splits > 1024) max_splits = 1024;
@@ -763,6 +786,7 @@ void ub_set_option(int key, int value) {
   if (key == 7) g_map_cache_on = value;
   if (key == 8) g_conv1_wgrad_tc = value;
   if (key == 9) g_conv1_dbg = value;
+  if (key == 11) g_pair_mode = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }
@@ -869,7 +893,7 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
   }
   if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
-  if ((e = make_map2(&P.b_map, w_fwd, 9ll * x->c, y->c, BN))) return e;
+  if ((e = make_map2(&P.b_map, w_fwd, 9ll * x->c, y->c, b_box_rows(BN)))) return e;
   if ((e = make_map4(&P.o_map[0], y, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = bias;
@@ -958,7 +982,7 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   }
   if ((e = make_map4(&P.a_map[0], dy, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
-  if ((e = make_map2(&P.b_map, w_dgrad, 9ll * dy->c, dx->c, BN))) return e;
+  if ((e = make_map2(&P.b_map, w_dgrad, 9ll * dy->c, dx->c, b_box_rows(BN)))) return e;
   if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = nullptr;
@@ -1001,10 +1025,14 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
                  : (x->c % 256 == 0)                        ? 256
                  : (x->c % 128 == 0)                        ? 128
                                                             : 64;
-  pick_kpatch(W, H, 2 + BN / 64, P.KW, P.KH);
+  const int m_rows = upconv ? 4 * dy->c : dy->c;
+  // CTA pairs (cta_group::2): M = 256 rows per pair, each CTA loads half of the X chunk
+  const bool pair = pair_mode(BN) && (m_rows % 256 == 0) && g_force_bn == 0;
+  const int blocks = pair ? 4 : 2 + BN / 64;
+  pick_kpatch(W, H, blocks, P.KW, P.KH);
   P.ksteps = P.KW * P.KH / 16;
   P.blk_bytes = P.KW * P.KH * 128;
-  P.stage_bytes = (2 + BN / 64) * P.blk_bytes;
+  P.stage_bytes = blocks * P.blk_bytes;
   P.nstage = WgradCfg::SMEM_LIMIT / P.stage_bytes;
   if (P.nstage > 8) P.nstage = 8;
   if (P.nstage < 2) return UB_E_SHAPE;
@@ -1014,22 +1042,22 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
   P.upconv = upconv;
   P.Cout = dy->c;
   P.Cin = x->c;
-  P.m_rows = upconv ? 4 * dy->c : dy->c;
+  P.m_rows = m_rows;
   P.n_taps = upconv ? 1 : 9;
   for (int t = 0; t < 9; ++t) {
     P.tap_dx[t] = upconv ? 0 : t % 3;
     P.tap_dy[t] = upconv ? 0 : t / 3;
   }
-  P.m_tiles = (P.m_rows + 127) / 128;
+  P.m_tiles = pair ? P.m_rows / 256 : (P.m_rows + 127) / 128;   // pair: tiles of 256 rows, one 128-row half per CTA
   P.n_tiles = x->c / BN;
   P.items = P.n_taps * P.m_tiles * P.n_tiles;
-  const SplitPlan sp = plan_splits(P.items, P.total_chunks, 4, 2.0);
+  const SplitPlan sp = plan_splits(P.items, P.total_chunks, 4, 2.0, pair ? num_sms_physical() / 2 : 0);
   P.splits = sp.splits;
   P.per = sp.per;
   P.slab_stride = (long long)P.m_rows * P.n_taps * P.Cin;
   {
     const long long units = (long long)P.items * P.splits;
-    const int plan[8] = {P.KW, P.KH, P.nstage, P.items, P.splits, P.per, BN, (int)(units < num_sms() ? units : num_sms())};
+    const int plan[8] = {P.KW, P.KH, P.nstage, P.items, P.splits, P.per, pair ? -BN : BN, (int)(units < num_sms() ? units : num_sms())};
     memcpy(g_last_plan, plan, sizeof(plan));
   }
   if (slabs_out) {
@@ -1051,6 +1079,18 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
   }
   if ((e = make_map4(&P.b_map, x, P.KW, P.KH))) return e;
   const int smem_bytes = P.nstage * P.stage_bytes + WgradCfg::BAR_BYTES + 1024;
+  if (pair) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t ce = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (ce != cudaSuccess) return (int)ce;
+      attr_set = true;
+    }
+    long long pairs = (long long)P.items * P.splits;
+    if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+    wgrad_pair_kernel<<<(int)(2 * pairs), 256, smem_bytes, st>>>(P);
+    return (int)cudaGetLastError();
+  }
   return launch_wgrad(P, BN, smem_bytes, st);
 }
 
@@ -1058,12 +1098,14 @@ static int launch_wgrad_generic(const ub_tensor4* x, const ub_tensor4* dy, int u
 //   Cout == 64                            : M = 128 filled with a one-pixel-shifted dY copy (wgrad4)
 //   Cin == 64                             : haloed patch, all nine taps, 32-channel tile (wgrad3)
 //   Cin 128 / 256 on maps >= 128 wide     : one tap row per CTA, three s taps per instruction, N = 192 (wgrad5)
-//   everything deeper / smaller           : one tap per unit, N = 256, persistent (wgrad_kernel)
+//   everything deeper / smaller           : one tap per unit, N = 256, persistent (wgrad_kernel); on CTA pairs
+//                                           (cta_group::2, M = 256) when Cout % 256 == 0 -- also 256 -> 256 wide maps
 static int conv3x3_wgrad_impl(const ub_tensor4* x, const ub_tensor4* dy, float* slabs, cudaStream_t st, int* slabs_out) {
   int mode = g_wgrad_mode;
   if (mode == 3) {
     if (dy->c == 64) mode = 5;
     else if (x->c < 128) mode = 2;
+    else if (x->c == 256 && dy->c % 256 == 0 && pair_mode(256)) mode = 0;   // CTA pairs beat the tap-row kernel (conv32c)
     else if (x->c <= 256 && dy->w >= 128) mode = 4;
     else if (x->c <= 128) mode = 2;
     else mode = 0;
@@ -1113,7 +1155,7 @@ int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, 
   P.kchunks = x->c / 64;
   if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
-  if ((e = make_map2(&P.b_map, w_fwd, x->c, 4ll * y->c, BN))) return e;
+  if ((e = make_map2(&P.b_map, w_fwd, x->c, 4ll * y->c, b_box_rows(BN)))) return e;
   for (int ab = 0; ab < 4; ++ab) {
     const int a = ab >> 1, b = ab & 1;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(y->ptr) + a * y->sy + b * y->sx;
@@ -1147,7 +1189,7 @@ int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tenso
     P.tap_dx[ab] = 0;
     P.tap_dy[ab] = 0;
   }
-  if ((e = make_map2(&P.b_map, w_dgrad, 4ll * dy->c, dx->c, BN))) return e;
+  if ((e = make_map2(&P.b_map, w_dgrad, 4ll * dy->c, dx->c, b_box_rows(BN)))) return e;
   if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = nullptr;

@@ -73,9 +73,18 @@ __device__ __forceinline__ WgradUnit wgrad_unit(const WgradParams& p, int u) {
 // the taps (r, s), r = 0..2; every box lands on a 1024-byte boundary of shared memory; row 0 of group 3 holds ones,
 // written once per stage at kernel start.  Column of tap (r, s) = 8 s + r, bias = column 24.  A chunk is 64 pixels of one output row.
 // Every unit stores one row of partial sums [640] = dW[64][9], db[64] into p.dw (summed in order by the unpack kernel).
-template <int BN, bool CONV1 = false>
-__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+//
+// PAIR (BN = 256): the same kernel on CTA pairs (tcgen05 cta_group::2, see igemm_pair.cuh for the protocol): one MMA of
+// M = 256 gradient rows x N = 256 columns per K step; each CTA loads its own 128 rows of dY and HALF of the X chunk
+// (128 of the 256 input channels): 32 KB instead of 48 KB per CTA and chunk.  Needs m_rows % 256 == 0.
+template <int BN, bool CONV1 = false, bool PAIR = false>
+__device__ __forceinline__ void wgrad_kernel_impl(const WgradParams& p) {
   using C = WgradCfg;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // CTA (pair) index and count for the unit loop
+  const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int NB_B = PAIR ? BN / 128 : BN / 64;                        // 64-channel X blocks this CTA loads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NSTAGE = p.nstage, STAGE_BYTES = p.stage_bytes, BLK = p.blk_bytes;
@@ -102,13 +111,18 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], PAIR ? 256 : 128);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if (CONV1 && !(p.dbg & 8)) {
     // the rows of every stage's B tile that no TMA box writes: rows 3..7 of the tap groups and rows 1..7 of group 3 =
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -130,8 +144,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     // ------------------------------------------------------- TMA producer (whole warp loops, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const WgradUnit w = wgrad_unit(p, u);
+    for (int u = cta; u < total_units; u += n_ctas) {
+      WgradUnit w = wgrad_unit(p, u);
+      if (PAIR) w.mt = 2 * w.mt + (int)rank;
       // the two 64-row blocks of this M tile: tensor map + channel coordinate
       const int row_a = w.mt * 128, row_b = row_a + 64;
       const int nblk = row_b < p.m_rows ? 2 : 1;
@@ -145,7 +160,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const CUtensorMap* am_a = &p.a_map[map_a];
       const CUtensorMap* am_b = &p.a_map[map_b];
       const int dx = p.tap_dx[w.tap], dy = p.tap_dy[w.tap];
-      const uint32_t tx_bytes = CONV1 ? (uint32_t)BLK + ((p.dbg & 1) ? 0u : 3u * 384u) : (uint32_t)(nblk + BN / 64) * (uint32_t)BLK;
+      const uint32_t tx_bytes = CONV1  ? (uint32_t)BLK + ((p.dbg & 1) ? 0u : 3u * 384u)
+                                : PAIR ? 2u * (uint32_t)(2 + NB_B) * (uint32_t)BLK      // both CTAs' loads, counted on the leader
+                                       : (uint32_t)(nblk + BN / 64) * (uint32_t)BLK;
       const int c_begin = w.split * p.per;
       const int c_end = min(p.total_chunks, c_begin + p.per);
       int cx = c_begin % p.chunks_x;
@@ -158,6 +175,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + (CONV1 ? BLK : 2 * BLK);
+          if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            tma_load_4d_2sm(sa, am_a, &full[stage], ch_a, x0, y0, img);
+            tma_load_4d_2sm(sa + BLK, am_b, &full[stage], ch_b, x0, y0, img);
+#pragma unroll
+            for (int b = 0; b < NB_B; ++b)
+              tma_load_4d_2sm(sb + b * BLK, &p.b_map, &full[stage], w.nt * BN + (int)rank * 128 + b * 64, x0 + dx, y0 + dy, img);
+          } else {
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sa, am_a, &full[stage], ch_a, x0, y0, img);
           if (CONV1) {
@@ -170,6 +195,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
 #pragma unroll
             for (int b = 0; b < BN / 64; ++b)
               tma_load_4d(sb + b * BLK, &p.b_map, &full[stage], w.nt * BN + b * 64, x0 + dx, y0 + dy, img);
+          }
           }
         }
         __syncwarp();
@@ -186,9 +212,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
     }
-  } else if (warp == 1) {
-    // --------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, CONV1 ? 0 : 1);
+  } else if (warp == 1 && leader) {
+    // --------------------------------------------------------- MMA issuer (of the pair's leader)
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN, 1, CONV1 ? 0 : 1);
     const uint32_t hiD = umma_desc_hi(1024);
     // MN-major: LBO = distance between the 64-element M / N blocks, SBO = 1024 B between 8-row K groups;
     // CONV1: B is K-major (rows = taps, 128 B = 64 pixels of K per row): SBO = 1024 B between 8-row groups, 32 B per K step
@@ -202,7 +228,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+    for (int u = cta; u < total_units; u += n_ctas, ++it) {
       const int split = u / p.items;
       const int c_begin = split * p.per;
       const int n_iters = min(p.total_chunks, c_begin + p.per) - c_begin;
@@ -217,11 +243,21 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           const uint32_t so = stage * stage16;
           // 16 pixels (K) per MMA = two 8-row groups = 2048 B (>>4 = 128)
 #pragma unroll 4
-          for (int k = 0; k < ((CONV1 && (p.dbg & 2)) ? 0 : ksteps); ++k)
-            umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + kstepB * k), idesc,
-                      (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
-          if (i == n_iters - 1) umma_commit(&tfull[acc]);
+          for (int k = 0; k < ((CONV1 && (p.dbg & 2)) ? 0 : ksteps); ++k) {
+            if (PAIR)
+              umma_bf16_2sm(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + kstepB * k), idesc,
+                            (i > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, umma_desc(hiD, loA0 + so + 128 * k), umma_desc(hiD, loB0 + so + kstepB * k), idesc,
+                        (i > 0 || k > 0) ? 1u : 0u);
+          }
+          if (PAIR) {
+            umma_commit_2sm(&empty[stage]);
+            if (i == n_iters - 1) umma_commit_2sm(&tfull[acc]);
+          } else {
+            umma_commit(&empty[stage]);
+            if (i == n_iters - 1) umma_commit(&tfull[acc]);
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) {
@@ -235,8 +271,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const int q = warp - 4;
     const int m = q * 32 + lane;  // accumulator row
     int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
-      const WgradUnit w = wgrad_unit(p, u);
+    for (int u = cta; u < total_units; u += n_ctas, ++it) {
+      WgradUnit w = wgrad_unit(p, u);
+      if (PAIR) w.mt = 2 * w.mt + (int)rank;
       const int acc = it & 1;
       const int row0 = (w.mt * 2 + (m >> 6)) * 64;  // first row of this thread's 64-row block
       const bool valid = row0 < p.m_rows;
@@ -271,16 +308,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+template <int BN, bool CONV1 = false>
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  wgrad_kernel_impl<BN, CONV1, false>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
+  wgrad_kernel_impl<256, false, true>(p);
 }
 
 }  // namespace ub

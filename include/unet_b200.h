@@ -58,7 +58,9 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  *        2 = wherever legal).
  * key 5: igemm ablation (1 = do not wait for earlier TMA stores): timing experiments only.
  * key 7: host-side cache of encoded TMA tensor maps (1 = on [default], 0 = encode on every call).
- * key 8: conv11c weight gradient on the tensor pipe (1 = on [default], 0 = CUDA-core kernel). */
+ * key 8: conv11c weight gradient on the tensor pipe (1 = on [default], 0 = CUDA-core kernel).
+ * key 11: N = 256 tiles of the tap-per-load conv / up-conv kernel on CTA pairs, tcgen05 cta_group::2 (1 = on [default],
+ *         0 = one CTA per 128 x 256 tile). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------

@@ -508,3 +508,41 @@ def test_unpack_range_sums_slabs_in_fixed_order(ops, n_slabs):
     assert all(torch.equal(e[4], f) for e, f in zip(entries, first))                    # deterministic
     table.unpack_all(accumulate=True)
     assert all(torch.equal(e[4], f + f) for e, f in zip(entries, first))
+
+
+@pytest.mark.parametrize("shape", [(1, 12, 12, 256, 256), (2, 20, 21, 128, 256), (3, 13, 17, 256, 512), (1, 30, 30, 512, 1024),
+                                   (5, 9, 40, 64, 256)])
+def test_igemm_pair_kernel(ops, shape):
+    """igemm_pair.cuh: the tap-per-load conv kernel on CTA pairs (tcgen05 cta_group::2, M = 256 pixels x N = 256 per
+    instruction, each CTA loads half of the weight slab).  N tiles of 256 are forced so that small shapes reach it; odd
+    tile counts leave one CTA of the last pair without work (zero-filled loads, clipped stores).  Same K order as the
+    one-CTA kernel, so the two must agree bit for bit."""
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device=DEV)
+    xq, wq = bf(x).float().requires_grad_(True), bf(wt).float()
+    dy = torch.randn(n, cout, h - 2, w - 2, device=DEV)
+    ref = F.relu(F.conv2d(xq, wq, b))
+    (gx,) = torch.autograd.grad(F.conv2d(xq, wq), xq, bf(dy).float())
+    outs = {}
+    ops.set_tuning(bn=256)
+    try:
+        for pair in (1, 0):
+            ops.set_option(11, pair)
+            y = torch.full((n, h - 2, w - 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            ops.conv3x3_fwd(nhwc(x), ops.pack_weight(wt, ops.PACK_CONV_FWD), b, y, relu=True)
+            dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+            if cin % 256 == 0:      # the dgrad's N is Cin
+                ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))
+            outs[pair] = (y, dx)
+    finally:
+        ops.set_option(11, 1)
+        ops.set_tuning()
+    y, dx = outs[1]
+    assert rel_l2(nchw(y), ref) < BF16_OUT_TOL
+    assert torch.equal(y, outs[0][0])
+    if cin % 256 == 0:
+        assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+        assert torch.equal(dx, outs[0][1])
