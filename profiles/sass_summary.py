@@ -1,5 +1,6 @@
 """SASS evidence per kernel of dl-unet_b200/csrc/libunet_b200.so: counts of the Blackwell-native instructions
-(UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA load / store, LDTM = tcgen05.ld) and of floating-point global atomics
+(UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA load / store, LDTM = tcgen05.ld; ".2CTA" = cta_group::2 forms of the MMA,
+the TMA loads and the multicast commit; LDGMC = multimem.ld_reduce through the NVSwitch multicast address) and of floating-point global atomics
 (RED / ATOM .ADD on fp32: none may remain in the training path -- deterministic gradients; ATOMG.EXCH / integer atomics are
 the dead-lock guard of mbar_wait and the loss kernel's block counter).   python profiles/sass_summary.py > profiles/r2_sass_summary.txt"""
 import collections
@@ -23,11 +24,11 @@ for line in sass.split("\n"):
     if fn is None:
         continue
     for key, pat in (("UTCHMMA", r"\bUTCHMMA"), ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("LDTM", r"\bLDTM"),
-                     ("HMMA", r"\bHMMA\."), ("fp32_atomic_add", r"\b(RED|ATOMG|ATOM)\.E\.ADD\.F32|\bRED\.E\.ADD\.F32|ATOMG\.E\.ADD\.F32|\bRED\.E\.ADD\.F32x"),
+                     ("HMMA", r"\bHMMA\."), ("2CTA", r"\.2CTA"), ("LDGMC", r"\bLDGMC"), ("fp32_atomic_add", r"\b(RED|ATOMG|ATOM)\.E\.ADD\.F32|\bRED\.E\.ADD\.F32|ATOMG\.E\.ADD\.F32|\bRED\.E\.ADD\.F32x"),
                      ("other_atomics", r"\b(ATOMG|ATOM|RED)\.")):
         if re.search(pat, line):
             counts[fn][key] += 1
-print(f"{'kernel':58s} {'UTCHMMA':>8s} {'UTMALDG':>8s} {'UTMASTG':>8s} {'LDTM':>6s} {'HMMA':>5s} {'f32 atomic add':>15s} {'other atomics':>14s}")
+print(f"{'kernel':58s} {'UTCHMMA':>8s} {'UTMALDG':>8s} {'UTMASTG':>8s} {'LDTM':>6s} {'.2CTA':>6s} {'LDGMC':>6s} {'HMMA':>5s} {'f32 atomic add':>15s} {'other atomics':>14s}")
 for fn, c in counts.items():
-    print(f"{fn[:58]:58s} {c['UTCHMMA']:8d} {c['UTMALDG']:8d} {c['UTMASTG']:8d} {c['LDTM']:6d} {c['HMMA']:5d} {c['fp32_atomic_add']:15d} "
+    print(f"{fn[:58]:58s} {c['UTCHMMA']:8d} {c['UTMALDG']:8d} {c['UTMASTG']:8d} {c['LDTM']:6d} {c['2CTA']:6d} {c['LDGMC']:6d} {c['HMMA']:5d} {c['fp32_atomic_add']:15d} "
           f"{c['other_atomics'] - c['fp32_atomic_add']:14d}")
