@@ -23,6 +23,10 @@ from .geometry import LAYERS, LAYER_BY_NAME, LEVEL_C, Geometry, weight_shape
 # UB_FUSED_POOL_LEVELS=0 restores the separate pool kernel everywhere (experiments)
 FUSED_POOL_LEVELS = int(__import__("os").environ.get("UB_FUSED_POOL_LEVELS", "2"))
 
+# UB_STREAMK_INFERENCE=1: stream-K in inference too (+1-2 % throughput; predictions then depend on the batch size in the
+# last bf16 bit of a few activations)
+STREAMK_INFERENCE = int(__import__("os").environ.get("UB_STREAMK_INFERENCE", "0"))
+
 PARAM_NAMES = [f"{n}.{p}" for (n, _, _, _) in LAYERS for p in ("weight", "bias")]
 # order in which backward finishes each layer's gradients
 BACKWARD_LAYER_ORDER = [n for (n, _, _, _) in reversed(LAYERS)]
@@ -200,15 +204,15 @@ class Workspace:
         plan["conv12e.bias"] = head + (130, 64, "head")
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
-            if l > 1:
-                plan[f"conv{l}2e.bias"] = ("colsum", (ops.PROD_COLSUM, B, g.dec2[l], g.dec2[l], C), C, 0, C, None)
+            if l > 1:   # the up-convolution below this level consumes d{l}2: its dgrad sums the columns of its dx
+                plan[f"conv{l}2e.bias"] = ("updgrad", (ops.PROD_UPDGRAD, B, g.dec2[l], g.dec2[l], C), C, 0, C, None)
             # conv{l}2e's dgrad sums its dx = the output gradient of conv{l}1e; conv{l}1e's dgrad that of upconv{l}
             plan[f"conv{l}1e.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.dec1[l], g.dec1[l], C, C, 0), C, 0, C, None)
             plan[f"upconv{l}.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.up[l], g.up[l], 2 * C, C, C), C, 0, C, None)
             plan[f"conv{l}2c.bias"] = ("pool", (ops.PROD_POOL, B, g.enc2[l], g.enc2[l], C), C, 0, C, None)
             if l > 1:
                 plan[f"conv{l}1c.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.enc1[l], g.enc1[l], C, C, 0), C, 0, C, None)
-        plan["conv52c.bias"] = ("colsum", (ops.PROD_COLSUM, B, g.enc2[5], g.enc2[5], 1024), 1024, 0, 1024, None)
+        plan["conv52c.bias"] = ("updgrad", (ops.PROD_UPDGRAD, B, g.enc2[5], g.enc2[5], 1024), 1024, 0, 1024, None)
         plan["conv51c.bias"] = ("dgrad", (ops.PROD_DGRAD, B, g.enc1[5], g.enc1[5], 1024, 1024, 0), 1024, 0, 1024, None)
         plan["conv11c.weight"] = ("conv1", (ops.PROD_CONV1, B, self.S, self.S), ops.CONV1_STRIDE, 0, 640, None)
         return plan
@@ -278,7 +282,22 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, image, train, argmax_out=None, want_logits=True):
-        """image: fp32 [B,1,S,S] CUDA.  Returns (logits fp32 [B,2,So,So] or None, workspace)."""
+        """image: fp32 [B,1,S,S] CUDA.  Returns (logits fp32 [B,2,So,So] or None, workspace).
+
+        Inference (train=False) runs with stream-K off: whole work units keep one K order whatever the batch size, so
+        the prediction for a tile does not depend on what else is in its batch (tests/test_gpu_dropin.py: the tile
+        route equals per-tile predict() bit for bit); training takes the 1-2 % stream-K gives -- its split points
+        depend on the batch shape only, so it stays bit-reproducible from run to run."""
+        prev = ops.get_option(ops.OPT_STREAM_K, 1)
+        if not train and not STREAMK_INFERENCE and prev != 0:
+            ops.set_option(ops.OPT_STREAM_K, 0)
+            try:
+                return self._forward(image, train, argmax_out, want_logits)
+            finally:
+                ops.set_option(ops.OPT_STREAM_K, prev)
+        return self._forward(image, train, argmax_out, want_logits)
+
+    def _forward(self, image, train, argmax_out, want_logits):
         if image.dim() != 4 or image.shape[1] != 1 or image.shape[2] != image.shape[3]:
             raise RuntimeError(f"expected a [B,1,S,S] image batch, got {tuple(image.shape)}")
         if not image.is_cuda:
@@ -387,7 +406,8 @@ class Engine:
         for l in (1, 2, 3, 4):
             C = LEVEL_C[l]
             # each dgrad also produces the bias gradient of the layer whose output gradient it computes
-            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=(l == 1),
+            # conv{l}2e's own bias gradient came with the kernel that produced dy: head_bwd (l = 1), upconv{l-1}'s dgrad
+            self._conv_bwd(f"conv{l}2e", a[f"d{l}1"], dy, gr[f"d{l}1"], a[f"d{l}1"], bias_done=True,
                            dx_bias=f"conv{l}1e.bias")
             self._conv_bwd(f"conv{l}1e", a[f"cat{l}"], gr[f"d{l}1"], gr[f"cat{l}"], None, bias_done=True,
                            dx_bias=f"upconv{l}.bias", dx_bias_c0=C)
@@ -398,10 +418,12 @@ class Engine:
             dyu = gr[f"cat{l}"][..., C:]
             ops.upconv2x2_wgrad(src, dyu, self._slabs["view"](up_name))
             self._finish(up_name)                    # its bias gradient came with conv{l}1e's dgrad
-            ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src)
+            # ... and its dgrad also leaves the bias gradient of the conv that produced its input (conv{l+1}2e / conv52c)
+            ops.upconv2x2_dgrad(dyu, pk[up_name][1], dsrc, src,
+                                dbias_part=part[f"conv{l + 1}2e.bias" if l < 4 else "conv52c.bias"])
             dy = dsrc
         # bottleneck
-        self._conv_bwd("conv52c", a["e51"], gr["e52"], gr["e51"], a["e51"], dx_bias="conv51c.bias")
+        self._conv_bwd("conv52c", a["e51"], gr["e52"], gr["e51"], a["e51"], bias_done=True, dx_bias="conv51c.bias")
         self._conv_bwd("conv51c", a["p4"], gr["e51"], gr["p4"], None, bias_done=True)
         for l in (4, 3, 2, 1):
             C = LEVEL_C[l]

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ub_conv3x3_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_upconv2x2_fwd": (_i, [_T4, _P, _P, _T4, _P]),
     "ub_upconv2x2_dgrad": (_i, [_T4, _P, _T4, _T4, _P]),
+    "ub_upconv2x2_dgrad_bias": (_i, [_T4, _P, _T4, _T4, _P, _P]),
     "ub_upconv2x2_wgrad": (_i, [_T4, _T4, _P, _P]),
     "ub_conv1_fwd": (_i, [_P, _P, _P, _P, _i, _i, _i, _P]),
     "ub_conv1_wgrad_workspace_bytes": (_ll, [_i, _i, _i]),

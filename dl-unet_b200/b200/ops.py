@@ -126,8 +126,17 @@ def set_tuning(bn=0, bw=0, bh=0, splits=0):
     _lib.load().ub_set_tuning(bn, bw, bh, splits)
 
 
+OPT_STREAM_K = 13
+_options = {}          # what set_option was last called with (the library has no getter)
+
+
 def set_option(key, value):
     _lib.load().ub_set_option(int(key), int(value))
+    _options[int(key)] = int(value)
+
+
+def get_option(key, default):
+    return _options.get(int(key), default)
 
 
 def device_error():
@@ -304,12 +313,23 @@ def upconv2x2_fwd(x, w_fwd, bias, y):
     return y
 
 
-def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None):
+def upconv2x2_dgrad(dy, w_dgrad, dx, relu_src=None, dbias=None, dbias_part=None):
+    """dbias_part: [partial_rows(PROD_UPDGRAD, n, h, w, C), C] also receives partial rows of the column sums of dx -- the
+    bias gradient of the conv that produced the up-convolution's input; dbias (fp32 [C]): reduced here and ADDED to it."""
     _need_cuda(dy, w_dgrad, dx)
     n, h, w, ci = dx.shape
+    own = dbias is not None and dbias_part is None
+    if own:
+        dbias_part = _part(partial_rows(PROD_UPDGRAD, n, h, w, ci), ci, dx)
     with _timed("igemm:up_dgrad", n * h * w * 2.0 * (4 * dy.shape[3] + ci * (2 if relu_src is not None else 1)),
                 2.0 * n * h * w * ci * 4 * dy.shape[3]):
-        _chk(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
+        if dbias_part is None:
+            _chk(_lib.load().ub_upconv2x2_dgrad(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _stream()), "upconv2x2_dgrad")
+        else:
+            _chk(_lib.load().ub_upconv2x2_dgrad_bias(_t4p(dy), _ptr(w_dgrad), _t4p(dx), _t4p(relu_src), _ptr(dbias_part),
+                                                     _stream()), "upconv2x2_dgrad_bias")
+    if own:
+        reduce_partials(dbias_part, dbias_part.shape[0], ci, ci, dbias, True)
     return dx
 
 
@@ -325,7 +345,7 @@ def upconv2x2_wgrad(x, dy, dw_packed):
 # Kernels that reduce over pixels into a short vector store one row of partial sums per CTA (no atomics); the rows are
 # summed in order by the unpack job table (engine) or by reduce_partials (the `dbias=` / `out=` forms below, which keep
 # the old "accumulate into a [C] tensor" semantics for tests and tools).
-PROD_POOL, PROD_COLSUM, PROD_DGRAD, PROD_HEAD, PROD_CONV1 = 0, 1, 2, 3, 4
+PROD_POOL, PROD_COLSUM, PROD_DGRAD, PROD_HEAD, PROD_CONV1, PROD_UPDGRAD = 0, 1, 2, 3, 4, 5
 HEAD_STRIDE, CONV1_STRIDE = 194, 640
 
 

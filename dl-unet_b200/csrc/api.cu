@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -41,6 +42,8 @@ int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_mask_l2_prefetch = 1;
 int g_igemm_dbg = 0;
+int g_pair_rings = 0;       // CTA-pair kernel smem split: 0 auto, 1 always <5 operand stages, 4 store buffers>, 2 always <3, 8>
+int g_stream_k = 1;         // stream-K in the CTA-pair kernel: 0 off, 1 when the last wave is < 97 % full, 2 always
 int g_pair_mode = 1;        // N = 256 tiles of the tap-per-load conv kernel on CTA pairs (cta_group::2); 0: one CTA per tile
 int g_conv1_dbg = 0;
 int g_conv1_wgrad_tc = 1;   // conv11c weight gradient on the tensor pipe (0: CUDA-core kernel)
@@ -220,7 +223,7 @@ int pick_bn(int n_total, long long m_tiles) {
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (n_total % bn) continue;
-    if (m_tiles * (n_total / bn) >= num_sms() || bn == 64) return bn;
+    if (m_tiles * (n_total / bn) >= num_sms_physical() || bn == 64) return bn;   // physical: a plan, not a launch property
   }
   return 64;
 }
@@ -243,20 +246,81 @@ int launch_igemm_t(const IgemmParams& P, cudaStream_t st) {
 bool pair_mode(int BN) { return BN == 256 && g_pair_mode != 0; }
 int b_box_rows(int BN) { return pair_mode(BN) ? 128 : BN; }   // a CTA of a pair loads half of the N = 256 weight rows
 
-int launch_igemm_pair(const IgemmParams& P, cudaStream_t st) {
-  using C = IgemmPairCfg;
+// Stream-K workspace of the CTA-pair kernel: one per (device, stream) -- launches on one stream are ordered, so they can
+// share it; 256 KB of dumped accumulators + two flags per pair.  Allocated on first use (inside a relaxed capture-mode
+// guard, as an allocator must when the stream is being captured); the flags are zeroed ON the stream, so that a
+// captured launch sequence replays the (idempotent) zeroing too.  Never freed: it lives as long as the library.
+struct SkWorkspace {
+  float* ws;
+  unsigned int* flags;
+};
+static constexpr int SK_MAX_PAIRS = 128;
+static int sk_workspace(cudaStream_t st, SkWorkspace* out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SkWorkspace> table;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = table.find({dev, st});
+  if (it != table.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  SkWorkspace w{nullptr, nullptr};
+  const size_t ws_bytes = (size_t)SK_MAX_PAIRS * SK_SLOT_FLOATS * sizeof(float);
+  const size_t flag_bytes = (size_t)SK_MAX_PAIRS * 2 * sizeof(unsigned int);
+  cudaError_t e = cudaMalloc(&w.ws, ws_bytes + flag_bytes);
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  if (e != cudaSuccess) return (int)e;
+  w.flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(w.ws) + ws_bytes);
+  e = cudaMemsetAsync(w.flags, 0, flag_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  table[{dev, st}] = w;
+  *out = w;
+  return 0;
+}
+
+template <int NSTAGE, int NEPI>
+static int launch_igemm_pair_t(const IgemmParams& P, int grid, cudaStream_t st) {
+  using C = IgemmPairCfg<NSTAGE, NEPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_pair_kernel<NSTAGE, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  igemm_pair_kernel<NSTAGE, NEPI><<<grid, 384, C::SMEM_BYTES, st>>>(P);
+  return (int)cudaGetLastError();
+}
+
+int launch_igemm_pair(const IgemmParams& P0, cudaStream_t st) {
+  IgemmParams P = P0;
   const long long m_tiles = (long long)P.n_img * P.tiles_y * P.tiles_x;
   const long long units = ((m_tiles + 1) / 2) * P.n_tiles_n;
   long long pairs = num_sms() / 2;
   if (units < pairs) pairs = units;
-  igemm_pair_kernel<<<(int)(2 * pairs), 384, C::SMEM_BYTES, st>>>(P);
-  return (int)cudaGetLastError();
+  // stream-K when the idle tail of the last round-robin wave is worth more than the dump + fix-up of the split units
+  // (~40 K steps of one pair: measured, profiles/r2_streamk_vs_units.log -- the up-convolutions, with 8-32 K steps per
+  // unit, lose; conv52c / conv41e forward gain 12 %), and a pair's share is at least one unit, so that a unit is never
+  // split across more than two pairs
+  P.stream_k = 0;
+  const long long waves = (units + pairs - 1) / pairs;
+  const double idle_ksteps = ((double)waves - (double)units / (double)pairs) * P.n_taps * P.kchunks;
+  if (g_stream_k != 0 && units >= pairs && pairs <= SK_MAX_PAIRS && (g_stream_k == 2 || idle_ksteps >= 40.0)) {
+    SkWorkspace w;
+    int e = sk_workspace(st, &w);
+    if (e) return e;
+    P.stream_k = 1;
+    P.sk_ws = w.ws;
+    P.sk_flags = w.flags;
+  }
+  // very short K loops (up-convolutions 1 and 2: 2-8 steps per unit) gain 2-7 % from more stores in flight; from 16 steps on
+  // the operand stages matter more (profiles/r2_pair_rings.log)
+  const int k_iters = P.n_taps * P.kchunks;
+  const bool store_bound = g_pair_rings == 2 || (g_pair_rings == 0 && k_iters <= 8);
+  return store_bound ? launch_igemm_pair_t<3, 8>(P, (int)(2 * pairs), st) : launch_igemm_pair_t<5, 4>(P, (int)(2 * pairs), st);
 }
 
 int launch_igemm(const IgemmParams& P0, int BN, cudaStream_t st) {
@@ -370,6 +434,9 @@ bool igemm2_eligible(const ub_tensor4* in, const ub_tensor4* out) {
   if (g_igemm2_mode == 0) return false;
   if (in->c > 256 || out->c > 256) return false;
   if (g_igemm2_mode == 1 && out->w < 96) return false;
+  // N = 256: the tap-per-load kernel on CTA pairs is faster (conv32e forward 155 -> 125 us, conv31c forward 143 -> 128 us,
+  // conv21e dgrad 325 -> 313 us with the fused column sums; profiles/r2_pair256_vs_igemm2.log)
+  if (g_igemm2_mode == 1 && out->c == 256 && g_pair_mode != 0 && g_force_bn == 0) return false;
   return true;
 }
 
@@ -787,6 +854,8 @@ void ub_set_option(int key, int value) {
   if (key == 8) g_conv1_wgrad_tc = value;
   if (key == 9) g_conv1_dbg = value;
   if (key == 11) g_pair_mode = value;
+  if (key == 13) g_stream_k = value;
+  if (key == 14) g_pair_rings = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }
@@ -990,7 +1059,22 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   P.relu = 0;
   P.omap_div = 1 << 30;
   if ((e = set_mask(P, relu_src, dx))) return e;
+  if (dbias != nullptr && pair_mode(BN) && dx->c <= 1024) {   // the CTA-pair kernel sums the stored columns itself
+    P.dbias = dbias;
+    P.dbias_c0 = dbias_c0;
+    P.dbias_rows = num_sms_physical();
+    *fused = true;
+  }
   return launch_igemm(P, BN, (cudaStream_t)stream);
+}
+
+// does the tap-per-load kernel run this output shape on CTA pairs (N tiles of 256)?
+static bool igemm_runs_on_pairs(int n, int h, int w, int c_out_total) {
+  IgemmParams P;
+  memset(&P, 0, sizeof(P));
+  int BN;
+  fill_common(P, w, h, n, c_out_total, BN);
+  return pair_mode(BN) && c_out_total <= 1024;
 }
 
 int ub_colsum(const void* g, float* part, long long n_pix, int c, long long ld, void* stream);
@@ -1168,9 +1252,10 @@ int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, 
   return launch_igemm(P, BN, (cudaStream_t)stream);
 }
 
-int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
-                       void* stream) {
+static int upconv2x2_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                                void* stream, float* dbias, bool* fused) {
   int e;
+  *fused = false;
   if ((e = check_view(dy)) || (e = check_view(dx))) return e;
   if (!w_dgrad || !aligned16(w_dgrad)) return w_dgrad ? UB_E_ALIGN : UB_E_ARG;
   if (dy->n != dx->n || dy->h != 2 * dx->h || dy->w != 2 * dx->w) return UB_E_SHAPE;
@@ -1197,7 +1282,29 @@ int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tenso
   P.relu = 0;
   P.omap_div = 1 << 30;
   if ((e = set_mask(P, relu_src, dx))) return e;
+  if (dbias != nullptr && pair_mode(BN) && dx->c <= 1024) {
+    P.dbias = dbias;
+    P.dbias_c0 = 0;
+    P.dbias_rows = num_sms_physical();
+    *fused = true;
+  }
   return launch_igemm(P, BN, (cudaStream_t)stream);
+}
+
+int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                       void* stream) {
+  bool fused;
+  return upconv2x2_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, nullptr, &fused);
+}
+
+int ub_upconv2x2_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                            float* dbias_part, void* stream) {
+  if (!dbias_part) return UB_E_ARG;
+  bool fused;
+  int e = upconv2x2_dgrad_impl(dy, w_dgrad, dx, relu_src, stream, dbias_part, &fused);
+  if (e || fused) return e;
+  if (dx->sy != (long long)dx->w * dx->sx || dx->sn != (long long)dx->h * dx->sy) return UB_E_SHAPE;
+  return ub_colsum(dx->ptr, dbias_part, (long long)dx->n * dx->h * dx->w, dx->c, dx->sx, stream);
 }
 
 int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream) {
@@ -1576,9 +1683,10 @@ int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) 
     case 2: {
       if (c <= c0 || c_dy <= 0) return UB_E_SHAPE;
       ub_tensor4 dx{nullptr, n, h, w, c, 0, 0, 0}, dy{nullptr, n, h - 2, w - 2, c_dy, 0, 0, 0};
-      if (igemm2_eligible(&dy, &dx)) return num_sms_physical();
+      if (igemm2_eligible(&dy, &dx) || igemm_runs_on_pairs(n, h, w, c)) return num_sms_physical();
       return colsum_blocks((long long)n * h * w, c - c0);
     }
+    case 5: return igemm_runs_on_pairs(n, h, w, c) ? num_sms_physical() : colsum_blocks((long long)n * h * w, c);
     case 3: return head_bwd_blocks((long long)n * h * w);
     case 4: {
       if (g_conv1_wgrad_tc) {

@@ -51,7 +51,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // once: with global loads in the row loop the kernel sat in long-scoreboard stalls (ncu: 9.4 of 13.9 cycles per
 // issued instruction) however many warps were resident.
 constexpr int C1_ROWS = 96;   // output rows per block
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 4) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                         int n_img, int H, int W) {
   // grid = (ceil(Wo/16), ceil(Ho/C1_ROWS), n): no index divisions; a thread keeps its channel quad and its x
@@ -72,42 +72,46 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     if (c < cols_in) cp_async_4(&sx[i], xb + (long long)r * W + c);
   }
   cp_async_commit();
-  float wr[4][9], br[4];
+  // Packed fp32 pairs (fma.rn.f32x2, sm_100): one instruction updates two output channels, so the 36 FMAs per pixel
+  // quad become 18 -- the scalar version was FMA-pipe bound (a three-register FFMA occupies its pipe for two cycles:
+  // ncu 73 % issue-active, math-pipe throttle the top stall).  Same rounding as fmaf per element: bit-identical output.
+  uint64_t wr2[2][9], br2[2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    br[c] = __ldg(b + q * 4 + c);
+  for (int c = 0; c < 2; ++c) {
+    br2[c] = pack_f32x2(__ldg(b + q * 4 + 2 * c), __ldg(b + q * 4 + 2 * c + 1));
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (q * 4 + c) * 9 + t);
+    for (int t = 0; t < 9; ++t) wr2[c][t] = pack_f32x2(__ldg(w + (q * 4 + 2 * c) * 9 + t), __ldg(w + (q * 4 + 2 * c + 1) * 9 + t));
   }
   cp_async_wait<0>();
   __syncthreads();
   if (ox >= Wo) return;
   const float* sp = sx + px;
-  float in[9];
+  uint64_t in2[9];
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
-    in[3 + s] = sp[s];
-    in[6 + s] = sp[18 + s];
+    in2[3 + s] = pack_f32x2(sp[s], sp[s]);
+    in2[6 + s] = pack_f32x2(sp[18 + s], sp[18 + s]);
   }
   __nv_bfloat16* yp = y + (((long long)n * Ho + y_begin) * Wo + ox) * 64 + q * 4;
   for (int r = 0; r < y_end - y_begin; ++r) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      in[s] = in[3 + s];
-      in[3 + s] = in[6 + s];
-      in[6 + s] = sp[(r + 2) * 18 + s];
-    }
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a = br[c];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(in[t], wr[c][t], a);
-      o[c] = fmaxf(a, 0.0f);
+      in2[s] = in2[3 + s];
+      in2[3 + s] = in2[6 + s];
+      const float v = sp[(r + 2) * 18 + s];
+      in2[6 + s] = pack_f32x2(v, v);
     }
     uint2 pk;
-    pk.x = pack_bf16x2(o[0], o[1]);
-    pk.y = pack_bf16x2(o[2], o[3]);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint64_t a = br2[c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fma_f32x2(in2[t], wr2[c][t], a);
+      float lo, hi;
+      unpack_f32x2(a, lo, hi);
+      const uint32_t v = pack_bf16x2(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
+      if (c == 0) pk.x = v; else pk.y = v;
+    }
     *reinterpret_cast<uint2*>(yp) = pk;
     yp += (long long)Wo * 64;
   }

@@ -22,7 +22,7 @@ __device__ __forceinline__ void load_mask(const __nv_bfloat16* mcols, uint4 (&m4
 __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, int relu, bool mask_on, bool mask_valid,
                                            const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                            const float* shead = nullptr, float2* head_part = nullptr,
-                                           bool stage = true, float* col_acc = nullptr) {
+                                           bool stage = true, float* col_acc = nullptr, bool sum_valid = true) {
   if (sbias != nullptr) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -77,6 +77,10 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
     }
   }
   if (col_acc != nullptr) {
+    if (!sum_valid) {   // a row that is no pixel of the tensor (patch smaller than 128 rows, tile beyond the last one)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = 0.0f;
+    }
     // Column sums over the warp's 32 pixel rows (the bias gradient of the layer that consumes this gradient):
     // recursive halving -- each step a lane keeps one half of its columns and receives the partner's sums of that
     // half -- 31 shuffles instead of 160, and lane l ends up with the total of column l of this warp's 32-column
@@ -104,14 +108,19 @@ __device__ __forceinline__ void epi_finish(float (&f)[32], const float* sbias, i
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, int relu, bool mask_on, bool mask_valid,
                                           const uint4 (&m4)[4], uint8_t* ebuf, int row, int h,
                                           const float* shead = nullptr, float2* head_part = nullptr,
-                                          bool stage = true, float* col_acc = nullptr) {
+                                          bool stage = true, float* col_acc = nullptr, bool sum_valid = true,
+                                          const float* partial = nullptr) {
   uint32_t v[32];
   tmem_ld_32x32b_x32(taddr, v);
   tmem_ld_wait();
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage, col_acc);
+  if (partial != nullptr) {   // stream-K: the rest of this unit's K range, dumped by another CTA as [column][128 rows]
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] += __ldcg(partial + i * 128);
+  }
+  epi_finish(f, sbias, relu, mask_on, mask_valid, m4, ebuf, row, h, shead, head_part, stage, col_acc, sum_valid);
 }
 
 }  // namespace ub

@@ -47,6 +47,15 @@ struct alignas(64) IgemmParams {
   int out_W, out_H;                     // valid output extent (for the mask read predicate)
   int omap_div;                         // column c -> o_map[c / omap_div], channel coord c % omap_div
   int dbg;                              // experiment switch (ub_set_option 5): 1 = do not wait for earlier TMA stores
+  // igemm_pair_kernel only: fused column sums of the stored output (bias gradient of the layer that produced the input of
+  // this dgrad): row blockIdx.x of dbias[dbias_rows][N - dbias_c0], channels >= dbias_c0; nullptr = off
+  float* dbias;
+  int dbias_c0, dbias_rows;
+  // igemm_pair_kernel only: stream-K (see igemm_pair.cuh).  sk_ws: [pairs][2 CTAs][256 columns][128 rows] fp32 partial
+  // accumulators, sk_flags: [pairs][2] "partial ready" flags (0 between launches)
+  int stream_k;
+  float* sk_ws;
+  unsigned int* sk_flags;
 };
 
 template <int BN>

@@ -15,6 +15,17 @@
 //   * epilogue + store warp (both CTAs): exactly igemm_kernel's, on the CTA's own 128 TMEM lanes; "accumulator drained"
 //     arrives on the leader's TEMPTY[acc] (2 x 256 arrivals).
 // TMEM is allocated and freed with the cta_group::2 forms by the same warp of both CTAs, cluster barriers around.
+//
+// Stream-K (p.stream_k): the deep layers have few, long units (conv52c forward: 224 units of 144 K steps on 74 pairs =
+// 3.03 waves, the last one 3 % full).  Instead of whole units round-robin, every pair takes one contiguous range of
+// total_units * k_iters / n_pairs K STEPS of the unit sequence, so all pairs finish together.  A range that starts
+// inside a unit computes that unit's remaining K steps FIRST and dumps the fp32 accumulator to a workspace slot
+// (coalesced, [column][row]) and raises the slot's flag; a range that ends inside a unit computes its leading K steps
+// LAST, and its epilogue adds the partial its successor dumped long before (a unit is split across at most two pairs:
+// a pair's share is >= one unit, the host guarantees it).  The waiter has the HIGHER block index than the pair it waits
+// for (ranges are handed out in reverse block order), so even with fewer resident CTAs than the grid the dumping pair
+// is scheduled first: no circular wait.  Flags are reset by their consumer: 0 between launches, CUDA-graph safe.
+// Deterministic: the split points are a function of the shape and the grid only.
 #pragma once
 #include "epilogue.cuh"
 #include "igemm.cuh"
@@ -22,21 +33,90 @@
 
 namespace ub {
 
+// NSTAGE operand stages of 32 KB and NEPI output staging buffers of 16 KB (one 128-row x 64-column bf16 chunk each) share
+// the 224 KB: <5, 4> for the convolutions (long K loops: the operand pipeline matters), <3, 8> for the up-convolutions,
+// whose K loop is 2-32 steps and whose pace-maker is the drain of the TMA stores -- with NEPI buffers NEPI - 1 stores
+// are in flight instead of one.
+template <int NSTAGE_, int NEPI_>
 struct IgemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = 128 * 128;          // this CTA's half of the 256 columns
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 2 * 16384;
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int NEPI = NEPI_;
+  static constexpr int EPI_BYTES = NEPI * 16384;
   static constexpr int BAR_BYTES = 2048;
-  static constexpr int SMEM_LIMIT = 232448 - 1024;
-  static constexpr int NSTAGE = (SMEM_LIMIT - EPI_BYTES - BAR_BYTES) / STAGE_BYTES;   // 6
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+  static_assert(NEPI >= 2 && NEPI <= 8 && NSTAGE >= 2 && NSTAGE <= 8, "ring sizes");
 };
 
+// One pair's sequence of work items: (unit, K-step range [kb, ke)).
+struct PairItem {
+  int u, kb, ke;
+};
+struct PairSched {
+  int u, step, total_units, k_iters;
+  long long g0, g1;   // stream-K: this pair's range of global K steps
+  bool sk;
+  __device__ __forceinline__ PairSched(int pair, int n_pairs, int total_units_, int k_iters_, bool sk_)
+      : total_units(total_units_), k_iters(k_iters_), sk(sk_) {
+    if (sk) {
+      const int lp = n_pairs - 1 - pair;   // reverse order: the pair waited for has the lower block index
+      const long long total = (long long)total_units * k_iters;
+      g0 = total * lp / n_pairs;
+      g1 = total * (lp + 1) / n_pairs;
+      u = (int)(g0 / k_iters);
+      step = 1;
+    } else {
+      g0 = g1 = 0;
+      u = pair;
+      step = n_pairs;
+    }
+  }
+  __device__ __forceinline__ bool next(PairItem& it) {
+    if (sk) {
+      const long long base = (long long)u * k_iters;
+      if (base >= g1) return false;
+      it.u = u;
+      it.kb = g0 > base ? (int)(g0 - base) : 0;
+      it.ke = g1 - base < k_iters ? (int)(g1 - base) : k_iters;
+    } else {
+      if (u >= total_units) return false;
+      it.u = u;
+      it.kb = 0;
+      it.ke = k_iters;
+    }
+    u += step;
+    return true;
+  }
+};
+
+constexpr int SK_SLOT_FLOATS = 2 * 256 * 128;   // one pair's dumped accumulators: [2 CTAs][256 columns][128 rows]
+
+// bounded spin until *flag != 0 (acquire), then reset it for the next launch
+__device__ __forceinline__ void sk_wait_and_reset(unsigned int* flag) {
+  unsigned int v;
+  const uint64_t t0 = globaltimer_ns();
+  unsigned int spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0) break;
+    __nanosleep(100);
+    if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > UB_WAIT_LIMIT_NS) {
+      atomicExch(&g_device_error, 0x90000000u | (blockIdx.x & 0xffff));
+      __threadfence_system();
+      __trap();
+    }
+  }
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");
+}
+
+template <int NSTAGE_, int NEPI_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
-  using C = IgemmPairCfg;
+  using C = IgemmPairCfg<NSTAGE_, NEPI_>;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -45,7 +125,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
   uint64_t* empty = full + C::NSTAGE;
   uint64_t* tfull = empty + C::NSTAGE;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* efull = tempty + 2;          // staging buffer written by the 256 epilogue threads
+  uint64_t* eempty = efull + C::NEPI;    // ... and read out by its TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty + C::NEPI);
   float* sbias = reinterpret_cast<float*>(epi + C::EPI_BYTES + 1024);
 
   const int warp = threadIdx.x >> 5;
@@ -70,6 +152,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 512);    // the epilogue threads of both CTAs (only the leader's copy is used)
     }
+    for (int i = 0; i < C::NEPI; ++i) {
+      mbar_init(&efull[i], 256);
+      mbar_init(&eempty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -92,7 +178,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     // ------------------------------------------------------- TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = pair; u < total_units; u += n_pairs) {
+    PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
+    PairItem item;
+    while (sched.next(item)) {
+      const int u = item.u;
       const int nt = u % p.n_tiles_n;
       int mt = (u / p.n_tiles_n) * 2 + (int)rank;
       const int tx = mt % p.tiles_x;
@@ -100,16 +189,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
       const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
-      if (p.mask != nullptr) {
+      if (p.mask != nullptr && item.kb == 0) {   // the pair that stores the unit reads the mask
         if (elect_one()) {
           for (int j = 0; j < BN / 64; ++j) tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, x0, y0, img);
         }
         __syncwarp();
       }
-      for (int tap = 0; tap < p.n_taps; ++tap) {
+      int tap = item.kb / p.kchunks, kc = item.kb - tap * p.kchunks;
+      for (int ki = item.kb; ki < item.ke; ++ki) {
         const CUtensorMap* am = &p.a_map[p.tap_map[tap]];
         const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        {
           mbar_wait(&empty[stage], phase ^ 1, 61);
           if (elect_one()) {
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -124,6 +214,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
             phase ^= 1;
           }
         }
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++tap;
+        }
       }
     }
   } else if (warp == 1 && leader) {
@@ -134,12 +228,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int u = pair; u < total_units; u += n_pairs, ++it) {
+    PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
+    PairItem item;
+    for (; sched.next(item); ++it) {
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, 62);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int ki = 0; ki < k_iters; ++ki) {
+      for (int ki = item.kb; ki < item.ke; ++ki) {
         mbar_wait(&full[stage], phase, 63);
         tc_fence_after();
         if (elect_one()) {
@@ -147,9 +243,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_2sm(d_tmem, umma_desc(hiD, loA0 + so + 2 * k), umma_desc(hiD, loB0 + so + 2 * k), idesc,
-                          (ki > 0 || k > 0) ? 1u : 0u);
+                          (ki > item.kb || k > 0) ? 1u : 0u);
           umma_commit_2sm(&empty[stage]);
-          if (ki == k_iters - 1) umma_commit_2sm(&tfull[acc]);
+          if (ki == item.ke - 1) umma_commit_2sm(&tfull[acc]);
         }
         __syncwarp();
         if (++stage == C::NSTAGE) {
@@ -161,7 +257,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
   } else if (warp == 3) {
     // ------------------------------------------------------- TMA store warp (both CTAs; see igemm.cuh)
     uint32_t c = 0;
-    for (int u = pair; u < total_units; u += n_pairs) {
+    PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
+    PairItem item;
+    while (sched.next(item)) {
+      if (item.kb > 0) continue;      // a dumped partial: nothing to store
+      const int u = item.u;
       const int nt = u % p.n_tiles_n;
       int mt = (u / p.n_tiles_n) * 2 + (int)rank;
       const int tx = mt % p.tiles_x;
@@ -170,24 +270,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       const int img = mt / p.tiles_y;
       const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
       for (int j = 0; j < BN / 64; ++j, ++c) {
-        const uint32_t b = c & 1;
-        named_bar_sync(2 + b, 288);
-        if (c >= 1) {
-          if (elect_one()) tma_store_wait_read<0>();
-          __syncwarp();
-          named_bar_arrive(4 + ((c - 1) & 1), 288);
-        }
-        if (elect_one()) {
+        const uint32_t b = c % C::NEPI;
+        mbar_wait(&efull[b], (c / C::NEPI) & 1, 66);
+        if (lane == 0) {
           const int col0 = n0 + j * 64;
           const int mi = col0 / p.omap_div;
           tma_store_4d(&p.o_map[mi], epi + b * 16384, col0 - mi * p.omap_div, x0, y0, img);
           tma_store_commit();
+          // up to NEPI - 1 stores in flight: the oldest of them has read its buffer out -> hand it back
+          if (c >= (uint32_t)(C::NEPI - 2)) {
+            tma_store_wait_read<C::NEPI - 2>();
+            mbar_arrive(&eempty[(c - (C::NEPI - 2)) % C::NEPI]);
+          }
         }
         __syncwarp();
       }
     }
-    if (elect_one()) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
+    if (p.dbias != nullptr) named_bar_arrive(6, 288);   // the staging buffers are free: the epilogue reuses them for the sums
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue (both CTAs, own 128 TMEM lanes)
     const int q = warp & 3;
@@ -197,9 +298,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     const int by = row / p.BW, bx = row - by * p.BW;
     const bool row_in_box = row < p.BW * p.BH;
     const bool mask_on = p.mask != nullptr;
+    // fused bias gradient: per-thread running column sums in registers, one per 64-column chunk of the N <= 1024 outputs
+    // (static indices only), combined across the four row quarters in fixed order at the end (deterministic)
+    const bool colsum_on = p.dbias != nullptr;
+    float cacc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cacc[i] = 0.0f;
     int it = 0;
     uint32_t chunk_ctr = 0;
-    for (int u = pair; u < total_units; u += n_pairs, ++it) {
+    PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
+    PairItem item;
+    const int lp = n_pairs - 1 - pair;      // stream-K: this pair's position in the range order = its workspace slot
+    for (; sched.next(item); ++it) {
+      const int u = item.u;
       const int nt = u % p.n_tiles_n;
       int mt = (u / p.n_tiles_n) * 2 + (int)rank;
       const int tx = mt % p.tiles_x;
@@ -217,6 +328,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       mbar_wait(&tfull[acc], acc_phase, 64);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (item.kb > 0) {
+        // stream-K: the trailing K steps of a unit another pair finishes -- dump the accumulator, raise the flag
+        float* slot = p.sk_ws + ((long long)lp * 2 + rank) * (SK_SLOT_FLOATS / 2) + row;
+#pragma unroll 1
+        for (int j = 0; j < BN / 64; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + j * 64 + hw * 32, v);
+          tmem_ld_wait();
+          float* d = slot + (j * 64 + hw * 32) * 128;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) __stcg(d + i * 128, __uint_as_float(v[i]));
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tempty[acc]);
+        __threadfence();
+        named_bar_sync(1, 256);
+        if (et == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + lp * 2 + rank), "r"(1u) : "memory");
+        continue;
+      }
+      const float* partial = nullptr;
+      if (item.ke < k_iters) {
+        // ... and the leading K steps of a unit whose rest the next range's pair dumped at its very start
+        if (et == 0) sk_wait_and_reset(p.sk_flags + (lp + 1) * 2 + rank);
+        named_bar_sync(1, 256);
+        partial = p.sk_ws + ((long long)(lp + 1) * 2 + rank) * (SK_SLOT_FLOATS / 2) + row;
+      }
       const bool px_valid = row_in_box && img < p.n_img && (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
       const __nv_bfloat16* mrow = nullptr;
       if (mask_on && px_valid)
@@ -224,17 +361,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
                n0 + hw * 32;
 #pragma unroll 1
       for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
-        uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-        if (chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 288);
+        const uint32_t eb = chunk_ctr % C::NEPI;
+        uint8_t* ebuf = epi + eb * 16384;
+        mbar_wait(&eempty[eb], ((chunk_ctr / C::NEPI) & 1) ^ 1, 65);
         uint4 m4[4];
         if (mrow != nullptr) load_mask(mrow + j * 64, m4);
+        float csum = 0.0f;
         epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
-                  mrow != nullptr, m4, ebuf, row, hw);
+                  mrow != nullptr, m4, ebuf, row, hw, nullptr, nullptr, true, colsum_on ? &csum : nullptr, px_valid,
+                  partial != nullptr ? partial + (j * 64 + hw * 32) * 128 : nullptr);
+        if (colsum_on) {
+          const int cidx = nt * (BN / 64) + j;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cacc[i] += cidx == i ? csum : 0.0f;
+        }
         fence_proxy_async_smem();
-        named_bar_arrive(2 + (chunk_ctr & 1), 288);
+        mbar_arrive(&efull[eb]);
       }
       tc_fence_before();
       mbar_arrive_leader(&tempty[acc]);
+    }
+    if (colsum_on) {
+      // one row of partial sums per CTA, no atomics: wait until the store warp has drained the staging buffers, then the
+      // row quarters q = 0..3 add their register sums into them one after the other; rows of CTAs that do not exist
+      // (grid smaller than the row count the host planned for) are zero-filled
+      named_bar_sync(6, 288);
+      float* scol = reinterpret_cast<float*>(epi);
+      const int N = p.n_tiles_n * BN;
+      for (int qq = 0; qq < 4; ++qq) {
+        if (q == qq) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = i * 64 + hw * 32 + lane;
+            if (col < N) scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc[i];
+          }
+        }
+        named_bar_sync(1, 256);
+      }
+      const int len = N - p.dbias_c0;
+      for (int ch = p.dbias_c0 + et; ch < N; ch += 256) {
+        p.dbias[(long long)blockIdx.x * len + ch - p.dbias_c0] = scol[ch];
+        for (int r = gridDim.x + blockIdx.x; r < p.dbias_rows; r += gridDim.x) p.dbias[(long long)r * len + ch - p.dbias_c0] = 0.0f;
+      }
     }
   }
 

@@ -60,7 +60,11 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  * key 7: host-side cache of encoded TMA tensor maps (1 = on [default], 0 = encode on every call).
  * key 8: conv11c weight gradient on the tensor pipe (1 = on [default], 0 = CUDA-core kernel).
  * key 11: N = 256 tiles of the tap-per-load conv / up-conv kernel on CTA pairs, tcgen05 cta_group::2 (1 = on [default],
- *         0 = one CTA per 128 x 256 tile). */
+ *         0 = one CTA per 128 x 256 tile).
+ * key 13: stream-K in the CTA-pair kernel (0 = whole units round-robin, 1 = contiguous K-step ranges per pair when the idle
+ *         tail of the last wave of units is worth >= 40 K steps [default], 2 = always).  Uses a library-owned 32 MB workspace per stream.
+ * key 14: shared-memory split of the CTA-pair kernel (0 = by K-loop length [default], 1 = 5 operand stages + 4 output
+ *         staging buffers, 2 = 3 + 8: up to 7 TMA stores in flight). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------
@@ -119,7 +123,8 @@ int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4
  *   producer 1: ub_colsum                     (n*h*w pixels, c channels)                       stride = c
  *   producer 2: ub_conv3x3_dgrad_bias         (n, h, w, c of dx; c_dy channels of dy; c0)      stride = c - c0
  *   producer 3: ub_head_bwd                   (n, h, w)                                        stride = 194
- *   producer 4: ub_conv1_wgrad                (n, h, w of the image)                           stride = 640 */
+ *   producer 4: ub_conv1_wgrad                (n, h, w of the image)                           stride = 640
+ *   producer 5: ub_upconv2x2_dgrad_bias       (n, h, w, c of dx)                               stride = c */
 int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0);
 /* dst[e] (+)= sum_r part[r * stride + e], e < length (one producer; the job table does all of them in one launch) */
 int ub_reduce_partials(const float* part, int rows, long long stride, int length, float* dst, int accumulate, void* stream);
@@ -145,6 +150,10 @@ int ub_conv3x3_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs,
 int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, const ub_tensor4* y, void* stream);
 int ub_upconv2x2_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
                        void* stream);
+/* ub_upconv2x2_dgrad, and partial rows (producer 5) of the column sums of dx: the bias gradient of the conv that produced
+ * the up-convolution's input (fused into the epilogue on the CTA-pair kernel, one extra column-sum pass otherwise) */
+int ub_upconv2x2_dgrad_bias(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
+                            float* dbias_part, void* stream);
 int ub_upconv2x2_wgrad(const ub_tensor4* x, const ub_tensor4* dy, float* dw_slabs, void* stream);
 
 /* ---- first convolution, Cin = 1 (network.py:131), fp32 NCHW image in, bf16 NHWC out, bias+ReLU fused ---- */

@@ -180,7 +180,8 @@ def test_conv3x3_fwd_fused_pool(ops, case):
 
 
 @pytest.mark.parametrize("shape", [(2, 20, 20, 64, 64, 0), (1, 70, 70, 64, 128, 64), (2, 33, 41, 128, 128, 0), (1, 12, 12, 256, 512, 0),
-                                   (1, 104, 104, 256, 256, 0)])
+                                   (1, 104, 104, 256, 256, 0), (2, 30, 30, 512, 1024, 0), (2, 58, 58, 256, 512, 256),
+                                   (3, 17, 23, 1024, 512, 0)])
 def test_conv3x3_dgrad_fused_bias(ops, shape):
     """dgrad + column sums of dx over the channels >= c0 (the bias gradient of the layer that produced the input;
     c0 > 0: only the up-conv half of a concat buffer), fused into the epilogue or -- for shapes that run on the
@@ -236,6 +237,15 @@ def test_upconv2x2(ops, shape):
     dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt, ops.PACK_UP_DGRAD), dx, nhwc(x))
     assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+    # ... with the column sums of dx (bias gradient of the conv below), fused on the CTA-pair kernel: same dx, same sums
+    dx2 = torch.full_like(dx, float("nan"))
+    db = torch.zeros(cin, device=DEV)
+    ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt, ops.PACK_UP_DGRAD), dx2, nhwc(x), dbias=db)
+    assert torch.equal(dx2, dx)
+    assert rel_l2(db, dx.float().sum((0, 1, 2))) < FP32_TOL
+    db2 = torch.zeros(cin, device=DEV)
+    ops.upconv2x2_dgrad(dyv, ops.pack_weight(wt, ops.PACK_UP_DGRAD), dx2, nhwc(x), dbias=db2)
+    assert torch.equal(db, db2)                                     # fixed summation order
     dwp = ops.wgrad_workspace(ops.PACK_UP_FWD, nhwc(x), cout, fill=float("nan"))
     ops.upconv2x2_wgrad(nhwc(x), dyv, dwp)
     dw = torch.empty_like(wt)
@@ -511,12 +521,14 @@ def test_unpack_range_sums_slabs_in_fixed_order(ops, n_slabs):
 
 
 @pytest.mark.parametrize("shape", [(1, 12, 12, 256, 256), (2, 20, 21, 128, 256), (3, 13, 17, 256, 512), (1, 30, 30, 512, 1024),
-                                   (5, 9, 40, 64, 256)])
+                                   (5, 9, 40, 64, 256), (12, 40, 37, 256, 512), (16, 30, 30, 1024, 1024)])
 def test_igemm_pair_kernel(ops, shape):
     """igemm_pair.cuh: the tap-per-load conv kernel on CTA pairs (tcgen05 cta_group::2, M = 256 pixels x N = 256 per
     instruction, each CTA loads half of the weight slab).  N tiles of 256 are forced so that small shapes reach it; odd
     tile counts leave one CTA of the last pair without work (zero-filled loads, clipped stores).  Same K order as the
-    one-CTA kernel, so the two must agree bit for bit."""
+    one-CTA kernel, so the two must agree bit for bit.  Stream-K (option 13 = 2: always; the two large shapes have more
+    units than pairs, so units are really split) changes the summation order inside split units only: same tolerance
+    against the fp32 reference, bit-identical from run to run."""
     n, h, w, cin, cout = shape
     torch.manual_seed(sum(shape))
     x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
@@ -529,20 +541,31 @@ def test_igemm_pair_kernel(ops, shape):
     outs = {}
     ops.set_tuning(bn=256)
     try:
-        for pair in (1, 0):
-            ops.set_option(11, pair)
+        for cfg in ((1, 0), (0, 0), (1, 2), (1, 2, "again")):
+            ops.set_option(11, cfg[0])
+            ops.set_option(13, cfg[1])
             y = torch.full((n, h - 2, w - 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
             ops.conv3x3_fwd(nhwc(x), ops.pack_weight(wt, ops.PACK_CONV_FWD), b, y, relu=True)
             dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
-            if cin % 256 == 0:      # the dgrad's N is Cin
-                ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x))
-            outs[pair] = (y, dx)
+            db = torch.zeros(cin, device=DEV)
+            if cin % 256 == 0:      # the dgrad's N is Cin; the pair kernel sums the columns of dx in its epilogue
+                ops.conv3x3_dgrad(nhwc(dy), ops.pack_weight(wt, ops.PACK_CONV_DGRAD), dx, nhwc(x), db)
+            outs[cfg] = (y, dx, db)
     finally:
         ops.set_option(11, 1)
+        ops.set_option(13, 1)
         ops.set_tuning()
-    y, dx = outs[1]
-    assert rel_l2(nchw(y), ref) < BF16_OUT_TOL
-    assert torch.equal(y, outs[0][0])
+    for cfg in ((1, 0), (1, 2)):
+        y, dx, db = outs[cfg]
+        assert rel_l2(nchw(y), ref) < BF16_OUT_TOL
+        if cin % 256 == 0:
+            assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
+            assert rel_l2(db, dx.float().sum((0, 1, 2))) < FP32_TOL
+    with_dgrad = cin % 256 == 0            # else dx was never written
+    assert torch.equal(outs[(1, 0)][0], outs[(0, 0)][0])                                   # pairs == one CTA, bit for bit
+    assert torch.equal(outs[(1, 2)][0], outs[(1, 2, "again")][0])                          # stream-K is deterministic
+    if with_dgrad:
+        assert torch.equal(outs[(1, 0)][1], outs[(0, 0)][1])
+        assert all(torch.equal(a, b) for a, b in zip(outs[(1, 2)][1:], outs[(1, 2, "again")][1:]))
     if cin % 256 == 0:
-        assert rel_l2(nchw(dx), gx * (xq > 0)) < BF16_OUT_TOL
-        assert torch.equal(dx, outs[0][1])
+        assert rel_l2(outs[(0, 0)][2], outs[(0, 0)][1].float().sum((0, 1, 2))) < FP32_TOL
