@@ -282,18 +282,20 @@ static int sk_workspace(cudaStream_t st, SkWorkspace* out) {
   return 0;
 }
 
-template <int NSTAGE, int NEPI>
+template <int NSTAGE, int NEPI, bool DGRAD>
 static int launch_igemm_pair_t(const IgemmParams& P, int grid, cudaStream_t st) {
   using C = IgemmPairCfg<NSTAGE, NEPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_pair_kernel<NSTAGE, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e =
+        cudaFuncSetAttribute(igemm_pair_kernel<NSTAGE, NEPI, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  igemm_pair_kernel<NSTAGE, NEPI><<<grid, 384, C::SMEM_BYTES, st>>>(P);
+  igemm_pair_kernel<NSTAGE, NEPI, DGRAD><<<grid, PAIR_THREADS, C::SMEM_BYTES, st>>>(P);
   return (int)cudaGetLastError();
 }
+static uint32_t div_magic(long long d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (unsigned long long)d - 1) / (unsigned long long)d); }
 
 int launch_igemm_pair(const IgemmParams& P0, cudaStream_t st) {
   IgemmParams P = P0;
@@ -320,7 +322,18 @@ int launch_igemm_pair(const IgemmParams& P0, cudaStream_t st) {
   // the operand stages matter more (profiles/r2_pair_rings.log)
   const int k_iters = P.n_taps * P.kchunks;
   const bool store_bound = g_pair_rings == 2 || (g_pair_rings == 0 && k_iters <= 8);
-  return store_bound ? launch_igemm_pair_t<3, 8>(P, (int)(2 * pairs), st) : launch_igemm_pair_t<5, 4>(P, (int)(2 * pairs), st);
+  P.mg_ntn = div_magic(P.n_tiles_n);
+  P.mg_tx = div_magic(P.tiles_x);
+  P.mg_ty = div_magic(P.tiles_y);
+  P.mg_bw = div_magic(P.BW);
+  P.mg_omap = div_magic(P.omap_div);
+  if (m_tiles * (long long)P.tiles_x >= (1ll << 31)) return UB_E_SHAPE;   // fast_div range
+  // dgrad flavour: ReLU-backward mask and / or column sums, no bias, no ReLU; forward flavour: the opposite
+  const bool dgrad = P.mask != nullptr || P.dbias != nullptr;
+  if (dgrad && (P.bias != nullptr || P.relu)) return UB_E_ARG;
+  const int grid = (int)(2 * pairs);
+  if (dgrad) return store_bound ? launch_igemm_pair_t<3, 8, true>(P, grid, st) : launch_igemm_pair_t<5, 4, true>(P, grid, st);
+  return store_bound ? launch_igemm_pair_t<3, 8, false>(P, grid, st) : launch_igemm_pair_t<5, 4, false>(P, grid, st);
 }
 
 int launch_igemm(const IgemmParams& P0, int BN, cudaStream_t st) {

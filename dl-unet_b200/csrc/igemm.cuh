@@ -56,6 +56,8 @@ struct alignas(64) IgemmParams {
   int stream_k;
   float* sk_ws;
   unsigned int* sk_flags;
+  // igemm_pair_kernel only: fast_div magics of n_tiles_n, tiles_x, tiles_y, BW, omap_div (filled by the launcher)
+  uint32_t mg_ntn, mg_tx, mg_ty, mg_bw, mg_omap;
 };
 
 template <int BN>

@@ -12,8 +12,14 @@
 //     leader arms FULL with the bytes of both CTAs.
 //   * MMA issuer (warp 1 of the leader only): waits FULL[stage], issues four cta_group::2 MMAs, and commits with a
 //     multicast arrive on EMPTY[stage] of both CTAs; the last commit of a tile multicasts on TFULL[acc] of both CTAs.
-//   * epilogue + store warp (both CTAs): exactly igemm_kernel's, on the CTA's own 128 TMEM lanes; "accumulator drained"
-//     arrives on the leader's TEMPTY[acc] (2 x 256 arrivals).
+//   * epilogue (16 warps of BOTH CTAs, on the CTA's own 128 TMEM lanes) + store warp; "accumulator drained" arrives on
+//     the leader's TEMPTY[acc] (2 x 512 arrivals).
+// Epilogue: SIXTEEN warps, warp = (TMEM lane quarter q, 16-column slice cs of the 64-column chunk).  The per-chunk chain
+// tcgen05.ld -> bias / mask -> bf16 -> st.shared -> proxy fence -> arrive is latency bound (ncu on up-convolution 1,
+// profiles/r2_ncu_upconv1_fwd_pair.txt: the eight warps of the first version issued 18 % of the time, the rest was
+// fixed-latency waits, fetch bubbles behind 15 branches per chunk and ~350 instructions of index arithmetic per tile),
+// and with K loops of 2-32 steps the epilogue IS the kernel.  Four warps per scheduler instead of two, forward / dgrad
+// variants compiled separately (no mask, column-sum or bias code in the other one), unit coordinates by multiply-high.
 // TMEM is allocated and freed with the cta_group::2 forms by the same warp of both CTAs, cluster barriers around.
 //
 // Stream-K (p.stream_k): the deep layers have few, long units (conv52c forward: 224 units of 144 K steps on 74 pairs =
@@ -114,10 +120,30 @@ __device__ __forceinline__ void sk_wait_and_reset(unsigned int* flag) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");
 }
 
-template <int NSTAGE_, int NEPI_>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
+struct UnitCoord {
+  int nt, x0, y0, img;
+};
+__device__ __forceinline__ UnitCoord decode_unit(const IgemmParams& p, int u, int rank) {
+  UnitCoord c;
+  const int mp = fast_div(u, p.mg_ntn);
+  c.nt = u - mp * p.n_tiles_n;
+  const int mt = mp * 2 + rank;
+  const int r = fast_div(mt, p.mg_tx);
+  c.x0 = (mt - r * p.tiles_x) * p.BW;
+  c.img = fast_div(r, p.mg_ty);
+  c.y0 = (r - c.img * p.tiles_y) * p.BH;
+  return c;
+}
+
+constexpr int PAIR_EPI_WARPS = 16;
+constexpr int PAIR_EPI_THREADS = PAIR_EPI_WARPS * 32;
+constexpr int PAIR_THREADS = 128 + PAIR_EPI_THREADS;
+
+template <int NSTAGE_, int NEPI_, bool DGRAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
   using C = IgemmPairCfg<NSTAGE_, NEPI_>;
   constexpr int BN = C::BN;
+  constexpr int ET = PAIR_EPI_THREADS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi = smem + C::NSTAGE * C::STAGE_BYTES;
@@ -125,7 +151,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
   uint64_t* empty = full + C::NSTAGE;
   uint64_t* tfull = empty + C::NSTAGE;
   uint64_t* tempty = tfull + 2;
-  uint64_t* efull = tempty + 2;          // staging buffer written by the 256 epilogue threads
+  uint64_t* efull = tempty + 2;          // staging buffer written by the epilogue threads
   uint64_t* eempty = efull + C::NEPI;    // ... and read out by its TMA store
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty + C::NEPI);
   float* sbias = reinterpret_cast<float*>(epi + C::EPI_BYTES + 1024);
@@ -150,10 +176,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 512);    // the epilogue threads of both CTAs (only the leader's copy is used)
+      mbar_init(&tempty[i], 2 * ET);    // the epilogue threads of both CTAs (only the leader's copy is used)
     }
     for (int i = 0; i < C::NEPI; ++i) {
-      mbar_init(&efull[i], 256);
+      mbar_init(&efull[i], ET);
       mbar_init(&eempty[i], 1);
     }
     fence_barrier_init();
@@ -181,38 +207,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
     PairItem item;
     while (sched.next(item)) {
-      const int u = item.u;
-      const int nt = u % p.n_tiles_n;
-      int mt = (u / p.n_tiles_n) * 2 + (int)rank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
-      const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
-      if (p.mask != nullptr && item.kb == 0) {   // the pair that stores the unit reads the mask
+      const UnitCoord uc = decode_unit(p, item.u, (int)rank);
+      const int n0 = uc.nt * BN;
+      if (DGRAD && p.mask != nullptr && item.kb == 0) {   // the pair that stores the unit reads the mask
         if (elect_one()) {
-          for (int j = 0; j < BN / 64; ++j) tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, x0, y0, img);
+          for (int j = 0; j < BN / 64; ++j) tma_prefetch_l2_4d(&p.m_map, n0 + j * 64, uc.x0, uc.y0, uc.img);
         }
         __syncwarp();
       }
       int tap = item.kb / p.kchunks, kc = item.kb - tap * p.kchunks;
       for (int ki = item.kb; ki < item.ke; ++ki) {
         const CUtensorMap* am = &p.a_map[p.tap_map[tap]];
-        const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
-        {
-          mbar_wait(&empty[stage], phase ^ 1, 61);
-          if (elect_one()) {
-            uint8_t* sa = smem + stage * C::STAGE_BYTES;
-            uint8_t* sb = sa + C::A_BYTES;
-            if (leader) mbar_arrive_expect_tx(&full[stage], 2u * ((uint32_t)p.a_bytes + (uint32_t)C::B_BYTES));
-            tma_load_4d_2sm(sa, am, &full[stage], kc * 64, ax, ay, img);
-            tma_load_2d_2sm(sb, &p.b_map, &full[stage], (tap * p.kchunks + kc) * 64, n0 + (int)rank * 128);
-          }
-          __syncwarp();
-          if (++stage == C::NSTAGE) {
-            stage = 0;
-            phase ^= 1;
-          }
+        const int ax = uc.x0 + p.tap_dx[tap], ay = uc.y0 + p.tap_dy[tap];
+        mbar_wait(&empty[stage], phase ^ 1, 61);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2u * ((uint32_t)p.a_bytes + (uint32_t)C::B_BYTES));
+          tma_load_4d_2sm(sa, am, &full[stage], kc * 64, ax, ay, uc.img);
+          tma_load_2d_2sm(sb, &p.b_map, &full[stage], (tap * p.kchunks + kc) * 64, n0 + (int)rank * 128);
+        }
+        __syncwarp();
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
         }
         if (++kc == p.kchunks) {
           kc = 0;
@@ -255,29 +273,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------- TMA store warp (both CTAs; see igemm.cuh)
+    // ------------------------------------------------------- TMA store warp (both CTAs): chunk c of the sequence lives in
+    // staging buffer c % NEPI; up to NEPI - 1 stores are in flight, the oldest one's buffer is handed back as soon as it
+    // has been read out
     uint32_t c = 0;
     PairSched sched(pair, n_pairs, total_units, k_iters, p.stream_k != 0);
     PairItem item;
     while (sched.next(item)) {
       if (item.kb > 0) continue;      // a dumped partial: nothing to store
-      const int u = item.u;
-      const int nt = u % p.n_tiles_n;
-      int mt = (u / p.n_tiles_n) * 2 + (int)rank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
-      const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+      const UnitCoord uc = decode_unit(p, item.u, (int)rank);
+      const int n0 = uc.nt * BN;
       for (int j = 0; j < BN / 64; ++j, ++c) {
         const uint32_t b = c % C::NEPI;
         mbar_wait(&efull[b], (c / C::NEPI) & 1, 66);
         if (lane == 0) {
           const int col0 = n0 + j * 64;
-          const int mi = col0 / p.omap_div;
-          tma_store_4d(&p.o_map[mi], epi + b * 16384, col0 - mi * p.omap_div, x0, y0, img);
+          const int mi = fast_div(col0, p.mg_omap);
+          tma_store_4d(&p.o_map[mi], epi + b * 16384, col0 - mi * p.omap_div, uc.x0, uc.y0, uc.img);
           tma_store_commit();
-          // up to NEPI - 1 stores in flight: the oldest of them has read its buffer out -> hand it back
           if (c >= (uint32_t)(C::NEPI - 2)) {
             tma_store_wait_read<C::NEPI - 2>();
             mbar_arrive(&eempty[(c - (C::NEPI - 2)) % C::NEPI]);
@@ -288,19 +301,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     }
     if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
-    if (p.dbias != nullptr) named_bar_arrive(6, 288);   // the staging buffers are free: the epilogue reuses them for the sums
+    if (DGRAD && p.dbias != nullptr) named_bar_arrive(6, ET + 32);   // the staging buffers are free: the epilogue reuses them
   } else if (warp >= 4) {
     // ----------------------------------------------------------- epilogue (both CTAs, own 128 TMEM lanes)
-    const int q = warp & 3;
-    const int hw = (warp - 4) >> 2;
+    const int q = warp & 3;                 // TMEM lane quarter = row quarter of the tile
+    const int cs = (warp - 4) >> 2;         // 16-column slice of each 64-column chunk
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
-    const int by = row / p.BW, bx = row - by * p.BW;
+    const int by = fast_div(row, p.mg_bw), bx = row - by * p.BW;
     const bool row_in_box = row < p.BW * p.BH;
-    const bool mask_on = p.mask != nullptr;
-    // fused bias gradient: per-thread running column sums in registers, one per 64-column chunk of the N <= 1024 outputs
-    // (static indices only), combined across the four row quarters in fixed order at the end (deterministic)
-    const bool colsum_on = p.dbias != nullptr;
+    const bool mask_on = DGRAD && p.mask != nullptr;
+    // fused bias gradient (dgrad): per-thread running column sums in registers, one per 64-column chunk of the N <= 1024
+    // outputs (static indices only), combined across the four row quarters in fixed order at the end (deterministic)
+    const bool colsum_on = DGRAD && p.dbias != nullptr;
     float cacc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) cacc[i] = 0.0f;
@@ -310,40 +323,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
     PairItem item;
     const int lp = n_pairs - 1 - pair;      // stream-K: this pair's position in the range order = its workspace slot
     for (; sched.next(item); ++it) {
-      const int u = item.u;
-      const int nt = u % p.n_tiles_n;
-      int mt = (u / p.n_tiles_n) * 2 + (int)rank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
-      const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * BN;
+      const UnitCoord uc = decode_unit(p, item.u, (int)rank);
+      const int n0 = uc.nt * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
-        if (it > 0) named_bar_sync(1, 256);
+      if (!DGRAD && p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
+        if (it > 0) named_bar_sync(1, ET);
         if (et < BN) sbias[et] = __ldg(p.bias + (n0 + et) % p.bias_mod);
-        named_bar_sync(1, 256);
+        named_bar_sync(1, ET);
       }
       mbar_wait(&tfull[acc], acc_phase, 64);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cs * 16;
       if (item.kb > 0) {
         // stream-K: the trailing K steps of a unit another pair finishes -- dump the accumulator, raise the flag
-        float* slot = p.sk_ws + ((long long)lp * 2 + rank) * (SK_SLOT_FLOATS / 2) + row;
+        float* slot = p.sk_ws + ((long long)lp * 2 + rank) * (SK_SLOT_FLOATS / 2) + cs * 16 * 128 + row;
 #pragma unroll 1
         for (int j = 0; j < BN / 64; ++j) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + j * 64 + hw * 32, v);
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + j * 64, v);
           tmem_ld_wait();
-          float* d = slot + (j * 64 + hw * 32) * 128;
+          float* d = slot + j * 64 * 128;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) __stcg(d + i * 128, __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) __stcg(d + i * 128, __uint_as_float(v[i]));
         }
         tc_fence_before();
         mbar_arrive_leader(&tempty[acc]);
         __threadfence();
-        named_bar_sync(1, 256);
+        named_bar_sync(1, ET);
         if (et == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + lp * 2 + rank), "r"(1u) : "memory");
         continue;
       }
@@ -351,27 +358,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       if (item.ke < k_iters) {
         // ... and the leading K steps of a unit whose rest the next range's pair dumped at its very start
         if (et == 0) sk_wait_and_reset(p.sk_flags + (lp + 1) * 2 + rank);
-        named_bar_sync(1, 256);
-        partial = p.sk_ws + ((long long)(lp + 1) * 2 + rank) * (SK_SLOT_FLOATS / 2) + row;
+        named_bar_sync(1, ET);
+        partial = p.sk_ws + ((long long)(lp + 1) * 2 + rank) * (SK_SLOT_FLOATS / 2) + cs * 16 * 128 + row;
       }
-      const bool px_valid = row_in_box && img < p.n_img && (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
+      const bool px_valid = row_in_box && uc.img < p.n_img && (uc.x0 + bx) < p.out_W && (uc.y0 + by) < p.out_H;
       const __nv_bfloat16* mrow = nullptr;
       if (mask_on && px_valid)
-        mrow = p.mask + (long long)img * p.mask_sn + (long long)(y0 + by) * p.mask_sy + (long long)(x0 + bx) * p.mask_sx +
-               n0 + hw * 32;
+        mrow = p.mask + (long long)uc.img * p.mask_sn + (long long)(uc.y0 + by) * p.mask_sy +
+               (long long)(uc.x0 + bx) * p.mask_sx + n0 + cs * 16;
 #pragma unroll 1
       for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
         const uint32_t eb = chunk_ctr % C::NEPI;
         uint8_t* ebuf = epi + eb * 16384;
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_addr + j * 64, v);
+        uint4 m4[2];
+        if (DGRAD && mrow != nullptr) {     // this pixel's 16 columns of the ReLU-backward mask source (32 B)
+          m4[0] = __ldg(reinterpret_cast<const uint4*>(mrow + j * 64));
+          m4[1] = __ldg(reinterpret_cast<const uint4*>(mrow + j * 64) + 1);
+        }
         mbar_wait(&eempty[eb], ((chunk_ctr / C::NEPI) & 1) ^ 1, 65);
-        uint4 m4[4];
-        if (mrow != nullptr) load_mask(mrow + j * 64, m4);
-        float csum = 0.0f;
-        epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
-                  mrow != nullptr, m4, ebuf, row, hw, nullptr, nullptr, true, colsum_on ? &csum : nullptr, px_valid,
-                  partial != nullptr ? partial + (j * 64 + hw * 32) * 128 : nullptr);
-        if (colsum_on) {
-          const int cidx = nt * (BN / 64) + j;
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (partial != nullptr) {   // stream-K: the rest of this unit's K range, dumped as [column][128 rows]
+          const float* pp = partial + j * 64 * 128;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] += __ldcg(pp + i * 128);
+        }
+        if (!DGRAD) {
+          if (p.bias != nullptr) {
+            const float* sb = sbias + j * 64 + cs * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = lds_f4(sb + i);   // same address in every lane: broadcast
+              f[i] += b4.x;
+              f[i + 1] += b4.y;
+              f[i + 2] += b4.z;
+              f[i + 3] += b4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+        }
+        uint4 o[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          o[c].x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
+          o[c].y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+          o[c].z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
+          o[c].w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+          if (DGRAD && mask_on) {
+            // ReLU backward on packed bf16 pairs: a bf16 is > 0 exactly when its bits, read as int16, are > 0
+            if (mrow != nullptr) {
+              o[c].x &= __vcmpgts2(m4[c].x, 0u);
+              o[c].y &= __vcmpgts2(m4[c].y, 0u);
+              o[c].z &= __vcmpgts2(m4[c].z, 0u);
+              o[c].w &= __vcmpgts2(m4[c].w, 0u);
+            } else {
+              o[c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          // 128 B staging rows in the SWIZZLE_128B pattern the TMA store expects
+          sts_u4(ebuf + row * 128 + (((cs * 2 + c) ^ (row & 7)) << 4), o[c]);
+        }
+        if (DGRAD && colsum_on) {
+          // column sums of the STORED values over the warp's 32 pixel rows: recursive halving over lane bits 3..0 (15
+          // shuffles: a lane keeps one half of its columns and receives the partner's sums of that half), then the two
+          // half-warps are added -- lanes l and l ^ 16 both end with the total of column l & 15 of this slice
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint4 oc = px_valid ? o[c] : make_uint4(0u, 0u, 0u, 0u);
+            f[c * 8 + 0] = __uint_as_float(oc.x << 16); f[c * 8 + 1] = __uint_as_float(oc.x & 0xffff0000u);
+            f[c * 8 + 2] = __uint_as_float(oc.y << 16); f[c * 8 + 3] = __uint_as_float(oc.y & 0xffff0000u);
+            f[c * 8 + 4] = __uint_as_float(oc.z << 16); f[c * 8 + 5] = __uint_as_float(oc.z & 0xffff0000u);
+            f[c * 8 + 6] = __uint_as_float(oc.w << 16); f[c * 8 + 7] = __uint_as_float(oc.w & 0xffff0000u);
+          }
+#pragma unroll
+          for (int s = 8; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+              const float keep = up ? f[i + s] : f[i];
+              const float send = up ? f[i] : f[i + s];
+              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+          }
+          const float csum = f[0] + __shfl_xor_sync(0xffffffffu, f[0], 16);
+          const int cidx = uc.nt * (BN / 64) + j;
 #pragma unroll
           for (int i = 0; i < 16; ++i) cacc[i] += cidx == i ? csum : 0.0f;
         }
@@ -385,21 +462,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) igemm_pair_k
       // one row of partial sums per CTA, no atomics: wait until the store warp has drained the staging buffers, then the
       // row quarters q = 0..3 add their register sums into them one after the other; rows of CTAs that do not exist
       // (grid smaller than the row count the host planned for) are zero-filled
-      named_bar_sync(6, 288);
+      named_bar_sync(6, ET + 32);
       float* scol = reinterpret_cast<float*>(epi);
       const int N = p.n_tiles_n * BN;
       for (int qq = 0; qq < 4; ++qq) {
-        if (q == qq) {
+        if (q == qq && lane < 16) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int col = i * 64 + hw * 32 + lane;
+            const int col = i * 64 + cs * 16 + lane;
             if (col < N) scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc[i];
           }
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, ET);
       }
       const int len = N - p.dbias_c0;
-      for (int ch = p.dbias_c0 + et; ch < N; ch += 256) {
+      for (int ch = p.dbias_c0 + et; ch < N; ch += ET) {
         p.dbias[(long long)blockIdx.x * len + ch - p.dbias_c0] = scol[ch];
         for (int r = gridDim.x + blockIdx.x; r < p.dbias_rows; r += gridDim.x) p.dbias[(long long)r * len + ch - p.dbias_c0] = 0.0f;
       }

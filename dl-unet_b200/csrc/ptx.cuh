@@ -187,6 +187,21 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// n / d for n * d < 2^32 with mg = ceil(2^32 / d) precomputed on the host (mg = 0 stands for d = 1): one IMAD.HI instead of
+// the ~25 instructions of a runtime integer division
+__device__ __forceinline__ int fast_div(int n, uint32_t mg) { return mg ? (int)__umulhi((uint32_t)n, mg) : n; }
+
 // ------------------------------------------------- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC share one MMA
 // The pair's LEADER is cluster rank 0.  Shared-memory addresses of the two CTAs differ in one bit of the shared::cluster
 // window; clearing it turns "my barrier" into "the leader's barrier at the same offset".
