@@ -917,16 +917,20 @@ int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* 
       if (cout[i] < 1 || cin[i] < cout[i]) return UB_E_SHAPE;
       t[i].slab_stride = cin[i];
       t[i].lanes = 8;
+      t[i].wide = 0;
+      t[i].ptile = 32;
       utiles += (cout[i] + 31) / 32;
       continue;
     }
     const long long numel = (long long)cout[i] * cin[i] * (kind[i] == 0 ? 9 : 4);
     begin += numel;
     if ((cout[i] % 32) || (cin[i] % 32)) return UB_E_SHAPE;
-    tiles += (cout[i] / 32) * (cin[i] / 32);
+    t[i].ptile = ((cout[i] % 64) || (cin[i] % 64)) ? 32 : 64;
+    tiles += (cout[i] / t[i].ptile) * (cin[i] / t[i].ptile);
     t[i].slab_stride = numel;
     t[i].lanes = slabs[i] >= 32 ? 8 : slabs[i] >= 16 ? 4 : slabs[i] >= 8 ? 2 : 1;
-    utiles += (cout[i] / (8 / t[i].lanes)) * (cin[i] / 32);
+    t[i].wide = (kind[i] == 0 && t[i].lanes == 1 && cin[i] % 128 == 0 && cout[i] % 8 == 0) ? 1 : 0;
+    utiles += t[i].wide ? (cout[i] / 8) * (cin[i] / 128) : (cout[i] / (8 / t[i].lanes)) * (cin[i] / 32);
   }
   utile_begin_out[n_jobs] = utiles;
   return tiles;  // >= 0: total pack tile count, to be passed back as `total` of ub_pack_all
@@ -934,13 +938,19 @@ int ub_job_table_fill(void* table_host, int n_jobs, const void* const* w, void* 
 
 int ub_pack_all(const void* table_dev, int n_jobs, long long total, void* stream) {
   if (!table_dev || n_jobs <= 0) return UB_E_ARG;
-  const int grid = (int)(total < 16ll * num_sms() ? total : 16ll * num_sms());
-  pack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, (int)total);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pack_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = (int)(total < 3ll * num_sms() ? total : 3ll * num_sms());   // 74 KB of staging per CTA: three per SM
+  pack_all_kernel<<<grid, 256, PACK_SMEM_BYTES, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, (int)total);
   return (int)cudaGetLastError();
 }
 
 int ub_unpack_range(const void* table_dev, int n_jobs, int tile_lo, int tile_hi, int accumulate, void* stream) {
-  if (!table_dev || n_jobs <= 0 || tile_lo < 0 || tile_hi <= tile_lo) return UB_E_ARG;
+  if (!table_dev || n_jobs <= 0 || n_jobs > UNPACK_MAX_JOBS || tile_lo < 0 || tile_hi <= tile_lo) return UB_E_ARG;
   const long long total = tile_hi - tile_lo;
   const int grid = (int)(total < 16ll * num_sms() ? total : 16ll * num_sms());
   unpack_all_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)table_dev, n_jobs, tile_lo, tile_hi, accumulate);

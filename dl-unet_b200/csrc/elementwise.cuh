@@ -845,9 +845,11 @@ struct PackJob {
   int kind;                // 0 = 3x3 conv, 2 = 2x2 up-conv, 3 = vector of `cout` elements (partial rows -> bias gradient)
   int cout, cin;
   long long elem_begin;    // prefix sum of element counts over the jobs
-  int tile_begin;          // prefix sum of 32x32-channel tile counts (pack_all)
+  int tile_begin;          // prefix sum of pack tile counts (pack_all)
+  int ptile;               // pack tile edge in channels: 64 (both channel counts multiples of 64) or 32
   int slabs;               // split-K slabs the wgrad kernel of this layer leaves (unpack source = their sum)
   int lanes;               // 1, 2, 4 or 8 slab lanes per unpack tile (CO_T = 8 / lanes channels per tile)
+  int wide;                // 1: conv job with < 8 slabs and cin % 128 == 0 -- unpack tile = 8 channels x 128 input channels
   int utile_begin;         // prefix sum of unpack tile counts: (cout / CO_T) * (cin / 32)
   long long slab_stride;   // elements between slabs
 };
@@ -865,14 +867,74 @@ __device__ __forceinline__ int find_tile_job(const PackJob* jobs, int n_jobs, in
   return lo;
 }
 
+// 64 x 64-channel tiles staged as bf16 (pitch 578 / 258 elements): both packed operands leave in 128 B runs -- with
+// 32 x 32 fp32 tiles the runs were 64 B and the kernel reached a third of the copy bandwidth.  Layers whose channel
+// counts are not multiples of 64 (tests) keep the 32 x 32 path.
+constexpr int PACK_SMEM_BYTES = 64 * 578 * 2;
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int n_tiles) {
-  __shared__ float T[32 * 289];
+  extern __shared__ __align__(16) uint8_t pack_smem[];
+  float* T = reinterpret_cast<float*>(pack_smem);
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(pack_smem);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const PackJob jb = jobs[find_tile_job(jobs, n_jobs, tile)];
     const int lt = tile - jb.tile_begin;
     const int Cin = jb.cin, Cout = jb.cout;
     __syncthreads();
-    if (jb.kind == 0) {
+    if (jb.ptile == 64 && jb.kind == 0) {
+      const int ci_tiles = Cin >> 6;
+      const int co0 = (lt / ci_tiles) * 64, ci0 = (lt % ci_tiles) * 64;
+      for (int e = threadIdx.x; e < 64 * 144; e += 256) {      // 576 contiguous floats per co, float4 loads
+        const int co = e / 144, k4 = e - co * 144;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(jb.w + ((long long)(co0 + co) * Cin + ci0) * 9) + k4);
+        __nv_bfloat16* h = H + co * 578 + k4 * 4;
+        *reinterpret_cast<__nv_bfloat162*>(h) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(h + 2) = __floats2bfloat162_rn(v.z, v.w);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 64 * 9 * 32; e += 256) {   // forward operand [co][t][ci]: a warp writes 128 B
+        const int ci = (e & 31) * 2, r = e >> 5;
+        const int t = r % 9, co = r / 9;
+        __nv_bfloat162 v;
+        v.x = H[co * 578 + ci * 9 + t];
+        v.y = H[co * 578 + (ci + 1) * 9 + t];
+        *reinterpret_cast<__nv_bfloat162*>(jb.dst_a + ((long long)(co0 + co) * 9 + t) * Cin + ci0 + ci) = v;
+      }
+      for (int e = threadIdx.x; e < 64 * 9 * 32; e += 256) {   // dgrad operand [ci][8-t][co]
+        const int co = (e & 31) * 2, r = e >> 5;
+        const int t = r % 9, ci = r / 9;
+        __nv_bfloat162 v;
+        v.x = H[co * 578 + ci * 9 + t];
+        v.y = H[(co + 1) * 578 + ci * 9 + t];
+        *reinterpret_cast<__nv_bfloat162*>(jb.dst_b + ((long long)(ci0 + ci) * 9 + (8 - t)) * Cout + co0 + co) = v;
+      }
+    } else if (jb.ptile == 64) {
+      const int co_tiles = Cout >> 6;
+      const int ci0 = (lt / co_tiles) * 64, co0 = (lt % co_tiles) * 64;
+      for (int e = threadIdx.x; e < 64 * 64; e += 256) {       // 256 contiguous floats per ci
+        const int ci = e >> 6, k4 = e & 63;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(jb.w + ((long long)(ci0 + ci) * Cout + co0) * 4) + k4);
+        __nv_bfloat16* h = H + ci * 258 + k4 * 4;
+        *reinterpret_cast<__nv_bfloat162*>(h) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(h + 2) = __floats2bfloat162_rn(v.z, v.w);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < 4 * 64 * 32; e += 256) {   // forward operand [(ab,co)][ci]
+        const int ci = (e & 31) * 2, r = e >> 5;
+        const int co = r & 63, ab = r >> 6;
+        __nv_bfloat162 v;
+        v.x = H[ci * 258 + co * 4 + ab];
+        v.y = H[(ci + 1) * 258 + co * 4 + ab];
+        *reinterpret_cast<__nv_bfloat162*>(jb.dst_a + ((long long)ab * Cout + co0 + co) * Cin + ci0 + ci) = v;
+      }
+      for (int e = threadIdx.x; e < 64 * 4 * 32; e += 256) {   // dgrad operand [ci][(ab,co)]
+        const int co = (e & 31) * 2, r = e >> 5;
+        const int ab = r & 3, ci = r >> 2;
+        __nv_bfloat162 v;
+        v.x = H[ci * 258 + co * 4 + ab];
+        v.y = H[ci * 258 + (co + 1) * 4 + ab];
+        *reinterpret_cast<__nv_bfloat162*>(jb.dst_b + ((long long)(ci0 + ci) * 4 + ab) * Cout + co0 + co) = v;
+      }
+    } else if (jb.kind == 0) {
       const int ci_tiles = Cin >> 5;
       const int co0 = (lt / ci_tiles) * 32, ci0 = (lt % ci_tiles) * 32;
       for (int e = threadIdx.x; e < 32 * 288; e += 256) {
@@ -920,15 +982,27 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict
 // 256 threads = 32 ci x 8 rows; the 8 rows are CO_T channels x LANES slab lanes (CO_T * LANES = 8): lane l sums
 // slabs l, l + LANES, ... and the lanes are added in order, so layers with hundreds of slabs (the wide shallow
 // ones, whose K dimension is split across the whole chip) still expose enough parallel loads.
-__global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int tile_lo,
+constexpr int UNPACK_MAX_JOBS = 128;
+constexpr int UP_PITCH = 33;   // odd pitch: the transposing read of the store phase is bank-conflict free
+constexpr int UW_PITCH = 132;  // wide path: 128 input channels per row, 16-byte aligned rows
+__global__ void __launch_bounds__(256, 2) unpack_all_kernel(const PackJob* __restrict__ jobs, int n_jobs, int tile_lo,
                                                          int tile_hi, int accumulate) {
-  __shared__ float P[8 * 9 * 32];
+  __shared__ __align__(16) float P[8 * 9 * UW_PITCH];   // block path: [8 rows][9 taps][UP_PITCH]; wide path: per warp [9][UW_PITCH]
+  __shared__ int sbegin[UNPACK_MAX_JOBS];
+  for (int i = threadIdx.x; i < n_jobs && i < UNPACK_MAX_JOBS; i += 256) sbegin[i] = jobs[i].utile_begin;
+  __syncthreads();
   const int ci = threadIdx.x & 31, y = threadIdx.x >> 5;
-  for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+  const int n_tiles = tile_hi - tile_lo;
+  bool prev_shared = false;   // the previous tile was read across warps: a block barrier before P is written again
+  // Tiles of the first and of the last layers of the table (the wide shallow ones: up to 148 slabs to add per tile) are
+  // the long ones; walking the range from both ends towards the middle starts them first, and the short single-slab
+  // tiles of the deep layers fill the tail.
+  for (int k = blockIdx.x; k < n_tiles; k += gridDim.x) {
+    const int tile = (k & 1) ? tile_hi - 1 - (k >> 1) : tile_lo + (k >> 1);
     int lo = 0, hi = n_jobs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].utile_begin <= tile) lo = mid; else hi = mid - 1;
+      if (sbegin[mid] <= tile) lo = mid; else hi = mid - 1;
     }
     const PackJob jb = jobs[lo];
     const int lt = tile - jb.utile_begin;
@@ -936,6 +1010,7 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restri
     if (jb.kind == 3) {
       // vector job (bias gradients, finalconv / conv11c weights): dw[e] = sum over the `slabs` partial rows the
       // producing kernel's CTAs stored; 32 elements per tile, 8 row lanes added in order
+      prev_shared = true;
       __syncthreads();
       const int e = lt * 32 + ci;
       float v = 0.0f;
@@ -943,12 +1018,12 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restri
 #pragma unroll 4
         for (int s = y; s < jb.slabs; s += 8) v += __ldcg(jb.packed + (long long)s * jb.slab_stride + e);
       }
-      P[y * 32 + ci] = v;
+      P[y * UP_PITCH + ci] = v;
       __syncthreads();
       if (y == 0 && e < Cout) {
         float t = P[ci];
 #pragma unroll
-        for (int l = 1; l < 8; ++l) t += P[l * 32 + ci];
+        for (int l = 1; l < 8; ++l) t += P[l * UP_PITCH + ci];
         jb.dw[e] = accumulate ? jb.dw[e] + t : t;
       }
       continue;
@@ -956,40 +1031,94 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restri
     const int lanes = jb.lanes, co_t = 8 / lanes;
     const int ci_tiles = Cin >> 5;
     const int co0 = (lt / ci_tiles) * co_t, ci0 = (lt % ci_tiles) * 32;
-    const int co = co0 + y / lanes, lane = y % lanes;
     const int T = jb.kind == 0 ? 9 : 4;
-    __syncthreads();
-    // all taps of one (co, ci) at once: T independent running sums, so every pass over the slabs keeps T loads in flight
-    const long long tap_stride = jb.kind == 0 ? (long long)Cin : (long long)Cout * Cin;
-    const float* src0 = jb.packed + (jb.kind == 0 ? (long long)co * 9 * Cin : (long long)co * Cin) + ci0 + ci;
-    float v[9];
+    if (jb.wide) {
+      // Few slabs and >= 128 input channels (the deep layers: most of the bytes).  Every warp transposes one output
+      // channel x 128 input channels on its own: nine 512-byte rows in (one 16-byte load per lane and tap: whole DRAM
+      // bursts instead of scattered 128-byte pieces), 1152 contiguous floats out, through its own slice of shared
+      // memory with warp-level synchronisation only -- the eight warps of the CTA drift apart, so the SM always has
+      // warps in their load phase.
+      if (prev_shared) __syncthreads();
+      prev_shared = false;
+      const int wt = Cin >> 7;
+      const int co = (lt / wt) * 8 + y, cw0 = (lt % wt) * 128;
+      const float* s0 = jb.packed + (long long)co * 9 * Cin + cw0 + ci * 4;
+      float4 acc[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = 0.0f;
-    if (jb.kind == 0) {
-#pragma unroll 2
-      for (int s = lane; s < jb.slabs; s += lanes) {
-        const float* sp = src0 + (long long)s * jb.slab_stride;
+      for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sl = 0; sl < jb.slabs; ++sl) {
+        const float* sp = s0 + (long long)sl * jb.slab_stride;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] += __ldcg(sp + t * tap_stride);
+        for (int t = 0; t < 9; ++t) {
+          const float4 v4 = __ldcg(reinterpret_cast<const float4*>(sp + (long long)t * Cin));
+          acc[t].x += v4.x; acc[t].y += v4.y; acc[t].z += v4.z; acc[t].w += v4.w;
+        }
       }
-    } else {
-#pragma unroll 4
-      for (int s = lane; s < jb.slabs; s += lanes) {
-        const float* sp = src0 + (long long)s * jb.slab_stride;
+      float* Pw = P + y * (9 * UW_PITCH);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[t] += __ldcg(sp + t * tap_stride);
+      for (int t = 0; t < 9; ++t) *reinterpret_cast<float4*>(Pw + t * UW_PITCH + ci * 4) = acc[t];
+      __syncwarp();
+      float* d0 = jb.dw + ((long long)co * Cin + cw0) * 9;
+#pragma unroll 4
+      for (int k = ci; k < 1152; k += 32) {
+        const int i = k / 9, t = k - i * 9;
+        const float v = Pw[t * UW_PITCH + i];
+        d0[k] = accumulate ? d0[k] + v : v;
+      }
+      __syncwarp();
+      continue;
+    }
+    prev_shared = true;
+    __syncthreads();
+    // The tile's source is 8 rows (co_t channels x `lanes` slab lanes) x T taps x 32 ci = 8 T x 8 float4 per slab round;
+    // a thread owns up to three of them and reads 16 bytes per load: with 4-byte loads (one 128 B line per warp
+    // request) the kernel stalled at 2.7 TB/s on the number of requests in flight, not on bytes.
+    const int n4 = 64 * T;
+    const float* src[3];
+    int lane_of[3], prow[3];
+    float4 acc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int idx = threadIdx.x + r * 256;
+      acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      src[r] = nullptr;
+      lane_of[r] = 0;
+      prow[r] = 0;
+      if (idx < n4) {
+        const int yy = idx / (8 * T), rem = idx - yy * (8 * T);
+        const int t = rem >> 3, c4 = rem & 7;
+        const int co = co0 + yy / lanes;
+        lane_of[r] = yy % lanes;
+        prow[r] = (yy * 9 + t) * UP_PITCH + c4 * 4;
+        src[r] = jb.packed + (jb.kind == 0 ? ((long long)co * 9 + t) * Cin : ((long long)t * Cout + co) * Cin) + ci0 + c4 * 4;
+      }
+    }
+    const int rounds = (jb.slabs + lanes - 1) / lanes;
+#pragma unroll 2
+    for (int i = 0; i < rounds; ++i) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int sl = lane_of[r] + i * lanes;
+        if (src[r] != nullptr && sl < jb.slabs) {
+          const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src[r] + (long long)sl * jb.slab_stride));
+          acc[r].x += v4.x; acc[r].y += v4.y; acc[r].z += v4.z; acc[r].w += v4.w;
+        }
       }
     }
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-      if (t < T) P[(y * 9 + t) * 32 + ci] = v[t];
+    for (int r = 0; r < 3; ++r) {
+      if (src[r] != nullptr) {
+        float* pr = P + prow[r];
+        pr[0] = acc[r].x; pr[1] = acc[r].y; pr[2] = acc[r].z; pr[3] = acc[r].w;
+      }
+    }
     __syncthreads();
     if (jb.kind == 0) {
       for (int e = threadIdx.x; e < co_t * 288; e += 256) {     // torch [co][ci][t]: 288 contiguous floats per co
         const int c = e / 288, k = e - c * 288;
         const int i = k / 9, t = k - i * 9;
-        float v = P[((c * lanes) * 9 + t) * 32 + i];
-        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * 32 + i];
+        float v = P[((c * lanes) * 9 + t) * UP_PITCH + i];
+        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * UP_PITCH + i];
         float* d = jb.dw + ((long long)(co0 + c) * Cin + ci0) * 9 + k;
         *d = accumulate ? *d + v : v;
       }
@@ -997,8 +1126,8 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const PackJob* __restri
       for (int e = threadIdx.x; e < 32 * co_t * 4; e += 256) {   // torch [ci][co][ab]: co_t * 4 contiguous floats per ci
         const int i = e / (co_t * 4), k = e - i * (co_t * 4);
         const int c = k >> 2, t = k & 3;
-        float v = P[((c * lanes) * 9 + t) * 32 + i];
-        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * 32 + i];
+        float v = P[((c * lanes) * 9 + t) * UP_PITCH + i];
+        for (int l = 1; l < lanes; ++l) v += P[((c * lanes + l) * 9 + t) * UP_PITCH + i];
         float* d = jb.dw + ((long long)(ci0 + i) * Cout + co0) * 4 + k;
         *d = accumulate ? *d + v : v;
       }
