@@ -40,7 +40,6 @@ namespace {
 int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
-int g_mask_l2_prefetch = 1;
 int g_igemm_dbg = 0;
 int g_pair_rings = 0;       // CTA-pair kernel smem split: 0 auto, 1 always <5 operand stages, 4 store buffers>, 2 always <3, 8>
 int g_stream_k = 1;         // stream-K in the CTA-pair kernel: 0 off, 1 when the last wave is < 97 % full, 2 always
@@ -438,7 +437,7 @@ int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
   }
   const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm2_kernel<BN, MT, HEAD, POOL><<<grid, 384, smem_bytes, st>>>(P);
+  igemm2_kernel<BN, MT, HEAD, POOL><<<grid, igemm2_threads<HEAD, POOL>(), smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
 }
 
@@ -474,7 +473,6 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   memset(&P, 0, sizeof(P));
   P.store_out = 1;
   P.prof = g_prof_buffer;
-  P.l2_prefetch = g_mask_l2_prefetch;
   const int head_smem = head ? 3072 : 0;   // head weights + two buffers of per-row partial sums
   const int mask_smem = relu_src ? 2 * 16384 : 0;   // two slots for the ReLU-mask tiles (dgrad)
   const int col_smem = dbias ? 1024 : 0;             // column-sum accumulators (fused bias gradient)

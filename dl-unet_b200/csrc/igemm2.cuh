@@ -47,7 +47,7 @@ struct alignas(64) Igemm2Params {
   uint8_t* pool_idx;       // same shape, 1 byte per element
   __nv_bfloat16* pool_cat; // concat buffer view (dense in n, y, x) or nullptr
   int pool_C, cat_H, cat_W, cat_C, c_off;
-  int l2_prefetch;            // (unused since the mask tiles travel through shared memory)
+  int reserved0;
   int dbias_rows;             // rows of the partial-sum buffer p.dbias (>= gridDim.x)
   int aux_bytes;              // bytes between the staging buffers and the mask tile buffers (2048, or 5120 with a head)
   float* dbias;               // fused column sums of the output (bias gradient of the consuming layer) or nullptr
@@ -57,9 +57,17 @@ struct alignas(64) Igemm2Params {
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
 
+// The plain conv instantiations run SIXTEEN epilogue warps of 16 columns each (640 threads; see igemm_pair.cuh for why: the
+// per-chunk epilogue chain is latency, and conv21c forward / conv11e dgrad were epilogue bound on eight warps); the fused
+// head / pool instantiations keep eight warps of 32 columns.
+template <bool HEAD, bool POOL>
+constexpr int igemm2_threads() { return (HEAD || POOL) ? 384 : 640; }
+
 template <int BN, int MT, bool HEAD = false, bool POOL = false>
-__global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
+__global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
   constexpr int P = 8 * MT + 2;          // patch width in pixels
+  constexpr bool WIDE = !HEAD && !POOL;
+  constexpr int ET = igemm2_threads<HEAD, POOL>() - 128;   // epilogue threads
   constexpr int B_BYTES = BN * 128;
   constexpr int TMEM_COLS = 2 * MT * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "tmem");
@@ -102,9 +110,9 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], ET);
       mbar_init(&m_full[i], 1);
-      mbar_init(&m_empty[i], 256);
+      mbar_init(&m_empty[i], ET);
     }
     fence_barrier_init();
   }
@@ -298,13 +306,14 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       for (int sub = 0; sub < MT; ++sub) {
         for (int j = 0; j < BN / 64; ++j, ++c) {
           const uint32_t b = c & 1;
-          named_bar_sync(2 + b, 288);
+          named_bar_sync(2 + b, ET + 32);
           // hand the OTHER buffer back first (its store was issued a whole chunk ago and has long read it): the
-          // ~600-cycle issue of this chunk's store must not sit between the epilogue and its next buffer
+          // ~600-cycle issue of this chunk's store must not sit between the epilogue and its next buffer.  (Issuing
+          // first and waiting for the previous store only -- two stores in flight -- measured the same.)
           if (c >= 1) {
             if (elect_one()) tma_store_wait_read<0>();
             __syncwarp();
-            named_bar_arrive(4 + ((c - 1) & 1), 288);
+            named_bar_arrive(4 + ((c - 1) & 1), ET + 32);
           }
           if (elect_one()) {
             tma_store_4d(&p.o_map, epi + b * 16384, nt * BN + j * 64, (tx * MT + sub) * 8, ty * 16, img);
@@ -319,6 +328,7 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------ epilogue
     // 8 warps: warp w reads TMEM lanes 32*(w%4).. and owns the 32-column half h = (w-4)/4 of every chunk
+    // (16 warps, WIDE: the 16-column slice h = (w-4)/4 of 0..3)
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -351,9 +361,9 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       if (p.bias != nullptr && (it == 0 || p.n_tiles_n > 1)) {
-        if (it > 0) named_bar_sync(1, 256);   // every warp has finished reading the previous tile's slice
+        if (it > 0) named_bar_sync(1, ET);   // every warp has finished reading the previous tile's slice
         if (et < BN) sbias[et] = __ldg(p.bias + n0 + et);
-        named_bar_sync(1, 256);
+        named_bar_sync(1, ET);
       }
       const long long c0 = (p.prof && et == 0) ? clock64() : 0;
       mbar_wait(&tfull[acc], acc_phase, 25);
@@ -368,6 +378,52 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
           // two staging buffers; plain convs hand them to the store warp (FULL / EMPTY named barriers), the fused
           // head / pool variants keep one barrier per chunk among the epilogue warps (see igemm.cuh)
+          if constexpr (WIDE) {
+            uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
+            const long long c1 = (p.prof && et == 0) ? clock64() : 0;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + j * 64 + h * 16, v);
+            if (chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), ET + 32);   // EMPTY[b]
+            const long long c2 = (p.prof && et == 0) ? clock64() : 0;
+            uint4 mcur[2];
+            if (mask_on) {   // this chunk's mask tile: same rows / swizzle as the staging buffer
+              const uint32_t sl = chunk_ctr & 1;
+              mbar_wait(&m_full[sl], (chunk_ctr >> 1) & 1, 27);
+              const uint8_t* mrow = mbuf + sl * 16384 + row * 128;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) mcur[i] = lds_u4(mrow + (((h * 2 + i) ^ (row & 7)) << 4));
+              mbar_arrive(&m_empty[sl]);
+            }
+            tmem_ld_wait();
+            const long long c3 = (p.prof && et == 0) ? clock64() : 0;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            float csum = 0.0f;
+            if (p.bias != nullptr || p.relu)
+              epi16_finish<true>(f, p.bias != nullptr ? sbias + j * 64 + h * 16 : nullptr, p.relu, false, true, mcur, ebuf, row, h);
+            else
+              epi16_finish<false>(f, nullptr, 0, mask_on, true, mcur, ebuf, row, h, colsum_on ? &csum : nullptr, true);
+            if (colsum_on) {
+              const int cidx = nt * (BN / 64) + j;   // 64-column chunk of the output channels
+              cacc0 += cidx == 0 ? csum : 0.0f;
+              cacc1 += cidx == 1 ? csum : 0.0f;
+              cacc2 += cidx == 2 ? csum : 0.0f;
+              cacc3 += cidx == 3 ? csum : 0.0f;
+            }
+            const long long c4 = (p.prof && et == 0) ? clock64() : 0;
+            fence_proxy_async_smem();
+            named_bar_arrive(2 + (chunk_ctr & 1), ET + 32);   // FULL[b]: the store warp takes it from here
+            if (p.prof && et == 0) {
+              const long long c5 = clock64();
+              prof_acc[1] += c5 - c1;          // the whole chunk
+              prof_acc[2] += c2 - c1;          // TMEM load issue + wait for the staging buffer (EMPTY)
+              prof_acc[3] += c3 - c2;          // mask tile wait + read, TMEM load wait
+              prof_acc[4] += c4 - c3;          // arithmetic, staging stores, column sums
+              prof_acc[5] += 1;
+            }
+            continue;
+          }
           constexpr bool async_store = !HEAD && !POOL;
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
           if (async_store && chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 288);   // EMPTY[b]
@@ -489,14 +545,14 @@ __global__ void __launch_bounds__(384, 1) igemm2_kernel(const __grid_constant__ 
       // planned for (ub_set_sm_limit) do not exist, so their rows are zero-filled here
       const int N = p.n_tiles_n * BN;
       for (int qq = 0; qq < 4; ++qq) {
-        if (q == qq) {
-          const int col = h * 32 + lane;
+        if (q == qq && (!WIDE || lane < 16)) {
+          const int col = WIDE ? h * 16 + lane : h * 32 + lane;
           if (col < N) scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc0;
           if (64 + col < N) scol[64 + col] = (qq == 0 ? 0.0f : scol[64 + col]) + cacc1;
           if (128 + col < N) scol[128 + col] = (qq == 0 ? 0.0f : scol[128 + col]) + cacc2;
           if (192 + col < N) scol[192 + col] = (qq == 0 ? 0.0f : scol[192 + col]) + cacc3;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, ET);
       }
       const int ch = et, len = N - p.dbias_c0;
       if (ch < N && ch >= p.dbias_c0) {

@@ -387,67 +387,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) ige
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] += __ldcg(pp + i * 128);
         }
-        if (!DGRAD) {
-          if (p.bias != nullptr) {
-            const float* sb = sbias + j * 64 + cs * 16;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = lds_f4(sb + i);   // same address in every lane: broadcast
-              f[i] += b4.x;
-              f[i + 1] += b4.y;
-              f[i + 2] += b4.z;
-              f[i + 3] += b4.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-          }
-        }
-        uint4 o[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          o[c].x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
-          o[c].y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
-          o[c].z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
-          o[c].w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
-          if (DGRAD && mask_on) {
-            // ReLU backward on packed bf16 pairs: a bf16 is > 0 exactly when its bits, read as int16, are > 0
-            if (mrow != nullptr) {
-              o[c].x &= __vcmpgts2(m4[c].x, 0u);
-              o[c].y &= __vcmpgts2(m4[c].y, 0u);
-              o[c].z &= __vcmpgts2(m4[c].z, 0u);
-              o[c].w &= __vcmpgts2(m4[c].w, 0u);
-            } else {
-              o[c] = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-          // 128 B staging rows in the SWIZZLE_128B pattern the TMA store expects
-          sts_u4(ebuf + row * 128 + (((cs * 2 + c) ^ (row & 7)) << 4), o[c]);
-        }
+        float csum = 0.0f;
+        epi16_finish<!DGRAD>(f, (!DGRAD && p.bias != nullptr) ? sbias + j * 64 + cs * 16 : nullptr, p.relu, mask_on,
+                             mrow != nullptr, m4, ebuf, row, cs, colsum_on ? &csum : nullptr, px_valid);
         if (DGRAD && colsum_on) {
-          // column sums of the STORED values over the warp's 32 pixel rows: recursive halving over lane bits 3..0 (15
-          // shuffles: a lane keeps one half of its columns and receives the partner's sums of that half), then the two
-          // half-warps are added -- lanes l and l ^ 16 both end with the total of column l & 15 of this slice
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint4 oc = px_valid ? o[c] : make_uint4(0u, 0u, 0u, 0u);
-            f[c * 8 + 0] = __uint_as_float(oc.x << 16); f[c * 8 + 1] = __uint_as_float(oc.x & 0xffff0000u);
-            f[c * 8 + 2] = __uint_as_float(oc.y << 16); f[c * 8 + 3] = __uint_as_float(oc.y & 0xffff0000u);
-            f[c * 8 + 4] = __uint_as_float(oc.z << 16); f[c * 8 + 5] = __uint_as_float(oc.z & 0xffff0000u);
-            f[c * 8 + 6] = __uint_as_float(oc.w << 16); f[c * 8 + 7] = __uint_as_float(oc.w & 0xffff0000u);
-          }
-#pragma unroll
-          for (int s = 8; s >= 1; s >>= 1) {
-            const bool up = (lane & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-              const float keep = up ? f[i + s] : f[i];
-              const float send = up ? f[i] : f[i + s];
-              f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-            }
-          }
-          const float csum = f[0] + __shfl_xor_sync(0xffffffffu, f[0], 16);
           const int cidx = uc.nt * (BN / 64) + j;
 #pragma unroll
           for (int i = 0; i < 16; ++i) cacc[i] += cidx == i ? csum : 0.0f;

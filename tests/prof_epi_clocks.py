@@ -12,6 +12,7 @@ from b200 import lib, ops  # noqa: E402
 DEV = "cuda:0"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 buf = torch.zeros(148 * 8, dtype=torch.int64, device=DEV)
+ORDERS = (0,)
 L = lib.load()
 
 
@@ -33,13 +34,23 @@ for name, hin, cin, cout in [("conv12c", 570, 64, 64), ("conv21c", 284, 64, 128)
         else:
             part = torch.empty(ops.partial_rows(ops.PROD_DGRAD, B, hin, hin, cin, cout, 0), cin, device=DEV)
             fn = lambda: ops.conv3x3_dgrad(dy, wd, dx, x, dbias_part=part)
-        fn()
-        torch.cuda.synchronize()
-        buf.zero_()
-        L.ub_set_prof_buffer(C.c_void_p(buf.data_ptr()))
-        fn()
-        torch.cuda.synchronize()
-        L.ub_set_prof_buffer(C.c_void_p(0))
-        v = buf.view(148, 8).double()
-        n, wait, work, tot = v[:, 5].mean().item(), v[:, 0].mean().item(), v[:, 1].mean().item(), v[:, 6].mean().item()
-        print(f"{name:8s} {what:8s} | {n:9.1f} | {wait:9.0f} | {work:9.0f} | {tot:9.0f} | {100 * wait / tot:5.1f} | {100 * work / tot:5.1f} | work/chunk {work / max(n, 1):6.0f} cyc, total/chunk {tot / max(n, 1):6.0f}")
+        for order in ORDERS:
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 100
+            buf.zero_()
+            L.ub_set_prof_buffer(C.c_void_p(buf.data_ptr()))
+            fn()
+            torch.cuda.synchronize()
+            L.ub_set_prof_buffer(C.c_void_p(0))
+            v = buf.view(148, 8).double()
+            n, wait, work, tot = v[:, 5].mean().item(), v[:, 0].mean().item(), v[:, 1].mean().item(), v[:, 6].mean().item()
+            ph = [v[:, i].mean().item() / max(n, 1) for i in (2, 3, 4)]
+            print(f"{name:8s} {what:8s} order {order} {us:7.1f} us | {n:9.1f} | {wait:9.0f} | {work:9.0f} | {tot:9.0f} | {100 * wait / tot:5.1f} | {100 * work / tot:5.1f} | work/chunk {work / max(n, 1):6.0f} cyc, total/chunk {tot / max(n, 1):6.0f}"
+                  f" | per chunk: staging-buffer wait {ph[0]:5.0f}, mask + tmem wait {ph[1]:5.0f}, arithmetic + stores {ph[2]:5.0f}")
