@@ -41,6 +41,7 @@ int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_igemm_dbg = 0;
+int g_igemm2_pair = 1;      // haloed-patch kernel on CTA pairs (ub_set_option 17)
 int g_pair_rings = 0;       // CTA-pair kernel smem split: 0 auto, 1 always <5 operand stages, 4 store buffers>, 2 always <3, 8>
 int g_stream_k = 1;         // stream-K in the CTA-pair kernel: 0 off, 1 when the last wave is < 97 % full, 2 always
 int g_pair_mode = 1;        // N = 256 tiles of the tap-per-load conv kernel on CTA pairs (cta_group::2); 0: one CTA per tile
@@ -427,18 +428,41 @@ void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) 
   P.out_H = H;
 }
 
-template <int BN, int MT, bool HEAD = false, bool POOL = false>
-int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
+template <int BN, int MT, bool HEAD, bool POOL, bool PAIR>
+int launch_igemm2_tp(const Igemm2Params& P, int smem_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT, HEAD, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, MT, HEAD, POOL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const long long total = (long long)P.n_img * P.tiles_y * P.tiles_x * P.n_tiles_n;
+  const long long m_tiles = (long long)P.n_img * P.tiles_y * P.tiles_x;
+  if (PAIR) {
+    const long long units = ((m_tiles + 1) / 2) * P.n_tiles_n;
+    long long pairs = num_sms() / 2;
+    if (units < pairs) pairs = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(igemm2_threads<HEAD, POOL>());
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at = {};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, igemm2_kernel<BN, MT, HEAD, POOL, PAIR>, P);
+  }
+  const long long total = m_tiles * P.n_tiles_n;
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  igemm2_kernel<BN, MT, HEAD, POOL><<<grid, igemm2_threads<HEAD, POOL>(), smem_bytes, st>>>(P);
+  igemm2_kernel<BN, MT, HEAD, POOL, PAIR><<<grid, igemm2_threads<HEAD, POOL>(), smem_bytes, st>>>(P);
   return (int)cudaGetLastError();
+}
+template <int BN, int MT, bool HEAD = false, bool POOL = false>
+int launch_igemm2_t(const Igemm2Params& P, int smem_bytes, cudaStream_t st, bool pair) {
+  return pair ? launch_igemm2_tp<BN, MT, HEAD, POOL, true>(P, smem_bytes, st) : launch_igemm2_tp<BN, MT, HEAD, POOL, false>(P, smem_bytes, st);
 }
 
 // Haloed-patch 3x3 conv (fwd: base_off 0, dgrad: base_off -2).  Returns 1 if the shape is not eligible.
@@ -480,7 +504,8 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   const int BN = (N % 128 == 0) ? 128 : 64;
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
-  const int b_slot = BN * 128;
+  const bool pair = g_igemm2_pair != 0;                 // CTA pairs: each CTA keeps half of every weight slab
+  const int b_slot = (pair ? BN / 2 : BN) * 128;
   const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem - mask_smem - col_smem;
   const int a_slot1 = ((10 * 18 * 128 + 1023) / 1024) * 1024, a_slot2 = ((18 * 18 * 128 + 1023) / 1024) * 1024;
   const int nb_stat = 9 * P.kchunks;
@@ -521,7 +546,7 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
     if ((e = make_map4(&P.m_map, relu_src, 8, 16))) return e;
   }
   if ((e = make_map4(&P.a_map, in, 8 * MT + 2, 18))) return e;
-  if ((e = make_map2(&P.b_map, w, 9ll * K, N, BN))) return e;
+  if ((e = make_map2(&P.b_map, w, 9ll * K, N, pair ? BN / 2 : BN))) return e;
   if (head) {
     if (BN != 64 || P.n_tiles_n != 1) return UB_E_SHAPE;
     P.head_w = head->w;
@@ -547,18 +572,18 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   P.dbias_c0 = dbias_c0;
   P.dbias_rows = num_sms_physical();
   const int smem_bytes = P.n_a * P.a_slot_bytes + P.n_b * b_slot + 2 * 16384 + 2048 + 1024 + head_smem + mask_smem + col_smem;
-  if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st) : UB_E_SHAPE;
+  if (head) return (BN == 64 && MT == 1) ? launch_igemm2_t<64, 1, true>(P, smem_bytes, st, pair) : UB_E_SHAPE;
   if (pool) {
-    if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1, false, true>(P, smem_bytes, st);
-    if (BN == 64 && MT == 2) return launch_igemm2_t<64, 2, false, true>(P, smem_bytes, st);
-    if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1, false, true>(P, smem_bytes, st);
-    if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2, false, true>(P, smem_bytes, st);
+    if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1, false, true>(P, smem_bytes, st, pair);
+    if (BN == 64 && MT == 2) return launch_igemm2_t<64, 2, false, true>(P, smem_bytes, st, pair);
+    if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1, false, true>(P, smem_bytes, st, pair);
+    if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2, false, true>(P, smem_bytes, st, pair);
     return UB_E_SHAPE;
   }
-  if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st);
-  if (BN == 64 && MT == 2) return launch_igemm2_t<64, 2>(P, smem_bytes, st);
-  if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st);
-  if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st);
+  if (BN == 64 && MT == 1) return launch_igemm2_t<64, 1>(P, smem_bytes, st, pair);
+  if (BN == 64 && MT == 2) return launch_igemm2_t<64, 2>(P, smem_bytes, st, pair);
+  if (BN == 128 && MT == 1) return launch_igemm2_t<128, 1>(P, smem_bytes, st, pair);
+  if (BN == 128 && MT == 2) return launch_igemm2_t<128, 2>(P, smem_bytes, st, pair);
   return UB_E_SHAPE;
 }
 
@@ -871,6 +896,7 @@ void ub_set_option(int key, int value) {
   if (key == 11) g_pair_mode = value;
   if (key == 13) g_stream_k = value;
   if (key == 14) g_pair_rings = value;
+  if (key == 17) g_igemm2_pair = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }

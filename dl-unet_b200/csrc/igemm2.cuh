@@ -63,12 +63,19 @@ constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
 template <bool HEAD, bool POOL>
 constexpr int igemm2_threads() { return (HEAD || POOL) ? 384 : 640; }
 
-template <int BN, int MT, bool HEAD = false, bool POOL = false>
+// PAIR: the kernel runs on CTA pairs (launched with a cluster dimension of 2; tcgen05 cta_group::2, protocol as in
+// igemm_pair.cuh).  The two CTAs work on two adjacent pixel tiles with the same output columns: ONE M = 256 MMA per step
+// feeds both accumulators, each CTA keeps its own haloed patches and only HALF of every weight slab (its BN / 2 columns) in
+// shared memory.  Why: the shallow layers are bound by shared-memory bandwidth -- an M = 128, N = 128 MMA reads 4 KB of A and
+// 4 KB of B in 64 cycles, exactly the 128 B/clk of the SM, and the patch fills, staging writes and TMA-store reads come on
+// top (N = 64: 6 KB per 54.5 cycles); with half of B per CTA the operand reads drop by 25 % (N = 128) / 17 % (N = 64), and
+// the resident weights take half the space, which leaves room for deeper patch rings.
+template <int BN, int MT, bool HEAD = false, bool POOL = false, bool PAIR = false>
 __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
   constexpr int P = 8 * MT + 2;          // patch width in pixels
   constexpr bool WIDE = !HEAD && !POOL;
   constexpr int ET = igemm2_threads<HEAD, POOL>() - 128;   // epilogue threads
-  constexpr int B_BYTES = BN * 128;
+  constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;     // this CTA's part of one 64-channel weight slab
   constexpr int TMEM_COLS = 2 * MT * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "tmem");
   extern __shared__ uint8_t smem_raw[];
@@ -93,6 +100,14 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  // work units: PAIR -> (two adjacent pixel tiles, column tile), this CTA's pixel tile = 2 * pair tile + rank (may lie beyond
+  // the last one: zero-filled loads, clipped stores); else one (pixel tile, column tile) per CTA
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
+  const int total_tiles = (PAIR ? (m_tiles + 1) >> 1 : m_tiles) * p.n_tiles_n;   // units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map);
@@ -110,22 +125,27 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], ET);
+      mbar_init(&tempty[i], PAIR ? 2 * ET : ET);   // PAIR: both CTAs' epilogues arrive on the leader's copy
       mbar_init(&m_full[i], 1);
       mbar_init(&m_empty[i], ET);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // barriers of both CTAs are initialised before anyone signals across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
   const int kchunks = p.kchunks;
   const uint32_t a_bytes = (uint32_t)P * 18u * 128u;
 
@@ -134,9 +154,9 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     bool first = true;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit0; t < total_tiles; t += unit_step) {
       const int nt = t % p.n_tiles_n;
-      int mt = t / p.n_tiles_n;
+      int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -145,8 +165,13 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&a_empty[as], aph ^ 1, 20);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&a_full[as], a_bytes);
-          tma_load_4d(sA + as * p.a_slot_bytes, &p.a_map, &a_full[as], kc * 64, x0, y0, img);
+          if (PAIR) {   // both CTAs' bytes are counted on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(&a_full[as], 2u * a_bytes);
+            tma_load_4d_2sm(sA + as * p.a_slot_bytes, &p.a_map, &a_full[as], kc * 64, x0, y0, img);
+          } else {
+            mbar_arrive_expect_tx(&a_full[as], a_bytes);
+            tma_load_4d(sA + as * p.a_slot_bytes, &p.a_map, &a_full[as], kc * 64, x0, y0, img);
+          }
         }
         __syncwarp();
         if (++as == p.n_a) {
@@ -158,8 +183,13 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
             if (elect_one()) {
               for (int tap = 0; tap < 9; ++tap) {
                 const int slot = kc * 9 + tap;
-                mbar_arrive_expect_tx(&b_full[slot], (uint32_t)B_BYTES);
-                tma_load_2d(sB + slot * B_BYTES, &p.b_map, &b_full[slot], (tap * kchunks + kc) * 64, n0);
+                if (PAIR) {
+                  if (leader) mbar_arrive_expect_tx(&b_full[slot], 2u * (uint32_t)B_BYTES);
+                  tma_load_2d_2sm(sB + slot * B_BYTES, &p.b_map, &b_full[slot], (tap * kchunks + kc) * 64, n0 + rank * (BN / 2));
+                } else {
+                  mbar_arrive_expect_tx(&b_full[slot], (uint32_t)B_BYTES);
+                  tma_load_2d(sB + slot * B_BYTES, &p.b_map, &b_full[slot], (tap * kchunks + kc) * 64, n0);
+                }
               }
             }
             __syncwarp();
@@ -168,8 +198,13 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bph ^ 1, 21);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_BYTES);
-              tma_load_2d(sB + bs * B_BYTES, &p.b_map, &b_full[bs], (tap * kchunks + kc) * 64, n0);
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&b_full[bs], 2u * (uint32_t)B_BYTES);
+                tma_load_2d_2sm(sB + bs * B_BYTES, &p.b_map, &b_full[bs], (tap * kchunks + kc) * 64, n0 + rank * (BN / 2));
+              } else {
+                mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_BYTES);
+                tma_load_2d(sB + bs * B_BYTES, &p.b_map, &b_full[bs], (tap * kchunks + kc) * 64, n0);
+              }
             }
             __syncwarp();
             if (++bs == p.n_b) {
@@ -181,12 +216,12 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
       }
       first = false;
     }
-  } else if (warp == 1) {
-    // --------------------------------------------------------------- MMA issuer (warp-uniform loop)
+  } else if (warp == 1 && leader) {
+    // --------------------------------------------------------------- MMA issuer (warp-uniform loop; PAIR: leader only)
     // Issue-side cost per MMA group must stay well below the tensor time of the group (4 x 54.5 clk for
     // N = 64): descriptors are (constant high word, low word = base + immediate), the tap loop is fully
     // unrolled, and a resident (stationary) weight slab is never waited on again.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
     const uint32_t hiA = umma_desc_hi(P * 128), hiB = umma_desc_hi(1024);
     const uint32_t loA0 = umma_desc_lo(smem_u32(sA), 16), loB0 = umma_desc_lo(smem_u32(sB), 16);
     const uint32_t a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
@@ -194,7 +229,7 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     uint32_t aph = 0, bph = 0;
     int it = 0;
     bool resident = false;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = unit0; t < total_tiles; t += unit_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1, 22);
@@ -216,13 +251,22 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t aoff = (((tap / 3) * P + (tap % 3) + 8 * sub) * 128 + k * 32) >> 4;
                   const uint32_t boff = (tap * B_BYTES + k * 32) >> 4;
-                  umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + boff), idesc,
-                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  if (PAIR)
+                    umma_bf16_2sm(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + boff), idesc,
+                                  (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  else
+                    umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + boff), idesc,
+                              (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
                 }
               }
             }
-            umma_commit(&a_empty[as]);
-            if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+            if (PAIR) {
+              umma_commit_2sm(&a_empty[as]);
+              if (kc == kchunks - 1) umma_commit_2sm(&tfull[acc]);
+            } else {
+              umma_commit(&a_empty[as]);
+              if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+            }
           }
           __syncwarp();
         } else {
@@ -237,14 +281,26 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t aoff = (((tap / 3) * P + (tap % 3) + 8 * sub) * 128 + k * 32) >> 4;
-                  umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + 2 * k), idesc,
-                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  if (PAIR)
+                    umma_bf16_2sm(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + 2 * k), idesc,
+                                  (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  else
+                    umma_bf16(d0 + sub * BN, umma_desc(hiA, loA + aoff), umma_desc(hiB, loB + 2 * k), idesc,
+                              (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
                 }
               }
-              umma_commit(&b_empty[bs]);
-              if (tap == 8) {
-                umma_commit(&a_empty[as]);
-                if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+              if (PAIR) {
+                umma_commit_2sm(&b_empty[bs]);
+                if (tap == 8) {
+                  umma_commit_2sm(&a_empty[as]);
+                  if (kc == kchunks - 1) umma_commit_2sm(&tfull[acc]);
+                }
+              } else {
+                umma_commit(&b_empty[bs]);
+                if (tap == 8) {
+                  umma_commit(&a_empty[as]);
+                  if (kc == kchunks - 1) umma_commit(&tfull[acc]);
+                }
               }
             }
             __syncwarp();
@@ -268,9 +324,9 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     // cost the epilogue ~2200 cycles per chunk (32 sectors per request, L2 latency on the critical path).
     if (p.mask != nullptr) {
       uint32_t c = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += unit_step) {
         const int nt = t % p.n_tiles_n;
-        int mt = t / p.n_tiles_n;
+        int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
         const int tx = mt % p.tiles_x;
         mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
@@ -296,9 +352,9 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     // written and go on with the next chunk; this warp waits for FULL[b], issues the store, and arrives on
     // EMPTY[b'] once the store that read buffer b' has finished with it.  Named barriers 2,3 = FULL, 4,5 = EMPTY.
     uint32_t c = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit0; t < total_tiles; t += unit_step) {
       const int nt = t % p.n_tiles_n;
-      int mt = t / p.n_tiles_n;
+      int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -350,9 +406,9 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     uint32_t chunk_ctr = 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = (p.prof && et == 0) ? clock64() : 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = unit0; t < total_tiles; t += unit_step, ++it) {
       const int nt = t % p.n_tiles_n;
-      int mt = t / p.n_tiles_n;
+      int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -373,7 +429,7 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
       for (int sub = 0; sub < MT; ++sub) {
         const int x0 = (tx * MT + sub) * 8;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + sub) * BN;
-        const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H;
+        const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H && img < p.n_img;
 #pragma unroll 1
         for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
           // two staging buffers; plain convs hand them to the store warp (FULL / EMPTY named barriers), the fused
@@ -482,7 +538,7 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
             const int py = pp >> 2, pxl = pp & 3;
             const int oy = (y0 >> 1) + py, ox = (x0 >> 1) + pxl;
             const int Ho = p.out_H >> 1, Wo = p.out_W >> 1;
-            if (oy < Ho && ox < Wo) {
+            if (oy < Ho && ox < Wo && img < p.n_img) {
               const int r00 = (2 * py) * 8 + 2 * pxl;
               float v[4][8];
 #pragma unroll
@@ -536,7 +592,8 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (PAIR) mbar_arrive_leader(&tempty[acc]);
+      else mbar_arrive(&tempty[acc]);
     }
     if (et == 0 && (HEAD || POOL)) tma_store_wait_all<0>();
     if (colsum_on) {
@@ -567,10 +624,12 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA frees TMEM or exits while its partner may still signal it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

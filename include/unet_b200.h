@@ -64,7 +64,9 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  * key 13: stream-K in the CTA-pair kernel (0 = whole units round-robin, 1 = contiguous K-step ranges per pair when the idle
  *         tail of the last wave of units is worth >= 40 K steps [default], 2 = always).  Uses a library-owned 32 MB workspace per stream.
  * key 14: shared-memory split of the CTA-pair kernel (0 = by K-loop length [default], 1 = 5 operand stages + 4 output
- *         staging buffers, 2 = 3 + 8: up to 7 TMA stores in flight). */
+ *         staging buffers, 2 = 3 + 8: up to 7 TMA stores in flight).
+ * key 17: the haloed-patch kernel on CTA pairs (1 = on [default]: one M = 256 tcgen05.mma.cta_group::2 per step for two adjacent
+ *         pixel tiles, each CTA keeps half of every weight slab; 0 = one CTA per tile). */
 void ub_set_option(int key, int value);
 
 /* ---- weight packing (derived caches of the fp32 masters; network.py:23-58) ----------

@@ -1,0 +1,19 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/c39_kernels.log 2>&1
+echo "kernels rc=$?"; tail -3 gpurun_out/c39_kernels.log
+timeout 600 python tests/prof_epi_clocks.py 16 > gpurun_out/c39_clocks.log 2>&1
+echo "prof rc=$?"; grep dgrad gpurun_out/c39_clocks.log | cut -c1-60,150-400
+timeout 900 python -m pytest tests/test_gpu_network.py -x -q -m gpu > gpurun_out/c39_net.log 2>&1
+echo "net rc=$?"; tail -3 gpurun_out/c39_net.log
+for i in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 5 --no-inference --no-gpu-baseline > gpurun_out/c39_bench$i.json 2> gpurun_out/c39_bench$i.err
+echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open("gpurun_out/c39_bench$i.json"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"])
+f=d["roofline"]["families"]
+print({k:round(v["ms_per_step"],3) for k,v in f.items() if k.startswith("igemm")})
+PY
+done

@@ -12,7 +12,7 @@ from b200 import lib, ops  # noqa: E402
 DEV = "cuda:0"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 buf = torch.zeros(148 * 8, dtype=torch.int64, device=DEV)
-ORDERS = (0,)
+ORDERS = (0, 1)   # ub_set_option(17): haloed-patch kernel on one CTA per tile / on CTA pairs
 L = lib.load()
 
 
@@ -35,6 +35,7 @@ for name, hin, cin, cout in [("conv12c", 570, 64, 64), ("conv21c", 284, 64, 128)
             part = torch.empty(ops.partial_rows(ops.PROD_DGRAD, B, hin, hin, cin, cout, 0), cin, device=DEV)
             fn = lambda: ops.conv3x3_dgrad(dy, wd, dx, x, dbias_part=part)
         for order in ORDERS:
+            ops.set_option(17, order)
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,5 +53,5 @@ for name, hin, cin, cout in [("conv12c", 570, 64, 64), ("conv21c", 284, 64, 128)
             v = buf.view(148, 8).double()
             n, wait, work, tot = v[:, 5].mean().item(), v[:, 0].mean().item(), v[:, 1].mean().item(), v[:, 6].mean().item()
             ph = [v[:, i].mean().item() / max(n, 1) for i in (2, 3, 4)]
-            print(f"{name:8s} {what:8s} order {order} {us:7.1f} us | {n:9.1f} | {wait:9.0f} | {work:9.0f} | {tot:9.0f} | {100 * wait / tot:5.1f} | {100 * work / tot:5.1f} | work/chunk {work / max(n, 1):6.0f} cyc, total/chunk {tot / max(n, 1):6.0f}"
+            print(f"{name:8s} {what:8s} pairs {order} {us:7.1f} us | {n:9.1f} | {wait:9.0f} | {work:9.0f} | {tot:9.0f} | {100 * wait / tot:5.1f} | {100 * work / tot:5.1f} | work/chunk {work / max(n, 1):6.0f} cyc, total/chunk {tot / max(n, 1):6.0f}"
                   f" | per chunk: staging-buffer wait {ph[0]:5.0f}, mask + tmem wait {ph[1]:5.0f}, arithmetic + stores {ph[2]:5.0f}")

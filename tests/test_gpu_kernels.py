@@ -192,14 +192,22 @@ def test_conv3x3_dgrad_fused_bias(ops, shape):
     wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
     dy = nhwc(torch.randn(n, cout, h - 2, w - 2, device=DEV))
     wd = ops.pack_weight(wt, ops.PACK_CONV_DGRAD)
-    for mask in (nhwc(x), None):
-        ref = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
-        ops.conv3x3_dgrad(dy, wd, ref, mask)
-        dx = torch.full_like(ref, float("nan"))
-        db = torch.zeros(cin - c0, device=DEV)
-        ops.conv3x3_dgrad(dy, wd, dx, mask, db, c0)
-        assert torch.equal(dx, ref)
-        assert rel_l2(db, ref[..., c0:].float().sum((0, 1, 2))) < FP32_TOL
+    try:
+        for pairs in (1, 0):        # 0: 256-column layers stay on the haloed-patch kernel (its 4-chunk column-sum path)
+            ops.set_option(11, pairs)
+            for mask in (nhwc(x), None):
+                ref = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+                ops.conv3x3_dgrad(dy, wd, ref, mask)
+                dx = torch.full_like(ref, float("nan"))
+                db = torch.zeros(cin - c0, device=DEV)
+                ops.conv3x3_dgrad(dy, wd, dx, mask, db, c0)
+                assert torch.equal(dx, ref)
+                assert rel_l2(db, ref[..., c0:].float().sum((0, 1, 2))) < FP32_TOL
+                db2 = torch.zeros(cin - c0, device=DEV)
+                ops.conv3x3_dgrad(dy, wd, dx, mask, db2, c0)
+                assert torch.equal(db, db2)                        # fixed summation order
+    finally:
+        ops.set_option(11, 1)
 
 
 def test_conv3x3_strided_views_write_in_place(ops):
@@ -569,3 +577,51 @@ def test_igemm_pair_kernel(ops, shape):
         assert all(torch.equal(a, b) for a, b in zip(outs[(1, 2)][1:], outs[(1, 2, "again")][1:]))
     if cin % 256 == 0:
         assert rel_l2(outs[(0, 0)][2], outs[(0, 0)][1].float().sum((0, 1, 2))) < FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 20, 64, 64), (3, 27, 35, 64, 128), (2, 70, 38, 128, 64), (1, 40, 104, 128, 128),
+                                   (5, 19, 21, 256, 128), (1, 100, 100, 64, 64)])
+def test_igemm2_pair_equals_single(ops, shape):
+    """The haloed-patch kernel on CTA pairs (option 17: tcgen05 cta_group::2, two adjacent pixel tiles per M = 256 MMA,
+    half of every weight slab per CTA) against one CTA per tile: same K order, so forward (plain, fused pool, fused head)
+    and dgrad (ReLU mask + fused column sums) agree bit for bit; odd tile counts leave the last pair's second CTA on a
+    tile beyond the tensor (zero-filled loads, clipped stores, no pooled / logit writes)."""
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = nhwc(torch.randn(n, cin, h, w, device=DEV).clamp_min(0))
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device=DEV)
+    dy = nhwc(torch.randn(n, cout, h - 2, w - 2, device=DEV))
+    wf, wd = ops.pack_weight(wt, ops.PACK_CONV_FWD), ops.pack_weight(wt, ops.PACK_CONV_DGRAD)
+    hw_, hb_ = torch.randn(2, 64, device=DEV), torch.randn(2, device=DEV)
+    ho, wo = h - 2, w - 2
+    res = {}
+    ops.set_option(2, 2)          # haloed-patch kernel wherever legal (small maps too)
+    try:
+        for pair in (1, 0):
+            ops.set_option(17, pair)
+            y = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            ops.conv3x3_fwd(x, wf, b, y, relu=True)
+            dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+            db = torch.zeros(cin, device=DEV)
+            ops.conv3x3_dgrad(dy, wd, dx, x, db)
+            pooled = torch.full((n, ho // 2, wo // 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            idx = torch.full((n, ho // 2, wo // 2, cout), 9, dtype=torch.uint8, device=DEV)
+            ops.conv3x3_fwd_pool(x, wf, b, cout, None, pooled, idx, None, 0)
+            out = [y, dx, db, pooled, idx]
+            if cout == 64:
+                logits = torch.full((n, 2, ho, wo), float("nan"), device=DEV)
+                ops.conv3x3_fwd_head(x, wf, b, None, hw_, hb_, logits=logits)
+                out.append(logits)
+            res[pair] = out
+    finally:
+        ops.set_option(17, 1)
+        ops.set_option(2, 1)
+    for i, (a, c) in enumerate(zip(res[1], res[0])):
+        assert not bool(torch.isnan(a.float()).any())
+        if i == 2:      # the column sums are grouped per CTA: same values, another fp32 summation order
+            assert rel_l2(a, c) < FP32_TOL
+        else:
+            assert torch.equal(a, c)
+    ref = F.relu(F.conv2d(nchw(x), bf(wt).float(), b))
+    assert rel_l2(nchw(res[1][0]), ref) < BF16_OUT_TOL
