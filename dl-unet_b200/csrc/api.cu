@@ -504,6 +504,7 @@ int launch_igemm2(const ub_tensor4* in, const void* w, const float* bias, const 
   const int BN = (N % 128 == 0) ? 128 : 64;
   P.kchunks = K / 64;
   P.n_tiles_n = N / BN;
+  if (dbias != nullptr && P.n_tiles_n != 1) return UB_E_SHAPE;   // fused column sums: one column tile only
   const bool pair = g_igemm2_pair != 0;                 // CTA pairs: each CTA keeps half of every weight slab
   const int b_slot = (pair ? BN / 2 : BN) * 128;
   const int limit = 232448 - 1024 /*align*/ - 2048 /*barriers + bias slice*/ - 2 * 16384 /*epilogue staging*/ - head_smem - mask_smem - col_smem;
@@ -1086,8 +1087,11 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   if (!w_dgrad || !aligned16(w_dgrad)) return w_dgrad ? UB_E_ALIGN : UB_E_ARG;
   if (dx->n != dy->n || dx->h != dy->h + 2 || dx->w != dy->w + 2) return UB_E_SHAPE;
   if (igemm2_eligible(dy, dx)) {
-    *fused = dbias != nullptr;
-    return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream, nullptr, nullptr, dbias, dbias_c0);
+    // the haloed-patch kernel sums the stored columns itself when one column tile covers them (N <= 128: its per-thread
+    // running sums are one register per column of the thread's slice); else the caller runs the column-sum pass
+    *fused = dbias != nullptr && dx->c <= 128;
+    return launch_igemm2(dy, w_dgrad, nullptr, dx, 0, relu_src, -2, (cudaStream_t)stream, nullptr, nullptr, *fused ? dbias : nullptr,
+                         dbias_c0);
   }
   IgemmParams P;
   memset(&P, 0, sizeof(P));
@@ -1734,7 +1738,9 @@ int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) 
     case 2: {
       if (c <= c0 || c_dy <= 0) return UB_E_SHAPE;
       ub_tensor4 dx{nullptr, n, h, w, c, 0, 0, 0}, dy{nullptr, n, h - 2, w - 2, c_dy, 0, 0, 0};
-      if (igemm2_eligible(&dy, &dx) || igemm_runs_on_pairs(n, h, w, c)) return num_sms_physical();
+      // same choice as conv3x3_dgrad_impl: the haloed-patch kernel wins where eligible and sums N <= 128 columns itself
+      if (igemm2_eligible(&dy, &dx)) return c <= 128 ? num_sms_physical() : colsum_blocks((long long)n * h * w, c - c0);
+      if (igemm_runs_on_pairs(n, h, w, c)) return num_sms_physical();
       return colsum_blocks((long long)n * h * w, c - c0);
     }
     case 5: return igemm_runs_on_pairs(n, h, w, c) ? num_sms_physical() : colsum_blocks((long long)n * h * w, c);

@@ -129,10 +129,33 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* sbias, in
 // 32 pixel rows: recursive halving over lane bits 3..0 (15 shuffles: a lane keeps one half of its columns and receives the
 // partner's sums of that half), then the two half-warps are added -- lanes l and l ^ 16 both end with the total of column
 // l & 15 of this slice (sum_valid = false: the row is no pixel of the tensor and counts as zero).
+// run16 (instead of col_acc): the stored values are added to the thread's OWN sixteen running sums (its pixel row, its
+// 16 columns) -- no shuffles per chunk; the caller reduces them over the warp's rows once per kernel (colsum16_reduce).
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t m) {   // 0xffff per half that is > 0 (one HSET2.BF16.BM)
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&m), __floats2bfloat162_rn(0.0f, 0.0f));
+}
+
+// sums of sixteen per-thread values over the warp's 32 lanes by recursive halving: lanes l and l ^ 16 return the total
+// of f[l & 15] (15 + 1 shuffles)
+__device__ __forceinline__ float colsum16_reduce(float (&f)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? f[i + s] : f[i];
+      const float send = up ? f[i] : f[i + s];
+      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return f[0] + __shfl_xor_sync(0xffffffffu, f[0], 16);
+}
+
 template <bool FWD>
 __device__ __forceinline__ void epi16_finish(float (&f)[16], const float* sbias16, int relu, bool mask_on, bool mask_valid,
                                              const uint4 (&m4)[2], uint8_t* ebuf, int row, int cs, float* col_acc = nullptr,
-                                             bool sum_valid = true) {
+                                             bool sum_valid = true, float* run16 = nullptr) {
   if (FWD) {
     if (sbias16 != nullptr) {
 #pragma unroll
@@ -157,18 +180,28 @@ __device__ __forceinline__ void epi16_finish(float (&f)[16], const float* sbias1
     o[c].z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
     o[c].w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
     if (!FWD && mask_on) {
-      // ReLU backward on packed bf16 pairs: a bf16 is > 0 exactly when its bits, read as int16, are > 0
+      // ReLU backward on packed bf16 pairs
       if (mask_valid) {
-        o[c].x &= __vcmpgts2(m4[c].x, 0u);
-        o[c].y &= __vcmpgts2(m4[c].y, 0u);
-        o[c].z &= __vcmpgts2(m4[c].z, 0u);
-        o[c].w &= __vcmpgts2(m4[c].w, 0u);
+        o[c].x &= bf16x2_gt0_mask(m4[c].x);
+        o[c].y &= bf16x2_gt0_mask(m4[c].y);
+        o[c].z &= bf16x2_gt0_mask(m4[c].z);
+        o[c].w &= bf16x2_gt0_mask(m4[c].w);
       } else {
         o[c] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
     // 128 B staging rows in the SWIZZLE_128B pattern the TMA store expects
     sts_u4(ebuf + row * 128 + (((cs * 2 + c) ^ (row & 7)) << 4), o[c]);
+  }
+  if (!FWD && run16 != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 oc = sum_valid ? o[c] : make_uint4(0u, 0u, 0u, 0u);
+      run16[c * 8 + 0] += __uint_as_float(oc.x << 16); run16[c * 8 + 1] += __uint_as_float(oc.x & 0xffff0000u);
+      run16[c * 8 + 2] += __uint_as_float(oc.y << 16); run16[c * 8 + 3] += __uint_as_float(oc.y & 0xffff0000u);
+      run16[c * 8 + 4] += __uint_as_float(oc.z << 16); run16[c * 8 + 5] += __uint_as_float(oc.z & 0xffff0000u);
+      run16[c * 8 + 6] += __uint_as_float(oc.w << 16); run16[c * 8 + 7] += __uint_as_float(oc.w & 0xffff0000u);
+    }
   }
   if (!FWD && col_acc != nullptr) {
 #pragma unroll
@@ -179,18 +212,7 @@ __device__ __forceinline__ void epi16_finish(float (&f)[16], const float* sbias1
       f[c * 8 + 4] = __uint_as_float(oc.z << 16); f[c * 8 + 5] = __uint_as_float(oc.z & 0xffff0000u);
       f[c * 8 + 6] = __uint_as_float(oc.w << 16); f[c * 8 + 7] = __uint_as_float(oc.w & 0xffff0000u);
     }
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
-      const bool up = (lane & s) != 0;
-#pragma unroll
-      for (int i = 0; i < s; ++i) {
-        const float keep = up ? f[i + s] : f[i];
-        const float send = up ? f[i] : f[i + s];
-        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-      }
-    }
-    *col_acc = f[0] + __shfl_xor_sync(0xffffffffu, f[0], 16);
+    *col_acc = colsum16_reduce(f);
   }
 }
 

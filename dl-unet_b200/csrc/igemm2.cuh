@@ -56,12 +56,19 @@ struct alignas(64) Igemm2Params {
 };
 
 constexpr int IG2_MAX_A = 4, IG2_MAX_B = 32;
+// epilogue phase clocks (ub_set_prof_buffer, tests/prof_epi_clocks.py): compiled into the diagnostics build only -- the
+// probe sums cost the sixteen-warp epilogue 14 registers of its 96
+#ifdef UB_DIAGNOSTICS
+constexpr bool IG2_PROF = true;
+#else
+constexpr bool IG2_PROF = false;
+#endif
 
 // The plain conv instantiations run SIXTEEN epilogue warps of 16 columns each (640 threads; see igemm_pair.cuh for why: the
 // per-chunk epilogue chain is latency, and conv21c forward / conv11e dgrad were epilogue bound on eight warps); the fused
 // head / pool instantiations keep eight warps of 32 columns.
 template <bool HEAD, bool POOL>
-constexpr int igemm2_threads() { return (HEAD || POOL) ? 384 : 640; }
+constexpr int igemm2_threads() { return HEAD ? 384 : 640; }
 
 // PAIR: the kernel runs on CTA pairs (launched with a cluster dimension of 2; tcgen05 cta_group::2, protocol as in
 // igemm_pair.cuh).  The two CTAs work on two adjacent pixel tiles with the same output columns: ONE M = 256 MMA per step
@@ -74,7 +81,9 @@ template <int BN, int MT, bool HEAD = false, bool POOL = false, bool PAIR = fals
 __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kernel(const __grid_constant__ Igemm2Params p) {
   constexpr int P = 8 * MT + 2;          // patch width in pixels
   constexpr bool WIDE = !HEAD && !POOL;
-  constexpr int ET = igemm2_threads<HEAD, POOL>() - 128;   // epilogue threads
+  // epilogue threads that drain the accumulators: sixteen warps of 16 columns (plain convs) or eight warps of 32 columns
+  // (fused head; fused pool, whose warps 12..19 pool the staged chunks one step behind the drain)
+  constexpr int ET = WIDE ? 512 : 256;
   constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;     // this CTA's part of one 64-channel weight slab
   constexpr int TMEM_COLS = 2 * MT * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "tmem");
@@ -381,6 +390,81 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
     }
     if (elect_one()) tma_store_wait_all<0>();
     __syncwarp();
+  } else if (POOL && warp >= 12) {
+    // ------------------------------------------------------------------------------------ pool stage (fused pool only)
+    // Eight warps, one chunk behind the drain warps: wait for FULL[b] (named barriers 2,3; the drain warps arrive), one
+    // thread issues the TMA store of the staged conv output, all 256 pool the staged 8 x 16 pixel tile 2x2 -- thread =
+    // (pooled pixel, channel octet) -- and write pooled values, argmax codes and the skip half of the concat buffer
+    // straight to global memory; EMPTY[b] (barriers 4,5) once the tile has been pooled and read by its store.
+    const int pt = threadIdx.x - 384;
+    const int pp = pt >> 3, c8 = pt & 7;
+    const int py = pp >> 2, pxl = pp & 3;
+    const int Ho = p.out_H >> 1, Wo = p.out_W >> 1;
+    uint32_t c = 0;
+    for (int t = unit0; t < total_tiles; t += unit_step) {
+      const int nt = t % p.n_tiles_n;
+      int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int y0 = ty * 16, n0 = nt * BN;
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const int x0 = (tx * MT + sub) * 8;
+        const int oy = (y0 >> 1) + py, ox = (x0 >> 1) + pxl;
+#pragma unroll 1
+        for (int j = 0; j < BN / 64; ++j, ++c) {
+          const uint32_t b = c & 1;
+          const uint8_t* ebuf = epi + b * 16384;
+          named_bar_sync(2 + b, 512);   // FULL[b]
+          if (pt == 0 && p.store_out) {
+            tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
+            tma_store_commit();
+          }
+          if (oy < Ho && ox < Wo && img < p.n_img) {
+            const int r00 = (2 * py) * 8 + 2 * pxl;
+            float v[4][8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = r00 + (k >> 1) * 8 + (k & 1);
+              unpack8(lds_u4(ebuf + r * 128 + ((c8 ^ (r & 7)) << 4)), v[k]);
+            }
+            float m[8];
+            uint32_t code[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              m[ch] = v[0][ch];
+              code[ch] = 0;
+#pragma unroll
+              for (int k = 1; k < 4; ++k) {
+                const float tv = v[k][ch];
+                if (tv > m[ch] || tv != tv) {   // first maximum in window order, NaN wins (ATen)
+                  m[ch] = tv;
+                  code[ch] = k;
+                }
+              }
+            }
+            const uint4 o = pack8(m);
+            const int ch = n0 + j * 64 + c8 * 8;
+            const long long pix = ((long long)img * Ho + oy) * Wo + ox;
+            *reinterpret_cast<uint4*>(p.pool_y + pix * p.pool_C + ch) = o;
+            uint2 cc;
+            cc.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+            cc.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+            *reinterpret_cast<uint2*>(p.pool_idx + pix * p.pool_C + ch) = cc;
+            if (p.pool_cat != nullptr) {
+              const int cy = oy - p.c_off, cx = ox - p.c_off;
+              if (cy >= 0 && cy < p.cat_H && cx >= 0 && cx < p.cat_W)
+                *reinterpret_cast<uint4*>(p.pool_cat + (((long long)img * p.cat_H + cy) * p.cat_W + cx) * p.cat_C + ch) = o;
+            }
+          }
+          if (pt == 0 && p.store_out) tma_store_wait_read<0>();
+          named_bar_arrive(4 + b, 512);   // EMPTY[b]
+        }
+      }
+    }
+    if (pt == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------------------------ epilogue
     // 8 warps: warp w reads TMEM lanes 32*(w%4).. and owns the 32-column half h = (w-4)/4 of every chunk
@@ -398,14 +482,18 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
       if (et < 2) shead[128 + et] = __ldg(p.head_b + et);
       named_bar_sync(1, 256);
     }
-    // fused bias gradient: per-thread running column sums in registers (static indices only), one per 64-column chunk
-    // of the N <= 256 outputs; combined across the four row quarters in fixed order at the end (deterministic)
-    const bool colsum_on = p.dbias != nullptr;
-    float cacc0 = 0.0f, cacc1 = 0.0f, cacc2 = 0.0f, cacc3 = 0.0f;
+    // fused bias gradient (dgrad, sixteen-warp epilogue, one column tile: N = BN <= 128 -- the host does not ask for it
+    // otherwise): every thread keeps running sums of the values it stores, one register per column of its slice of each
+    // 64-column chunk (static indices: the chunk loop is unrolled); they are reduced over the warp's 32 pixel rows once,
+    // after the last tile, and combined across the four row quarters in fixed order (deterministic, no atomics)
+    const bool colsum_on = WIDE && p.dbias != nullptr;
+    float crun[WIDE ? (BN / 64) * 16 : 1];
+#pragma unroll
+    for (int i = 0; i < (WIDE ? (BN / 64) * 16 : 1); ++i) crun[i] = 0.0f;
     int it = 0;
     uint32_t chunk_ctr = 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
-    const long long prof_t0 = (p.prof && et == 0) ? clock64() : 0;
+    const long long prof_t0 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
     for (int t = unit0; t < total_tiles; t += unit_step, ++it) {
       const int nt = t % p.n_tiles_n;
       int mt = PAIR ? (t / p.n_tiles_n) * 2 + rank : t / p.n_tiles_n;
@@ -421,26 +509,26 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
         if (et < BN) sbias[et] = __ldg(p.bias + n0 + et);
         named_bar_sync(1, ET);
       }
-      const long long c0 = (p.prof && et == 0) ? clock64() : 0;
+      const long long c0 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
       mbar_wait(&tfull[acc], acc_phase, 25);
       tc_fence_after();
-      if (p.prof && et == 0) prof_acc[0] += clock64() - c0;
+      if (IG2_PROF && p.prof && et == 0) prof_acc[0] += clock64() - c0;
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
         const int x0 = (tx * MT + sub) * 8;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + sub) * BN;
         const bool px_valid = (x0 + bx) < p.out_W && (y0 + by) < p.out_H && img < p.n_img;
-#pragma unroll 1
-        for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
-          // two staging buffers; plain convs hand them to the store warp (FULL / EMPTY named barriers), the fused
-          // head / pool variants keep one barrier per chunk among the epilogue warps (see igemm.cuh)
-          if constexpr (WIDE) {
+        // two staging buffers; plain convs hand them to the store warp (FULL / EMPTY named barriers), the fused
+        // head / pool variants keep one barrier per chunk among the epilogue warps (see igemm.cuh)
+        if constexpr (WIDE) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {
             uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-            const long long c1 = (p.prof && et == 0) ? clock64() : 0;
+            const long long c1 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_addr + j * 64 + h * 16, v);
             if (chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), ET + 32);   // EMPTY[b]
-            const long long c2 = (p.prof && et == 0) ? clock64() : 0;
+            const long long c2 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             uint4 mcur[2];
             if (mask_on) {   // this chunk's mask tile: same rows / swizzle as the staging buffer
               const uint32_t sl = chunk_ctr & 1;
@@ -451,26 +539,18 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
               mbar_arrive(&m_empty[sl]);
             }
             tmem_ld_wait();
-            const long long c3 = (p.prof && et == 0) ? clock64() : 0;
+            const long long c3 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            float csum = 0.0f;
             if (p.bias != nullptr || p.relu)
               epi16_finish<true>(f, p.bias != nullptr ? sbias + j * 64 + h * 16 : nullptr, p.relu, false, true, mcur, ebuf, row, h);
             else
-              epi16_finish<false>(f, nullptr, 0, mask_on, true, mcur, ebuf, row, h, colsum_on ? &csum : nullptr, true);
-            if (colsum_on) {
-              const int cidx = nt * (BN / 64) + j;   // 64-column chunk of the output channels
-              cacc0 += cidx == 0 ? csum : 0.0f;
-              cacc1 += cidx == 1 ? csum : 0.0f;
-              cacc2 += cidx == 2 ? csum : 0.0f;
-              cacc3 += cidx == 3 ? csum : 0.0f;
-            }
-            const long long c4 = (p.prof && et == 0) ? clock64() : 0;
+              epi16_finish<false>(f, nullptr, 0, mask_on, true, mcur, ebuf, row, h, nullptr, true, colsum_on ? crun + j * 16 : nullptr);
+            const long long c4 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             fence_proxy_async_smem();
             named_bar_arrive(2 + (chunk_ctr & 1), ET + 32);   // FULL[b]: the store warp takes it from here
-            if (p.prof && et == 0) {
+            if (IG2_PROF && p.prof && et == 0) {
               const long long c5 = clock64();
               prof_acc[1] += c5 - c1;          // the whole chunk
               prof_acc[2] += c2 - c1;          // TMEM load issue + wait for the staging buffer (EMPTY)
@@ -478,11 +558,12 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
               prof_acc[4] += c4 - c3;          // arithmetic, staging stores, column sums
               prof_acc[5] += 1;
             }
-            continue;
           }
-          constexpr bool async_store = !HEAD && !POOL;
+        }
+#pragma unroll 1
+        for (int j = 0; !WIDE && j < BN / 64; ++j, ++chunk_ctr) {
           uint8_t* ebuf = epi + (chunk_ctr & 1) * 16384;
-          if (async_store && chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 288);   // EMPTY[b]
+          if (POOL && chunk_ctr >= 2) named_bar_sync(4 + (chunk_ctr & 1), 512);   // EMPTY[b]: pooled and read by its store
           uint4 mcur[4];
           if (mask_on) {   // this chunk's mask tile: same rows / swizzle as the staging buffer
             const uint32_t sl = chunk_ctr & 1;
@@ -493,87 +574,33 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
             mbar_arrive(&m_empty[sl]);
           }
           float2 hp = make_float2(0.0f, 0.0f);
-          const long long c1 = (p.prof && et == 0) ? clock64() : 0;
-          float csum = 0.0f;
+          const long long c1 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
           epi_chunk(t_addr + j * 64 + h * 32, p.bias != nullptr ? sbias + j * 64 + h * 32 : nullptr, p.relu, mask_on,
-                    true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL,
-                    colsum_on ? &csum : nullptr);
-          if (colsum_on) {
-            const int cidx = nt * (BN / 64) + j;   // 64-column chunk of the output channels
-            cacc0 += cidx == 0 ? csum : 0.0f;
-            cacc1 += cidx == 1 ? csum : 0.0f;
-            cacc2 += cidx == 2 ? csum : 0.0f;
-            cacc3 += cidx == 3 ? csum : 0.0f;
-          }
-          const long long c2 = (p.prof && et == 0) ? clock64() : 0;
+                    true, mcur, ebuf, row, h, head_on ? shead + h * 32 : nullptr, &hp, store_out || POOL);
+          const long long c2 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
           if (head_on && h == 1) hpart[(chunk_ctr & 1) * 128 + row] = hp;
           fence_proxy_async_smem();
-          if (async_store) {
-            named_bar_arrive(2 + (chunk_ctr & 1), 288);   // FULL[b]: the store warp takes it from here
-            if (p.prof && et == 0) {
+          if constexpr (POOL) {
+            named_bar_arrive(2 + (chunk_ctr & 1), 512);   // FULL[b]: the pool stage takes it from here
+            if (IG2_PROF && p.prof && et == 0) {
               prof_acc[1] += c2 - c1;          // TMEM load + arithmetic + staging
               prof_acc[5] += 1;
             }
           } else {
             if (et == 0 && store_out) tma_store_wait_read<0>();
-            const long long c3 = (p.prof && et == 0) ? clock64() : 0;
+            const long long c3 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             named_bar_sync(1, 256);
-            const long long c4 = (p.prof && et == 0) ? clock64() : 0;
+            const long long c4 = (IG2_PROF && p.prof && et == 0) ? clock64() : 0;
             if (et == 0 && store_out) {
               tma_store_4d(&p.o_map, ebuf, n0 + j * 64, x0, y0, img);
               tma_store_commit();
             }
-            if (p.prof && et == 0) {
+            if (IG2_PROF && p.prof && et == 0) {
               prof_acc[1] += c2 - c1;          // TMEM load + arithmetic + staging
               prof_acc[2] += c3 - c2;          // fence + wait for the previous TMA store's smem reads
               prof_acc[3] += c4 - c3;          // chunk barrier (skew between the 8 epilogue warps)
               prof_acc[4] += clock64() - c4;   // TMA store issue
               prof_acc[5] += 1;
-            }
-          }
-          if (POOL) {
-            // 2x2 max pool of the staged 8 x 16 pixel tile: thread = (pooled pixel, channel octet); the staging
-            // buffer is rewritten two chunks from now, i.e. after every reader has passed the next barrier
-            const int pp = et >> 3, c8 = et & 7;
-            const int py = pp >> 2, pxl = pp & 3;
-            const int oy = (y0 >> 1) + py, ox = (x0 >> 1) + pxl;
-            const int Ho = p.out_H >> 1, Wo = p.out_W >> 1;
-            if (oy < Ho && ox < Wo && img < p.n_img) {
-              const int r00 = (2 * py) * 8 + 2 * pxl;
-              float v[4][8];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int r = r00 + (k >> 1) * 8 + (k & 1);
-                unpack8(lds_u4(ebuf + r * 128 + ((c8 ^ (r & 7)) << 4)), v[k]);
-              }
-              float m[8];
-              uint32_t code[8];
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                m[c] = v[0][c];
-                code[c] = 0;
-#pragma unroll
-                for (int k = 1; k < 4; ++k) {
-                  const float t = v[k][c];
-                  if (t > m[c] || t != t) {   // first maximum in window order, NaN wins (ATen)
-                    m[c] = t;
-                    code[c] = k;
-                  }
-                }
-              }
-              const uint4 o = pack8(m);
-              const int ch = n0 + j * 64 + c8 * 8;
-              const long long pix = ((long long)img * Ho + oy) * Wo + ox;
-              *reinterpret_cast<uint4*>(p.pool_y + pix * p.pool_C + ch) = o;
-              uint2 cc;
-              cc.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
-              cc.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
-              *reinterpret_cast<uint2*>(p.pool_idx + pix * p.pool_C + ch) = cc;
-              if (p.pool_cat != nullptr) {
-                const int cy = oy - p.c_off, cx = ox - p.c_off;
-                if (cy >= 0 && cy < p.cat_H && cx >= 0 && cx < p.cat_W)
-                  *reinterpret_cast<uint4*>(p.pool_cat + (((long long)img * p.cat_H + cy) * p.cat_W + cx) * p.cat_C + ch) = o;
-              }
             }
           }
           if (head_on && h == 0 && px_valid) {
@@ -595,19 +622,25 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
       if (PAIR) mbar_arrive_leader(&tempty[acc]);
       else mbar_arrive(&tempty[acc]);
     }
-    if (et == 0 && (HEAD || POOL)) tma_store_wait_all<0>();
+    if (et == 0 && HEAD) tma_store_wait_all<0>();
     if (colsum_on) {
       // one flush per CTA, no atomics: the row quarters q = 0..3 add their register sums into scol one after the
       // other, then the CTA stores its row of the partial sums [dbias_rows][N - c0]; CTAs beyond the grid the host
       // planned for (ub_set_sm_limit) do not exist, so their rows are zero-filled here
-      const int N = p.n_tiles_n * BN;
+      const int N = BN;
+      float cfin[BN / 64];     // lanes l and l ^ 16: the warp's total of column h * 16 + (l & 15) of chunk j
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) {
+        float t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = crun[WIDE ? j * 16 + i : 0];
+        cfin[j] = colsum16_reduce(t);
+      }
       for (int qq = 0; qq < 4; ++qq) {
-        if (q == qq && (!WIDE || lane < 16)) {
-          const int col = WIDE ? h * 16 + lane : h * 32 + lane;
-          if (col < N) scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc0;
-          if (64 + col < N) scol[64 + col] = (qq == 0 ? 0.0f : scol[64 + col]) + cacc1;
-          if (128 + col < N) scol[128 + col] = (qq == 0 ? 0.0f : scol[128 + col]) + cacc2;
-          if (192 + col < N) scol[192 + col] = (qq == 0 ? 0.0f : scol[192 + col]) + cacc3;
+        if (q == qq && lane < 16) {
+          const int col = h * 16 + lane;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) scol[j * 64 + col] = (qq == 0 ? 0.0f : scol[j * 64 + col]) + cfin[j];
         }
         named_bar_sync(1, ET);
       }
@@ -617,7 +650,7 @@ __global__ void __launch_bounds__((igemm2_threads<HEAD, POOL>()), 1) igemm2_kern
         for (int r = gridDim.x + blockIdx.x; r < p.dbias_rows; r += gridDim.x) p.dbias[(long long)r * len + ch - p.dbias_c0] = 0.0f;
       }
     }
-    if (p.prof && et == 0) {
+    if (IG2_PROF && p.prof && et == 0) {
       for (int i = 0; i < 6; ++i) p.prof[blockIdx.x * 8 + i] = (unsigned long long)prof_acc[i];
       p.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - prof_t0);
     }

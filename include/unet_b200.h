@@ -43,7 +43,8 @@ const char* ub_error_string(int code);
 /* Non-zero after a kernel aborted on a pipeline dead-lock guard; host memory out-param. Synchronises. */
 int ub_device_error(unsigned int* out_code);
 /* experiment: device buffer of 148 x 8 uint64 that igemm2 launches fill with the clock sums of their epilogue phases
- * (wait for the MMAs, TMEM load + arithmetic + staging, store wait, chunk barrier, store issue, chunks, total); NULL = off */
+ * (wait for the MMAs, TMEM load + arithmetic + staging, store wait, chunk barrier, store issue, chunks, total); NULL = off.
+ * The probes are compiled into the diagnostics build (libunet_b200_diag.so) only; the product library accepts and ignores the buffer. */
 void ub_set_prof_buffer(void* dev_ptr);
 /* Size the persistent grids of the following launches for n_sms SMs instead of all of them (0 = all): leaves SMs free
  * for a collective that runs concurrently on another stream (data-parallel gradient all-reduce), so that neither

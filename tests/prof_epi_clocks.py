@@ -6,6 +6,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "dl-unet_b200"))
+# the clock probes live in the diagnostics build only (UB_DIAGNOSTICS); the product library ignores the buffer
+os.environ.setdefault("UB_LIB_PATH", os.path.join(ROOT, "dl-unet_b200", "csrc", "libunet_b200_diag.so"))
 import torch  # noqa: E402
 from b200 import lib, ops  # noqa: E402
 
