@@ -41,6 +41,7 @@ int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_igemm_dbg = 0;
+int g_boxes3d = 1;          // CTA-pair kernel, 3x3 convolutions: boxes that span several images (ub_set_option 18)
 int g_igemm2_pair = 1;      // haloed-patch kernel on CTA pairs (ub_set_option 17)
 int g_pair_rings = 0;       // CTA-pair kernel smem split: 0 auto, 1 always <5 operand stages, 4 store buffers>, 2 always <3, 8>
 int g_stream_k = 1;         // stream-K in the CTA-pair kernel: 0 off, 1 when the last wave is < 97 % full, 2 always
@@ -130,16 +131,16 @@ int cached_map(CUtensorMap* m, const MapKey& key, Encode encode) {
 
 // 4-D NHWC bf16 map over a (possibly strided) view: dims {c, w, h, n}, box {64, bw, bh, 1}, SWIZZLE_128B.
 int make_map4(CUtensorMap* m, void* ptr, int c, int w, int h, int n, long long sx, long long sy, long long sn,
-              int bw, int bh, int box_c = 64) {
+              int bw, int bh, int box_c = 64, int bi = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return UB_E_DRIVER;
   const MapKey key = {{(uint64_t)(uintptr_t)ptr, ((uint64_t)(uint32_t)c << 32) | (uint32_t)w, ((uint64_t)(uint32_t)h << 32) | (uint32_t)n,
                        (uint64_t)sx, (uint64_t)sy, (uint64_t)sn, ((uint64_t)(uint32_t)bw << 32) | (uint32_t)bh,
-                       (4ull << 32) | (uint32_t)box_c}};
+                       (4ull << 32) | ((uint64_t)(uint32_t)bi << 16) | (uint32_t)box_c}};
   return cached_map(m, key, [&](CUtensorMap* out) {
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
     cuuint32_t es[4] = {1, 1, 1, 1};
     // the swizzle span equals the box row: 64 channels = 128 B, 32 channels = 64 B
     const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -148,8 +149,8 @@ int make_map4(CUtensorMap* m, void* ptr, int c, int w, int h, int n, long long s
     return r == CUDA_SUCCESS ? 0 : UB_E_TENSORMAP;
   });
 }
-int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh, int box_c = 64) {
-  return make_map4(m, t->ptr, t->c, t->w, t->h, t->n, t->sx, t->sy, t->sn, bw, bh, box_c);
+int make_map4(CUtensorMap* m, const ub_tensor4* t, int bw, int bh, int box_c = 64, int bi = 1) {
+  return make_map4(m, t->ptr, t->c, t->w, t->h, t->n, t->sx, t->sy, t->sn, bw, bh, box_c, bi);
 }
 // 2-D K-major weight matrix [rows][k] bf16, box {64, box_rows}
 int make_map2(CUtensorMap* m, const void* ptr, long long k, long long rows, int box_rows) {
@@ -188,6 +189,31 @@ void pick_patch(int W, int H, int& BW, int& BH) {
         best = score;
         BW = bw;
         BH = bh;
+      }
+    }
+  }
+}
+// The same with boxes that also span BI images (CTA-pair kernel, 3x3 convolutions): BW x BH x BI <= 128 rows.  Fewest
+// tiles first, then fewer images per box (spatial locality of the nine shifted loads), then wider rows.  Small maps whose
+// sides have few divisors near 128 gain most: 28 x 28 -> 4 x 4 x 8 (128 of 128 rows) instead of 28 x 4 (112), 54 x 54 ->
+// 8 x 2 x 8 (96 %) instead of 18 x 7 (95 %), 138 x 138 -> 4 x 2 x 16 (99 %) instead of 18 x 7 (93 %).
+void pick_patch3(int W, int H, int n_img, int& BW, int& BH, int& BI) {
+  long long best = -1;
+  BW = 8;
+  BH = 16;
+  BI = 1;
+  for (int bi = 1; bi <= 16 && (bi == 1 || bi < 2 * n_img); bi *= 2) {
+    for (int bh = 1; bh * bi <= 128 && bh <= H; ++bh) {
+      const int bwmax = 128 / (bh * bi);
+      for (int bw = 1; bw <= bwmax && bw <= W; ++bw) {
+        const long long tiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((n_img + bi - 1) / bi);
+        const long long score = (tiles * 32 + bi) * 1024 - bw;
+        if (best < 0 || score < best) {
+          best = score;
+          BW = bw;
+          BH = bh;
+          BI = bi;
+        }
       }
     }
   }
@@ -299,7 +325,7 @@ static uint32_t div_magic(long long d) { return d <= 1 ? 0u : (uint32_t)((0x1000
 
 int launch_igemm_pair(const IgemmParams& P0, cudaStream_t st) {
   IgemmParams P = P0;
-  const long long m_tiles = (long long)P.n_img * P.tiles_y * P.tiles_x;
+  const long long m_tiles = (long long)P.img_tiles * P.tiles_y * P.tiles_x;
   const long long units = ((m_tiles + 1) / 2) * P.n_tiles_n;
   long long pairs = num_sms() / 2;
   if (units < pairs) pairs = units;
@@ -326,6 +352,7 @@ int launch_igemm_pair(const IgemmParams& P0, cudaStream_t st) {
   P.mg_tx = div_magic(P.tiles_x);
   P.mg_ty = div_magic(P.tiles_y);
   P.mg_bw = div_magic(P.BW);
+  P.mg_bwh = div_magic((long long)P.BW * P.BH);
   P.mg_omap = div_magic(P.omap_div);
   if (m_tiles * (long long)P.tiles_x >= (1ll << 31)) return UB_E_SHAPE;   // fast_div range
   // dgrad flavour: ReLU-backward mask and / or column sums, no bias, no ReLU; forward flavour: the opposite
@@ -416,13 +443,31 @@ int conv1_wgrad_rpb(int n, int h) {
   return rpb < 1 ? 1 : rpb;
 }
 
-void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN) {
+bool pair_mode(int BN);
+// boxes3d: the caller's tensor maps take the image extent P.BI of the box (3x3 convolutions); used only where the shape
+// runs on the CTA-pair kernel, and only if it leaves the N tile unchanged
+void fill_common(IgemmParams& P, int W, int H, int n_img, int n_total, int& BN, bool boxes3d = false) {
   pick_patch(W, H, P.BW, P.BH);
+  P.BI = 1;
+  P.img_tiles = n_img;
   P.tiles_x = (W + P.BW - 1) / P.BW;
   P.tiles_y = (H + P.BH - 1) / P.BH;
   P.n_img = n_img;
-  P.a_bytes = P.BW * P.BH * 128;
   BN = pick_bn(n_total, (long long)P.tiles_x * P.tiles_y * n_img);
+  if (boxes3d && g_boxes3d != 0 && pair_mode(BN) && g_force_bw <= 0) {
+    int bw, bh, bi;
+    pick_patch3(W, H, n_img, bw, bh, bi);
+    const long long tiles3 = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((n_img + bi - 1) / bi);
+    if (bi > 1 && tiles3 < (long long)P.tiles_x * P.tiles_y * n_img && pick_bn(n_total, tiles3) == BN) {
+      P.BW = bw;
+      P.BH = bh;
+      P.BI = bi;
+      P.img_tiles = (n_img + bi - 1) / bi;
+      P.tiles_x = (W + bw - 1) / bw;
+      P.tiles_y = (H + bh - 1) / bh;
+    }
+  }
+  P.a_bytes = P.BW * P.BH * P.BI * 128;
   P.n_tiles_n = n_total / BN;
   P.out_W = W;
   P.out_H = H;
@@ -781,7 +826,7 @@ int set_mask(IgemmParams& P, const ub_tensor4* relu_src, const ub_tensor4* dx) {
   P.mask_sn = relu_src->sn;
   P.mask_sy = relu_src->sy;
   P.mask_sx = relu_src->sx;
-  return make_map4(&P.m_map, relu_src, P.BW, P.BH);
+  return make_map4(&P.m_map, relu_src, P.BW, P.BH, 64, P.BI);
 }
 
 static long long wm_align(long long v) { return (v + 255) & ~255ll; }
@@ -898,6 +943,7 @@ void ub_set_option(int key, int value) {
   if (key == 13) g_stream_k = value;
   if (key == 14) g_pair_rings = value;
   if (key == 17) g_igemm2_pair = value;
+  if (key == 18) g_boxes3d = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }
@@ -1004,7 +1050,7 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
-  fill_common(P, y->w, y->h, y->n, y->c, BN);
+  fill_common(P, y->w, y->h, y->n, y->c, BN, true);
   P.n_taps = 9;
   P.kchunks = x->c / 64;
   for (int t = 0; t < 9; ++t) {
@@ -1012,10 +1058,10 @@ int ub_conv3x3_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, co
     P.tap_dx[t] = t % 3;
     P.tap_dy[t] = t / 3;
   }
-  if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
   if ((e = make_map2(&P.b_map, w_fwd, 9ll * x->c, y->c, b_box_rows(BN)))) return e;
-  if ((e = make_map4(&P.o_map[0], y, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.o_map[0], y, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = bias;
   P.bias_mod = y->c;
@@ -1096,7 +1142,7 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
-  fill_common(P, dx->w, dx->h, dx->n, dx->c, BN);
+  fill_common(P, dx->w, dx->h, dx->n, dx->c, BN, true);
   P.n_taps = 9;
   P.kchunks = dy->c / 64;
   for (int t = 0; t < 9; ++t) {
@@ -1104,10 +1150,10 @@ static int conv3x3_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const u
     P.tap_dx[t] = t % 3 - 2;
     P.tap_dy[t] = t / 3 - 2;
   }
-  if ((e = make_map4(&P.a_map[0], dy, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.a_map[0], dy, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
   if ((e = make_map2(&P.b_map, w_dgrad, 9ll * dy->c, dx->c, b_box_rows(BN)))) return e;
-  if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = nullptr;
   P.bias_mod = dx->c;

@@ -30,11 +30,15 @@ struct alignas(64) IgemmParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
   CUtensorMap o_map[4];
-  CUtensorMap m_map;  // ReLU-mask source view, box {64, BW, BH, 1}: L2 prefetch only
+  CUtensorMap m_map;  // ReLU-mask source view, box {64, BW, BH, BI}: L2 prefetch only
   int n_taps, kchunks;
   int tiles_x, tiles_y, n_img, n_tiles_n;
   int BW, BH;
-  int a_bytes;  // BW*BH*128: bytes one A box deposits
+  // igemm_pair_kernel, 3x3 convolutions: the box also spans BI images (BW * BH * BI <= 128 pixel rows, row = (image, y, x)),
+  // so that small maps fill the 128 MMA rows (28 x 28: 4 x 4 x 8 = 128 rows instead of 28 x 4 = 112); img_tiles =
+  // ceil(n_img / BI).  Everything else: BI = 1, img_tiles = n_img.
+  int BI, img_tiles;
+  int a_bytes;  // BW*BH*BI*128: bytes one A box deposits
   int tap_map[IG_MAX_TAPS];
   int tap_dx[IG_MAX_TAPS];
   int tap_dy[IG_MAX_TAPS];
@@ -57,7 +61,7 @@ struct alignas(64) IgemmParams {
   float* sk_ws;
   unsigned int* sk_flags;
   // igemm_pair_kernel only: fast_div magics of n_tiles_n, tiles_x, tiles_y, BW, omap_div (filled by the launcher)
-  uint32_t mg_ntn, mg_tx, mg_ty, mg_bw, mg_omap;
+  uint32_t mg_ntn, mg_tx, mg_ty, mg_bw, mg_bwh, mg_omap;   // mg_bwh: BW * BH
 };
 
 template <int BN>

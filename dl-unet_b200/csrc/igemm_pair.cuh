@@ -130,8 +130,9 @@ __device__ __forceinline__ UnitCoord decode_unit(const IgemmParams& p, int u, in
   const int mt = mp * 2 + rank;
   const int r = fast_div(mt, p.mg_tx);
   c.x0 = (mt - r * p.tiles_x) * p.BW;
-  c.img = fast_div(r, p.mg_ty);
-  c.y0 = (r - c.img * p.tiles_y) * p.BH;
+  const int it = fast_div(r, p.mg_ty);
+  c.y0 = (r - it * p.tiles_y) * p.BH;
+  c.img = it * p.BI;          // first image of the box
   return c;
 }
 
@@ -195,7 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) ige
 
   // work units: (pair of adjacent M tiles, N tile); this CTA's M tile = 2 * pair tile + rank (may lie beyond the last
   // tile: its loads are zero-filled, its stores clipped)
-  const int m_tiles = p.n_img * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.img_tiles * p.tiles_y * p.tiles_x;
   const int m_pairs = (m_tiles + 1) >> 1;
   const int total_units = m_pairs * p.n_tiles_n;
   const int k_iters = p.n_taps * p.kchunks;
@@ -308,8 +309,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) ige
     const int cs = (warp - 4) >> 2;         // 16-column slice of each 64-column chunk
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
-    const int by = fast_div(row, p.mg_bw), bx = row - by * p.BW;
-    const bool row_in_box = row < p.BW * p.BH;
+    // tile row -> (image of the box, y, x)
+    const int bi = fast_div(row, p.mg_bwh), rr = row - bi * p.BW * p.BH;
+    const int by = fast_div(rr, p.mg_bw), bx = rr - by * p.BW;
+    const bool row_in_box = row < p.BW * p.BH * p.BI;
     const bool mask_on = DGRAD && p.mask != nullptr;
     // fused bias gradient (dgrad): per-thread running column sums in registers, one per 64-column chunk of the N <= 1024
     // outputs (static indices only), combined across the four row quarters in fixed order at the end (deterministic)
@@ -361,10 +364,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) ige
         named_bar_sync(1, ET);
         partial = p.sk_ws + ((long long)(lp + 1) * 2 + rank) * (SK_SLOT_FLOATS / 2) + cs * 16 * 128 + row;
       }
-      const bool px_valid = row_in_box && uc.img < p.n_img && (uc.x0 + bx) < p.out_W && (uc.y0 + by) < p.out_H;
+      const bool px_valid = row_in_box && (uc.img + bi) < p.n_img && (uc.x0 + bx) < p.out_W && (uc.y0 + by) < p.out_H;
       const __nv_bfloat16* mrow = nullptr;
       if (mask_on && px_valid)
-        mrow = p.mask + (long long)uc.img * p.mask_sn + (long long)(uc.y0 + by) * p.mask_sy +
+        mrow = p.mask + (long long)(uc.img + bi) * p.mask_sn + (long long)(uc.y0 + by) * p.mask_sy +
                (long long)(uc.x0 + bx) * p.mask_sx + n0 + cs * 16;
 #pragma unroll 1
       for (int j = 0; j < BN / 64; ++j, ++chunk_ctr) {

@@ -66,6 +66,8 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  *         tail of the last wave of units is worth >= 40 K steps [default], 2 = always).  Uses a library-owned 32 MB workspace per stream.
  * key 14: shared-memory split of the CTA-pair kernel (0 = by K-loop length [default], 1 = 5 operand stages + 4 output
  *         staging buffers, 2 = 3 + 8: up to 7 TMA stores in flight).
+ * key 18: CTA-pair tap-per-load kernel, 3x3 convolutions: TMA boxes that also span several images so that small maps fill the
+ *         128 MMA rows (1 = on [default], 0 = boxes inside one image).
  * key 17: the haloed-patch kernel on CTA pairs (1 = on [default]: one M = 256 tcgen05.mma.cta_group::2 per step for two adjacent
  *         pixel tiles, each CTA keeps half of every weight slab; 0 = one CTA per tile). */
 void ub_set_option(int key, int value);

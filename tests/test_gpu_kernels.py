@@ -579,6 +579,44 @@ def test_igemm_pair_kernel(ops, shape):
         assert rel_l2(outs[(0, 0)][2], outs[(0, 0)][1].float().sum((0, 1, 2))) < FP32_TOL
 
 
+@pytest.mark.parametrize("shape", [(16, 30, 30, 512, 256), (5, 30, 30, 256, 256), (16, 56, 56, 256, 256), (7, 54, 54, 256, 512),
+                                   (16, 140, 140, 256, 256), (3, 32, 32, 256, 256)])
+def test_igemm_pair_image_spanning_boxes(ops, shape):
+    """CTA-pair kernel, 3x3 convolutions: TMA boxes that also span several images (option 18, default on: 28 x 28 maps
+    fill the 128 MMA rows as 4 x 4 pixels x 8 images instead of 28 x 4 pixels) against boxes inside one image: same K
+    order per output element, so forward and dgrad (ReLU mask) agree bit for bit; batch sizes that are no multiple of
+    the image extent leave part of the last box beyond the tensor (zero-filled loads, clipped stores); the fused
+    column sums group other rows per CTA (fp32 tolerance)."""
+    n, h, w, cin, cout = shape
+    torch.manual_seed(sum(shape))
+    x = nhwc(torch.randn(n, cin, h, w, device=DEV).clamp_min(0))
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device=DEV)
+    dy = nhwc(torch.randn(n, cout, h - 2, w - 2, device=DEV))
+    wf, wd = ops.pack_weight(wt, ops.PACK_CONV_FWD), ops.pack_weight(wt, ops.PACK_CONV_DGRAD)
+    res = {}
+    ops.set_tuning(bn=256)
+    try:
+        for boxes3d in (1, 0):
+            ops.set_option(18, boxes3d)
+            y = torch.full((n, h - 2, w - 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            ops.conv3x3_fwd(x, wf, b, y, relu=True)
+            dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+            db = torch.zeros(cin, device=DEV)
+            ops.conv3x3_dgrad(dy, wd, dx, x, db)
+            res[boxes3d] = (y, dx, db)
+    finally:
+        ops.set_option(18, 1)
+        ops.set_tuning()
+    for t in res[1]:
+        assert not bool(torch.isnan(t.float()).any())
+    assert torch.equal(res[1][0], res[0][0])
+    assert torch.equal(res[1][1], res[0][1])
+    assert rel_l2(res[1][2], res[0][2]) < FP32_TOL
+    assert rel_l2(nchw(res[1][0]), F.relu(F.conv2d(nchw(x), bf(wt).float(), b))) < BF16_OUT_TOL
+    assert rel_l2(res[1][2], res[1][1].float().sum((0, 1, 2))) < FP32_TOL
+
+
 @pytest.mark.parametrize("shape", [(1, 20, 20, 64, 64), (3, 27, 35, 64, 128), (2, 70, 38, 128, 64), (1, 40, 104, 128, 128),
                                    (5, 19, 21, 256, 128), (1, 100, 100, 64, 64)])
 def test_igemm2_pair_equals_single(ops, shape):
