@@ -1335,16 +1335,16 @@ int ub_upconv2x2_fwd(const ub_tensor4* x, const void* w_fwd, const float* bias, 
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
-  fill_common(P, x->w, x->h, x->n, 4 * y->c, BN);
+  fill_common(P, x->w, x->h, x->n, 4 * y->c, BN, true);
   P.n_taps = 1;
   P.kchunks = x->c / 64;
-  if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.a_map[0], x, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.a_map[i] = P.a_map[0];
   if ((e = make_map2(&P.b_map, w_fwd, x->c, 4ll * y->c, b_box_rows(BN)))) return e;
   for (int ab = 0; ab < 4; ++ab) {
     const int a = ab >> 1, b = ab & 1;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(y->ptr) + a * y->sy + b * y->sx;
-    if ((e = make_map4(&P.o_map[ab], base, y->c, x->w, x->h, x->n, 2 * y->sx, 2 * y->sy, y->sn, P.BW, P.BH))) return e;
+    if ((e = make_map4(&P.o_map[ab], base, y->c, x->w, x->h, x->n, 2 * y->sx, 2 * y->sy, y->sn, P.BW, P.BH, 64, P.BI))) return e;
   }
   P.bias = bias;
   P.bias_mod = y->c;
@@ -1363,20 +1363,20 @@ static int upconv2x2_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const
   IgemmParams P;
   memset(&P, 0, sizeof(P));
   int BN;
-  fill_common(P, dx->w, dx->h, dx->n, dx->c, BN);
+  fill_common(P, dx->w, dx->h, dx->n, dx->c, BN, true);
   P.n_taps = 4;
   P.kchunks = dy->c / 64;
   for (int ab = 0; ab < 4; ++ab) {
     const int a = ab >> 1, b = ab & 1;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(dy->ptr) + a * dy->sy + b * dy->sx;
-    if ((e = make_map4(&P.a_map[ab], base, dy->c, dx->w, dx->h, dx->n, 2 * dy->sx, 2 * dy->sy, dy->sn, P.BW, P.BH)))
+    if ((e = make_map4(&P.a_map[ab], base, dy->c, dx->w, dx->h, dx->n, 2 * dy->sx, 2 * dy->sy, dy->sn, P.BW, P.BH, 64, P.BI)))
       return e;
     P.tap_map[ab] = ab;
     P.tap_dx[ab] = 0;
     P.tap_dy[ab] = 0;
   }
   if ((e = make_map2(&P.b_map, w_dgrad, 4ll * dy->c, dx->c, b_box_rows(BN)))) return e;
-  if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH))) return e;
+  if ((e = make_map4(&P.o_map[0], dx, P.BW, P.BH, 64, P.BI))) return e;
   for (int i = 1; i < 4; ++i) P.o_map[i] = P.o_map[0];
   P.bias = nullptr;
   P.bias_mod = dx->c;

@@ -225,7 +225,7 @@ def test_conv3x3_strided_views_write_in_place(ops):
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 8, 128, 64), (2, 14, 14, 1024, 512), (1, 25, 25, 256, 128), (1, 52, 52, 512, 256),
-                                   (6, 28, 28, 1024, 512), (2, 98, 98, 128, 64)])
+                                   (6, 28, 28, 1024, 512), (2, 98, 98, 128, 64), (9, 28, 28, 512, 256), (16, 52, 52, 256, 128)])
 def test_upconv2x2(ops, shape):
     n, h, w, cin, cout = shape
     torch.manual_seed(sum(shape))
