@@ -41,6 +41,7 @@ int g_force_bn = 0, g_force_bw = 0, g_force_bh = 0, g_force_splits = 0;
 int g_igemm2_mode = 1;
 unsigned long long* g_prof_buffer = nullptr;   // experiment: epilogue phase clocks of igemm2 (ub_set_prof_buffer)
 int g_igemm_dbg = 0;
+int g_wgrad4_pack = 1;      // 64-output-channel weight gradient: nine taps in ten slots (ub_set_option 19); 0: in twelve
 int g_boxes3d = 1;          // CTA-pair kernel, 3x3 convolutions: boxes that span several images (ub_set_option 18)
 int g_igemm2_pair = 1;      // haloed-patch kernel on CTA pairs (ub_set_option 17)
 int g_pair_rings = 0;       // CTA-pair kernel smem split: 0 auto, 1 always <5 operand stages, 4 store buffers>, 2 always <3, 8>
@@ -735,8 +736,24 @@ int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
       break;
     }
   }
+  P.pack = g_wgrad4_pack != 0;
+  if (P.pack) {   // rows y in [0, H]: the one-row-shifted dY copy must also see row H-1
+    long long best1 = -1;
+    for (int kh = 8; kh >= 2; kh >>= 1) {
+      const long long padded = (long long)((dy->h + 1 + kh - 1) / kh) * kh;
+      if (best1 < 0 || padded < best1) best1 = padded;
+    }
+    for (int kh = 8; kh >= 2; kh >>= 1) {
+      const long long padded = (long long)((dy->h + 1 + kh - 1) / kh) * kh;
+      if (padded * 100 <= best1 * 106) {
+        P.KH = kh;
+        break;
+      }
+    }
+  }
+  const int gh = P.KH + (P.pack ? 1 : 0);   // rows of the dY box
   P.chunks_x = (dy->w + 1 + 15) / 16;  // x in [0, W]: the one-pixel-shifted dY copy must also see column W-1
-  P.chunks_y = (dy->h + P.KH - 1) / P.KH;
+  P.chunks_y = (dy->h + (P.pack ? 1 : 0) + P.KH - 1) / P.KH;
   P.n_img = dy->n;
   P.Cin = x->c;
   P.ci_tiles = x->c / 64;
@@ -750,11 +767,12 @@ int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
     *slabs_out = P.splits;
     return 0;
   }
-  P.nstage = Wgrad4Cfg::nstage(P.KH);
-  P.stage_bytes = Wgrad4Cfg::stage_bytes(P.KH);
-  P.g_bytes = Wgrad4Cfg::g_bytes(P.KH);
+  P.g_bytes = Wgrad4Cfg::g_bytes(gh);
+  P.stage_bytes = P.g_bytes + Wgrad4Cfg::x_bytes(P.KH);
+  P.nstage = Wgrad4Cfg::SMEM_LIMIT / P.stage_bytes;
+  if (P.nstage > Wgrad4Cfg::MAX_STAGES) P.nstage = Wgrad4Cfg::MAX_STAGES;
   int e;
-  if ((e = make_map4(&P.g_map, dy, 17, P.KH, 64))) return e;
+  if ((e = make_map4(&P.g_map, dy, 17, gh, 64))) return e;
   if ((e = make_map4(&P.x_map, x, 18, P.KH + 2, 64))) return e;
   static bool attr_set = false;
   if (!attr_set) {
@@ -762,7 +780,7 @@ int launch_wgrad4(const ub_tensor4* x, const ub_tensor4* dy, float* dw, cudaStre
     if (ce != cudaSuccess) return (int)ce;
     attr_set = true;
   }
-  wgrad4_kernel<<<(int)(P.ci_tiles * P.splits), 256, Wgrad4Cfg::smem_bytes(P.KH), st>>>(P);
+  wgrad4_kernel<<<(int)(P.ci_tiles * P.splits), 256, P.nstage * P.stage_bytes + Wgrad4Cfg::BAR_BYTES + 1024, st>>>(P);
   return (int)cudaGetLastError();
 }
 
@@ -944,6 +962,7 @@ void ub_set_option(int key, int value) {
   if (key == 14) g_pair_rings = value;
   if (key == 17) g_igemm2_pair = value;
   if (key == 18) g_boxes3d = value;
+  if (key == 19) g_wgrad4_pack = value;
 }
 
 void ub_set_sm_limit(int n_sms) { g_sm_limit = n_sms; }

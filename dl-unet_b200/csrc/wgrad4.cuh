@@ -14,6 +14,15 @@
 // The dY box is 17 pixels wide and starts at x0-1 (out-of-bounds = zero), the X patch is 18 x (KH+2);
 // chunks cover x in [0, W] so that the shifted copy also sees the last column.  One CTA owns a
 // 64-channel ci tile and all nine taps (three accumulators of 128 columns), split-K over pixel chunks.
+//
+// p.pack (round 2, default): nine taps in TEN slots instead of twelve.  The dY box gets one more row on top (17 x (KH+1)
+// pixels from (x0-1, y0-1)), so the second half of M can also be a ONE-ROW-shifted copy, and per 16-pixel K step
+//   MMA 1 (N = 192): A = [dY(y, x-1), dY(y, x)] (LBO one pixel),    B = [X(y, x), X(y+1, x), X(y+2, x)] (LBO one patch row)
+//                    -> taps (rb, 1) from block 0 and (rb, 0) from block 1, rb = 0..2: six taps, no waste
+//   MMA 2 (N = 128): A = [dY(y-1, x), dY(y, x)] (LBO one box row), B = [X(y, x+2), X(y+2, x+2)]    (LBO two patch rows)
+//                    -> taps (0, 2), (2, 2) from block 1, (1, 2) and a discarded (3, 2) from block 0
+// 96 + 64 = 160 tensor cycles per K step against 3 x 64 = 192; chunks also cover y in [0, H] so that the row-shifted copy
+// sees the last row.
 #pragma once
 #include "ptx.cuh"
 
@@ -28,6 +37,7 @@ struct alignas(64) Wgrad4Params {
   int Cin;
   int nstage, stage_bytes, g_bytes;
   int per;                // pixel chunks per split (no split is empty)
+  int pack;               // 1: ten-slot tap packing (dY box has KH+1 rows and starts at y0-1)
   float* dw;              // slabs [splits][Cout][9][Cin] fp32: split s STORES its partial sums into slab s (deterministic;
                           // the slabs are summed in fixed order by the unpack kernel)
   long long slab_stride;  // elements between slabs
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
 
   if (n_iters > 0) {
     if (warp == 0) {
-      const uint32_t tx_bytes = 17u * KH * 128u + 18u * (KH + 2) * 128u;
+      const uint32_t tx_bytes = 17u * (KH + (p.pack ? 1 : 0)) * 128u + 18u * (KH + 2) * 128u;
       int stage = 0;
       uint32_t phase = 0;
       for (int c = c_begin; c < c_end; ++c) {
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
         if (elect_one()) {
           uint8_t* sg = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          tma_load_4d(sg, &p.g_map, &full[stage], 0, x0 - 1, y0, img);
+          tma_load_4d(sg, &p.g_map, &full[stage], 0, x0 - 1, p.pack ? y0 - 1 : y0, img);
           tma_load_4d(sg + G_BYTES, &p.x_map, &full[stage], ct * 64, x0, y0, img);
         }
         __syncwarp();
@@ -126,7 +136,28 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
       for (int i = 0; i < n_iters; ++i) {
         mbar_wait(&full[stage], phase, 41);
         tc_fence_after();
-        if (elect_one()) {
+        if (p.pack) {
+          if (elect_one()) {
+            constexpr uint32_t idesc192 = umma_idesc_bf16(128, 192, 1, 1);
+            const uint32_t so = stage * stage16;
+            // box row 0 is dY row y0-1: the chunk's own rows start one box row (17 pixels) further down
+            uint32_t loAx = umma_desc_lo(smem_u32(smem) + 17 * 128, 128) + so;          // [dY(y, x-1), dY(y, x)]
+            uint32_t loAy = umma_desc_lo(smem_u32(smem) + 128, 17 * 128) + so;          // [dY(y-1, x), dY(y, x)]
+            uint32_t loB3 = umma_desc_lo(smem_u32(smem) + G_BYTES, 18 * 128) + so;      // X(y + rb, x), rb = 0..2
+            uint32_t loB2 = umma_desc_lo(smem_u32(smem) + G_BYTES + 256, 36 * 128) + so;  // X(y, x+2), X(y+2, x+2)
+            for (int y = 0; y < KH; ++y) {
+              const uint32_t acc = (i > 0 || y > 0) ? 1u : 0u;
+              umma_bf16(tmem_base, umma_desc(hiD, loAx), umma_desc(hiD, loB3), idesc192, acc);
+              umma_bf16(tmem_base + 192, umma_desc(hiD, loAy), umma_desc(hiD, loB2), idesc, acc);
+              loAx += 136;
+              loAy += 136;
+              loB3 += 144;
+              loB2 += 144;
+            }
+            umma_commit(&empty[stage]);
+            if (i == n_iters - 1) umma_commit(tfull);
+          }
+        } else if (elect_one()) {
           uint32_t loA = loA0 + stage * stage16, loB = loB0 + stage * stage16;
           for (int y = 0; y < KH; ++y) {
             const uint32_t acc = (i > 0 || y > 0) ? 1u : 0u;
@@ -152,8 +183,32 @@ __global__ void __launch_bounds__(256, 1) wgrad4_kernel(const __grid_constant__ 
       mbar_wait(tfull, 0, 42);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (p.pack) {
+        // accumulator 1 (columns 0..191): block rb of 64 ci -> tap (rb, blk ? 0 : 1); accumulator 2 (192..319): block b ->
+        // tap (2b, 2) for blk 1, (2b + 1, 2) for blk 0 (b = 1: discarded)
 #pragma unroll 1
-      for (int r = 0; r < 3; ++r) {
+        for (int cb = 0; cb < 5; ++cb) {
+          const int r = cb < 3 ? cb : (blk ? 2 * (cb - 3) : 2 * (cb - 3) + 1);
+          const int s = cb < 3 ? (blk ? 0 : 1) : 2;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_addr + cb * 64 + hh * 32, v);
+            tmem_ld_wait();
+            if (r < 3) {
+              float* drow = p.dw + (long long)split * p.slab_stride + ((long long)co * 9 + r * 3 + s) * p.Cin + ct * 64 + hh * 32;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 a = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                       __uint_as_float(v[i + 3]));
+                __stcg(reinterpret_cast<float4*>(drow + i), a);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll 1
+      for (int r = 0; r < (p.pack ? 0 : 3); ++r) {
 #pragma unroll 1
         for (int sb = 0; sb < 2; ++sb) {
           const int s = blk ? 2 * sb : 1 + 2 * sb;  // blk 1: taps 0, 2;  blk 0: taps 1, (3)

@@ -68,6 +68,8 @@ void ub_set_tuning(int force_bn, int force_bw, int force_bh, int force_splits);
  *         staging buffers, 2 = 3 + 8: up to 7 TMA stores in flight).
  * key 18: CTA-pair tap-per-load kernel, 3x3 convolutions: TMA boxes that also span several images so that small maps fill the
  *         128 MMA rows (1 = on [default], 0 = boxes inside one image).
+ * key 19: weight gradient of the layers with 64 output channels: nine taps in ten accumulator slots (N = 192 + N = 128 per K
+ *         step, one-pixel- and one-row-shifted dY copies; 1 = on [default]) or in twelve (three N = 128 steps; 0).
  * key 17: the haloed-patch kernel on CTA pairs (1 = on [default]: one M = 256 tcgen05.mma.cta_group::2 per step for two adjacent
  *         pixel tiles, each CTA keeps half of every weight slab; 0 = one CTA per tile). */
 void ub_set_option(int key, int value);

@@ -179,6 +179,38 @@ def test_conv3x3_fwd_fused_pool(ops, case):
     assert torch.equal(outs[1][1], pooled) and torch.equal(outs[1][2], idx) and torch.equal(outs[1][3], cat)
 
 
+@pytest.mark.parametrize("shape", [(1, 20, 20, 64), (2, 35, 51, 128), (3, 18, 19, 64), (1, 66, 34, 128), (4, 11, 83, 64), (2, 102, 100, 64)])
+def test_wgrad_64_output_channels_tap_packing(ops, shape):
+    """wgrad4.cuh (Cout = 64: conv12c, conv11e, conv12e): nine taps in ten accumulator slots (option 19, default: an
+    N = 192 step with a one-pixel-shifted dY copy + an N = 128 step with a one-row-shifted copy) and in twelve (three
+    N = 128 steps), both against fp32 autograd; ragged widths / heights exercise the extra chunk row and column the
+    shifted copies need, NaN-filled slabs must come back fully overwritten, two runs agree bit for bit."""
+    n, h, w, cin = shape
+    cout = 64
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=DEV).clamp_min(0)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV)
+    dy = torch.randn(n, cout, h - 2, w - 2, device=DEV)
+    xq, wq = bf(x).float(), bf(wt).float().requires_grad_(True)
+    (gw,) = torch.autograd.grad(F.conv2d(xq, wq), wq, bf(dy).float())
+    res = {}
+    try:
+        for pack in (1, 0):
+            ops.set_option(19, pack)
+            dwp = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
+            ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp)
+            dw = torch.empty_like(wt)
+            ops.unpack_grad(dwp, dw, ops.PACK_CONV_FWD)
+            assert rel_l2(dw, gw) < FP32_TOL, pack
+            dwp2 = ops.wgrad_workspace(ops.PACK_CONV_FWD, nhwc(x), cout, fill=float("nan"))
+            ops.conv3x3_wgrad(nhwc(x), nhwc(dy), dwp2)
+            assert torch.equal(dwp, dwp2)
+            res[pack] = dw
+    finally:
+        ops.set_option(19, 1)
+    assert rel_l2(res[1], res[0]) < FP32_TOL
+
+
 @pytest.mark.parametrize("shape", [(2, 20, 20, 64, 64, 0), (1, 70, 70, 64, 128, 64), (2, 33, 41, 128, 128, 0), (1, 12, 12, 256, 512, 0),
                                    (1, 104, 104, 256, 256, 0), (2, 30, 30, 512, 1024, 0), (2, 58, 58, 256, 512, 256),
                                    (3, 17, 23, 1024, 512, 0)])
