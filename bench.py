@@ -468,7 +468,9 @@ def main():
             "config": dict(workload_config(per_gpu, global_batch, world),
                            l2="working set per step (>5 GB of activations) is far larger than the 126 MB L2; no flush needed",
                            timing="CUDA events on the launch stream, barrier+synchronize both sides, max over ranks",
-                           step_api="b200.train.TrainStep" + (" (CUDA-graph replay)" if world == 1 else " (eager schedule + bucketed all-reduce)"),
+                           step_api="b200.train.TrainStep" + (" (CUDA-graph replay)" if world == 1 else
+                                                             " (CUDA-graph replay incl. the gradient all-reduce)" if dp_graph else
+                                                             " (eager schedule + gradient all-reduce)"),
                            roofline_timing="per-launch CUDA events over a second pass of the same K steps issued eagerly"),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": ke,
                     "step_ms_min_median_max": [e2e_step_ms[0], e2e_step_ms[len(e2e_step_ms) // 2], e2e_step_ms[-1]]},
