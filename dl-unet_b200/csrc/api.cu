@@ -1197,6 +1197,15 @@ static bool igemm_runs_on_pairs(int n, int h, int w, int c_out_total) {
   return pair_mode(BN) && c_out_total <= 1024;
 }
 
+// does the up-convolution dgrad of this output shape sum its columns itself (same rule as upconv2x2_dgrad_impl)?
+static bool upconv_dgrad_sums_fused(int n, int h, int w, int c) {
+  IgemmParams P;
+  memset(&P, 0, sizeof(P));
+  int BN;
+  fill_common(P, w, h, n, c, BN, true);
+  return (pair_mode(BN) && c <= 1024) || (!pair_mode(BN) && P.n_tiles_n == 1);
+}
+
 int ub_colsum(const void* g, float* part, long long n_pix, int c, long long ld, void* stream);
 
 int ub_conv3x3_dgrad(const ub_tensor4* dy, const void* w_dgrad, const ub_tensor4* dx, const ub_tensor4* relu_src,
@@ -1402,7 +1411,8 @@ static int upconv2x2_dgrad_impl(const ub_tensor4* dy, const void* w_dgrad, const
   P.relu = 0;
   P.omap_div = 1 << 30;
   if ((e = set_mask(P, relu_src, dx))) return e;
-  if (dbias != nullptr && pair_mode(BN) && dx->c <= 1024) {
+  // the CTA-pair kernel sums the stored columns itself (N <= 1024), the one-CTA kernel when one column tile covers them
+  if (dbias != nullptr && ((pair_mode(BN) && dx->c <= 1024) || (!pair_mode(BN) && P.n_tiles_n == 1))) {
     P.dbias = dbias;
     P.dbias_c0 = 0;
     P.dbias_rows = num_sms_physical();
@@ -1808,7 +1818,7 @@ int ub_partial_rows(int producer, int n, int h, int w, int c, int c_dy, int c0) 
       if (igemm_runs_on_pairs(n, h, w, c)) return num_sms_physical();
       return colsum_blocks((long long)n * h * w, c - c0);
     }
-    case 5: return igemm_runs_on_pairs(n, h, w, c) ? num_sms_physical() : colsum_blocks((long long)n * h * w, c);
+    case 5: return upconv_dgrad_sums_fused(n, h, w, c) ? num_sms_physical() : colsum_blocks((long long)n * h * w, c);
     case 3: return head_bwd_blocks((long long)n * h * w);
     case 4: {
       if (g_conv1_wgrad_tc) {

@@ -51,7 +51,7 @@ struct alignas(64) IgemmParams {
   int out_W, out_H;                     // valid output extent (for the mask read predicate)
   int omap_div;                         // column c -> o_map[c / omap_div], channel coord c % omap_div
   int dbg;                              // experiment switch (ub_set_option 5): 1 = do not wait for earlier TMA stores
-  // igemm_pair_kernel only: fused column sums of the stored output (bias gradient of the layer that produced the input of
+  // fused column sums of the stored output (igemm_pair_kernel; igemm_kernel with one column tile) (bias gradient of the layer that produced the input of
   // this dgrad): row blockIdx.x of dbias[dbias_rows][N - dbias_c0], channels >= dbias_c0; nullptr = off
   float* dbias;
   int dbias_c0, dbias_rows;
@@ -249,6 +249,12 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
     const int by = row / p.BW, bx = row - by * p.BW;
     const bool row_in_box = row < p.BW * p.BH;
     const bool mask_on = p.mask != nullptr;
+    // fused bias gradient (dgrad flavour, one column tile: N = BN; the host asks for it only then): lane l keeps the running
+    // total of column hw * 32 + l of each 64-column chunk over the rows of its quarter; fixed order, no atomics
+    const bool colsum_on = p.dbias != nullptr;
+    float cacc[BN / 64];
+#pragma unroll
+    for (int i = 0; i < BN / 64; ++i) cacc[i] = 0.0f;
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -284,14 +290,40 @@ __global__ void __launch_bounds__(384, 1) igemm_kernel(const __grid_constant__ I
         uint4 m4[4];
         // the mask row is requested first: its latency overlaps the TMEM load
         if (mrow != nullptr) load_mask(mrow + j * 64, m4);
+        float csum = 0.0f;
         epi_chunk(t_addr + j * 64 + hw * 32, p.bias != nullptr ? sbias + j * 64 + hw * 32 : nullptr, p.relu, mask_on,
-                  mrow != nullptr, m4, ebuf, row, hw);
+                  mrow != nullptr, m4, ebuf, row, hw, nullptr, nullptr, true, colsum_on ? &csum : nullptr, px_valid);
+        if (colsum_on) {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) cacc[i] += (j == i) ? csum : 0.0f;
+        }
         fence_proxy_async_smem();
         named_bar_arrive(2 + (chunk_ctr & 1), 288);
       }
       // all of this thread's TMEM reads of accumulator `acc` are complete
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+    }
+    if (colsum_on) {
+      // one row of partial sums per CTA: the row quarters q = 0..3 add their sums one after the other into the (unused:
+      // no bias in the dgrad flavour) bias slice, then the CTA stores row blockIdx.x of dbias[dbias_rows][N - c0]; rows of
+      // CTAs that do not exist (grid smaller than the row count the host planned for) are zero-filled
+      float* scol = sbias;
+      for (int qq = 0; qq < 4; ++qq) {
+        if (q == qq) {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) {
+            const int col = i * 64 + hw * 32 + lane;
+            scol[col] = (qq == 0 ? 0.0f : scol[col]) + cacc[i];
+          }
+        }
+        named_bar_sync(1, 256);
+      }
+      const int len = BN - p.dbias_c0;
+      for (int ch = p.dbias_c0 + et; ch < BN; ch += 256) {
+        p.dbias[(long long)blockIdx.x * len + ch - p.dbias_c0] = scol[ch];
+        for (int r = gridDim.x + blockIdx.x; r < p.dbias_rows; r += gridDim.x) p.dbias[(long long)r * len + ch - p.dbias_c0] = 0.0f;
+      }
     }
   }
 
