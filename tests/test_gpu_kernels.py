@@ -175,6 +175,13 @@ def test_conv3x3_fwd_fused_pool(ops, case):
     else:                                                                  # the pool kernel wants even, dense input
         ops.pool2x2_fwd(y[:, :2 * hp, :2 * wq].contiguous(), p_ref, i_ref, None, 0)
     assert torch.equal(pooled, p_ref) and torch.equal(idx, i_ref) and torch.equal(cat, cat_ref)
+    # ... and ATen itself on the stored activation: same values, same argmax (first maximum in window order)
+    a_val, a_idx = F.max_pool2d(nchw(y).float(), 2, 2, return_indices=True)
+    assert torch.equal(nchw(pooled).float(), a_val)
+    code = idx.permute(0, 3, 1, 2).long()
+    py = torch.arange(hp, device=DEV).view(1, 1, hp, 1)
+    px = torch.arange(wq, device=DEV).view(1, 1, 1, wq)
+    assert torch.equal((2 * py + (code >> 1)) * wo + 2 * px + (code & 1), a_idx)
     # without the activation store: identical pooled outputs
     assert torch.equal(outs[1][1], pooled) and torch.equal(outs[1][2], idx) and torch.equal(outs[1][3], cat)
 
